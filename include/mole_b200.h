@@ -1,0 +1,303 @@
+/*
+ * mole_b200.h — C ABI of the B200-native walker-ensemble VMC/DMC hot path of Jvanrhijn/mole.
+ *
+ * The reference has no FFI: its boundary is the Rust trait surface re-exported by
+ * `mole::prelude` (src/lib.rs:10-21).  Every entry point below names the reference item it
+ * replaces (paths relative to the reference tree).  A Rust `-sys` crate binds this header
+ * verbatim (see INTEGRATION.md and rust/mole-b200-sys/); the safe wrapper implements the
+ * original traits by delegating to these symbols.
+ *
+ * Conventions
+ *  - every call returns an int32 status (MOLE_OK == 0); nothing unwinds across the boundary;
+ *  - all pointers are caller-owned HOST memory unless the name ends in `_dev`;
+ *  - configurations are row-major (N_e, 3) fp64 exactly like the reference's `Array2<f64>`;
+ *    ensembles are passed as (W, N_e, 3); on the device they are stored structure-of-arrays;
+ *  - one mole_ctx per GPU; calls on one ctx are not re-entrant, different ctxs may be driven
+ *    from different threads (the analogue of the `Send + Sync` bounds, src/vmc/src/vmc.rs:29-32);
+ *  - there is NO CPU fallback: with no usable sm_100 device every device entry point fails with
+ *    MOLE_ERR_CUDA / MOLE_ERR_NO_DEVICE.
+ */
+#ifndef MOLE_B200_H
+#define MOLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes: 1..6 mirror `errors::Error` one to one (src/errors/src/lib.rs:8-15) ---- */
+enum {
+  MOLE_OK = 0,
+  MOLE_ERR_LINALG = 1,                /* Error::LinalgError   (singular SR matrix, optimizers.rs:251) */
+  MOLE_ERR_SHAPE = 2,                 /* Error::ShapeError */
+  MOLE_ERR_FUNC = 3,                  /* Error::FuncError     (e.g. gradient of WaveFunctionMock) */
+  MOLE_ERR_OPERATOR_VALUE_ACCESS = 4, /* Error::OperatorValueAccessError */
+  MOLE_ERR_DATA_ACCESS = 5,           /* Error::DataAccessError (observable missing, util.rs:12-27) */
+  MOLE_ERR_EMPTY_CACHE = 6,           /* Error::EmptyCacheError */
+  MOLE_ERR_CUDA = 100,
+  MOLE_ERR_NCCL = 101,
+  MOLE_ERR_INVALID_ARG = 102,
+  MOLE_ERR_NO_DEVICE = 103,
+  MOLE_ERR_ASSERT = 104               /* reference `assert!` failures (montecarlo.rs:29) */
+};
+
+typedef struct mole_ctx_s* mole_ctx_t;
+typedef struct mole_wf_s* mole_wf_t;
+typedef struct mole_op_s* mole_op_t;
+typedef struct mole_ens_s* mole_ens_t;
+typedef struct mole_metrop_s* mole_metrop_t;
+typedef struct mole_opt_s* mole_opt_t;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int32_t mole_ctx_create(int32_t device, mole_ctx_t* ctx);
+int32_t mole_ctx_destroy(mole_ctx_t ctx);
+int32_t mole_ctx_synchronize(mole_ctx_t ctx);
+const char* mole_last_error_string(mole_ctx_t ctx); /* ctx may be NULL: last global error */
+/* the ctx's CUDA stream (cudaStream_t) so that callers can record their own events on it */
+int32_t mole_ctx_stream(mole_ctx_t ctx, void** stream);
+int32_t mole_version(void);
+
+/* ---- trial wavefunction descriptors -------------------------------------------------------
+ * Replaces user impls of Function<f64,D=Ix2> / Differentiate / WaveFunction / Optimize
+ * (src/wavefunction_traits/src/lib.rs:7-24, src/optimize/src/traits.rs:8-16).  Arbitrary Rust
+ * impls cannot run on the device, so the closed set of kinds used by the reference's
+ * examples/ and tests/ is provided. */
+enum {
+  MOLE_WF_STO_1S = 0,         /* examples/dmc.rs:95-149                    geom: -            P=1 (alpha) */
+  MOLE_WF_GAUSSIAN = 1,       /* examples/dmc.rs:34-92, tests/sho_optimize.rs:52-111          P=1 (a)     */
+  MOLE_WF_STO_PRODUCT = 2,    /* examples/helium_atom_singlet.rs:35-118    geom: -            P=1 (alpha) */
+  MOLE_WF_H2_HL_STO = 3,      /* examples/hydrogen_molecule.rs:65-168      geom: [R]          P=1 (alpha) */
+  MOLE_WF_H2P_PRODUCT = 4,    /* tests/hydrogen_molecular_ion_lcao.rs:51-98 geom: [R], params[0]=alpha, P=0 */
+  MOLE_WF_SLATER_JASTROW = 5, /* SURVEY.md §8(c) config 5 + theory/jastrow.tex; geom: [kappa,n_up,n_dn];
+                                 params: zeta1,zeta2,zeta3,b1,b2,b3,b4 (P=7) */
+  MOLE_WF_CONSTANT = 6        /* src/metropolis/src/metrop.rs:225-255 WaveFunctionMock; geom: [value] */
+};
+#define MOLE_WF_MAX_PARAMS 8
+#define MOLE_WF_MAX_GEOM 8
+#define MOLE_WF_MAX_ELEC 10
+
+typedef struct {
+  int32_t kind;
+  int32_t n_elec;
+  int32_t n_params;
+  int32_t reserved;
+  double params[MOLE_WF_MAX_PARAMS]; /* Optimize::parameters */
+  double geom[MOLE_WF_MAX_GEOM];     /* fixed constants, see the kind list */
+} mole_wf_desc;
+
+int32_t mole_wf_create(mole_ctx_t ctx, const mole_wf_desc* desc, mole_wf_t* wf);
+int32_t mole_wf_destroy(mole_wf_t wf);
+int32_t mole_wf_num_electrons(mole_wf_t wf, int32_t* n);            /* WaveFunction::num_electrons */
+int32_t mole_wf_num_parameters(mole_wf_t wf, int32_t* n);           /* Optimize::num_parameters   */
+int32_t mole_wf_get_parameters(mole_wf_t wf, double* params);       /* Optimize::parameters       */
+int32_t mole_wf_update_parameters(mole_wf_t wf, const double* deltap); /* Optimize::update_parameters */
+int32_t mole_wf_set_parameters(mole_wf_t wf, const double* params);
+/* pointwise entry points, evaluated ON THE DEVICE for one configuration (parity tests):        */
+int32_t mole_wf_value(mole_wf_t wf, const double* cfg, double* out);              /* Function::value          */
+int32_t mole_wf_gradient(mole_wf_t wf, const double* cfg, double* out);           /* Differentiate::gradient  */
+int32_t mole_wf_laplacian(mole_wf_t wf, const double* cfg, double* out);          /* Differentiate::laplacian */
+int32_t mole_wf_parameter_gradient(mole_wf_t wf, const double* cfg, double* out); /* Optimize::parameter_gradient */
+
+/* ---- local operators (src/operator/src/operator.rs) ----------------------------------------- */
+enum {
+  MOLE_OP_KINETIC = 0,    /* KineticEnergy          operator.rs:103-125 */
+  MOLE_OP_IONIC_POT = 1,  /* IonicPotential         operator.rs:16-62   */
+  MOLE_OP_ELEC_POT = 2,   /* ElectronicPotential    operator.rs:68-97   */
+  MOLE_OP_IONIC = 3,      /* IonicHamiltonian       operator.rs:130-149 */
+  MOLE_OP_ELECTRONIC = 4, /* ElectronicHamiltonian  operator.rs:156-184 */
+  MOLE_OP_HARMONIC = 5    /* HarmonicHamiltonian    examples/custom_operator.rs:30-61 */
+};
+#define MOLE_OP_MAX_IONS 8
+typedef struct {
+  int32_t kind;
+  int32_t n_ions;
+  double ion_pos[MOLE_OP_MAX_IONS * 3]; /* (N_n,3) row-major */
+  int32_t ion_charge[MOLE_OP_MAX_IONS]; /* Array1<i32>, operator.rs:19 */
+  double frequency;                     /* HarmonicHamiltonian::frequency */
+} mole_op_desc;
+
+int32_t mole_op_create(mole_ctx_t ctx, const mole_op_desc* desc, mole_op_t* op);
+int32_t mole_op_destroy(mole_op_t op);
+/* LocalOperator::act_on (src/operator/src/traits.rs:263-265): returns H psi, NOT divided by psi */
+int32_t mole_op_act_on(mole_op_t op, mole_wf_t wf, const double* cfg, double* out);
+
+/* ---- walker ensemble -------------------------------------------------------------------------
+ * Structure-of-arrays fp64 ensemble resident in HBM.  Walker w of this ensemble has the global id
+ * walker_offset + w, which (with the sweep counter) keys its Philox stream: results do not depend
+ * on how walkers are sharded over GPUs.  Replaces Sampler::{new,with_initial_configuration}
+ * (src/montecarlo/src/samplers.rs:40-71), the per-worker clones of src/vmc/src/vmc.rs:56 and
+ * DmcRunner::new's walker vector (src/dmc/src/dmc.rs:49-58). */
+int32_t mole_ensemble_create(mole_ctx_t ctx, int64_t n_walkers, int32_t n_elec, const uint8_t seed[32],
+                             uint64_t walker_offset, mole_ens_t* ens);
+int32_t mole_ensemble_destroy(mole_ens_t ens);
+int32_t mole_ensemble_num_walkers(mole_ens_t ens, int64_t* n);
+/* cfg ~ U(lo,hi): samplers.rs:45-46.  broadcast_walker0 != 0 gives every walker the configuration
+ * of global walker 0 (the reference clones ONE sampler, vmc.rs:56). */
+int32_t mole_ensemble_init_uniform(mole_ens_t ens, double lo, double hi, int32_t broadcast_walker0);
+/* cfg ~ N(0,sigma): dmc.rs:49-58 (`vec![x; n]` clones one draw: broadcast_walker0 = 1 is faithful) */
+int32_t mole_ensemble_init_normal(mole_ens_t ens, double sigma, int32_t broadcast_walker0);
+int32_t mole_ensemble_set_configs(mole_ens_t ens, const double* cfgs /* (W,N_e,3) */);
+int32_t mole_ensemble_set_configs_broadcast(mole_ens_t ens, const double* cfg /* (N_e,3) */);
+int32_t mole_ensemble_get_configs(mole_ens_t ens, double* cfgs /* (W,N_e,3) */);
+int32_t mole_ensemble_set_weights(mole_ens_t ens, const double* w);
+int32_t mole_ensemble_get_weights(mole_ens_t ens, double* w);
+/* device-side copy of the current configurations / restore from it (the master sampler whose
+ * configuration every per-iteration clone starts from, vmc.rs:56) */
+int32_t mole_ensemble_snapshot(mole_ens_t ens);
+int32_t mole_ensemble_restore(mole_ens_t ens);
+/* Metropolis::reseed_rng (src/metropolis/src/traits.rs:33): new key, sweep counter back to 0 */
+int32_t mole_ensemble_reseed(mole_ens_t ens, const uint8_t seed[32]);
+int32_t mole_ensemble_set_step(mole_ens_t ens, uint32_t step);
+int32_t mole_ensemble_get_step(mole_ens_t ens, uint32_t* step);
+/* Metropolis::generate_seed (traits.rs:35-37): the n-th 32-byte seed derived from `master` */
+int32_t mole_derive_seed(const uint8_t master[32], uint32_t n, uint8_t out[32]);
+
+/* ---- batched evaluation on identical walker configurations (parity entry point) ---------------
+ * psi[W], grad[W*N_e*3] (un-normalised), lap[W], hpsi[W] (= act_on, un-normalised; needs op),
+ * pgrad[W*P] (un-normalised d psi/d p).  Any output may be NULL. */
+int32_t mole_eval_vgl(mole_ens_t ens, mole_wf_t wf, mole_op_t op, double* psi, double* grad, double* lap,
+                      double* hpsi, double* pgrad);
+
+/* ---- Metropolis samplers (src/metropolis/src/metrop.rs) ---------------------------------------- */
+enum { MOLE_METROP_BOX = 0 /* metrop.rs:22-101 */, MOLE_METROP_DIFFUSE = 1 /* metrop.rs:103-217 */ };
+int32_t mole_metropolis_create(int32_t kind, double param /* box_side | time_step */, mole_metrop_t* m);
+int32_t mole_metropolis_destroy(mole_metrop_t m);
+
+/* ---- fused sweep: Sampler::move_state + Sampler::sample + Runner::run's block loop -------------
+ * (samplers.rs:81-117, montecarlo.rs:24-46) for all walkers, n_sweeps sweeps in ONE launch. */
+enum {
+  MOLE_OBS_ENERGY = 1,  /* "Energy" => op                                                        */
+  MOLE_OBS_PGRAD = 2,   /* "Parameter gradient" => ParameterGradient   src/vmc/src/operators.rs:7-14  */
+  MOLE_OBS_WFVALUE = 4, /* "Wavefunction value" => WavefunctionValue  src/vmc/src/operators.rs:16-24 */
+  MOLE_OBS_KINETIC = 8  /* "Kin. Energy" => KineticEnergy             examples/helium_atom_singlet.rs:162 */
+};
+/* compat flags */
+enum {
+  /* reproduce `Vector / Scalar == scalar / array` (src/operator/src/traits.rs:149-150): the stored
+   * "Parameter gradient" sample becomes 1/(d psi/d p) and O_k = 1/(psi d psi/d p).  Default (0) is
+   * the intended O_k = (d psi/d p)/psi. */
+  MOLE_COMPAT_VECTOR_DIV = 1,
+  /* reproduce optimizers.rs:219-224, which subtracts <O_i><O_j> from EVERY element of S */
+  MOLE_COMPAT_SR_SUBTRACT = 2
+};
+
+typedef struct {
+  int32_t n_sweeps;       /* sweeps in this call                                                    */
+  int32_t n_discard;      /* leading sweeps of this call that are moved but not sampled (block 0)   */
+  int32_t block_size;     /* blocking-analysis block, vmc.rs:150-170 (>=1)                          */
+  uint32_t observables;   /* MOLE_OBS_* mask; accumulators are updated for the enabled ones         */
+  uint32_t compat;        /* MOLE_COMPAT_*                                                          */
+  int32_t reserved;
+  /* optional per-sample traces, HOST pointers, sample-major: trace[s*W + w], s over sampled sweeps */
+  double* energy_trace;   /* E_L                                   (W*n_samples) */
+  double* wfvalue_trace;  /* psi  (the stored "Wavefunction value") (W*n_samples) */
+  double* kinetic_trace;  /* -0.5 lap/psi                           (W*n_samples) */
+  double* pgrad_trace;    /* stored "Parameter gradient", [s][k][w] (W*n_samples*P) */
+  uint8_t* accept_trace;  /* accept bits, [sweep][electron][w]      (W*n_sweeps*N_e) */
+} mole_sweep_args;
+
+int32_t mole_sweep(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, const mole_sweep_args* args);
+
+/* ---- accumulators ------------------------------------------------------------------------------
+ * Device-resident sums that replace the reference's raw sample vectors
+ * (concatenate_worker_data vmc.rs:108-130, process_monte_carlo_results vmc.rs:133-172,
+ * compute_energy_gradient util.rs:6-46, construct_sr_matrix optimizers.rs:191-233). */
+#define MOLE_ACC_MAX_PARAMS 8
+typedef struct {
+  double n_samples;  /* number of E_L samples (all walkers)                          */
+  double sum_e;      /* sum E_L                                                      */
+  double sum_e2;     /* sum E_L^2                                                    */
+  double sum_b;      /* sum of block means (blocks never straddle walkers)           */
+  double sum_b2;     /* sum of squared block means                                   */
+  double n_blocks;   /* number of complete blocks                                    */
+  double n_accept;   /* accepted single-electron moves                               */
+  double n_moves;    /* proposed single-electron moves                               */
+  double sum_t;      /* sum of -0.5 lap/psi                                          */
+  double sum_psi;    /* sum of psi                                                   */
+  double sum_o[MOLE_ACC_MAX_PARAMS];                                  /* sum O_k        */
+  double sum_oe[MOLE_ACC_MAX_PARAMS];                                 /* sum O_k E_L    */
+  double sum_oo[MOLE_ACC_MAX_PARAMS * (MOLE_ACC_MAX_PARAMS + 1) / 2]; /* sum O_k O_l, k<=l packed row-major */
+  int32_t n_params;
+  int32_t reserved;
+} mole_acc_host;
+
+int32_t mole_acc_reset(mole_ens_t ens);
+int32_t mole_acc_get(mole_ens_t ens, mole_acc_host* out);
+/* sum the device accumulators over all ranks of the communicator (NCCL allreduce, fp64 sum) */
+int32_t mole_acc_allreduce(mole_ens_t ens);
+/* device pointer + length (doubles) of the packed accumulator vector, for callers that bring their
+ * own collective (e.g. torch.distributed) */
+int32_t mole_acc_device_ptr(mole_ens_t ens, void** ptr_dev, int32_t* n_doubles);
+/* host finaliser: mean energy, blocking error (vmc.rs:150-170), acceptance, energy gradient
+ * g_k = 2(<O_k E> - <O_k><E>) (util.rs:6-46).  grad may be NULL. */
+int32_t mole_acc_finalize(const mole_acc_host* acc, double* energy, double* error, double* acceptance_per_sweep,
+                          double* grad);
+
+/* ---- NCCL communicator (walkers shard across the GPUs of one box) ------------------------------ */
+#define MOLE_NCCL_UNIQUE_ID_BYTES 128
+int32_t mole_comm_get_unique_id(uint8_t id[MOLE_NCCL_UNIQUE_ID_BYTES]);
+int32_t mole_comm_init(mole_ctx_t ctx, int32_t nranks, int32_t rank, const uint8_t id[MOLE_NCCL_UNIQUE_ID_BYTES]);
+int32_t mole_comm_destroy(mole_ctx_t ctx);
+
+/* ---- optimizers (host side; src/optimize/src/optimizers.rs) ------------------------------------ */
+enum {
+  MOLE_OPT_SD = 0,       /* SteepestDescent            optimizers.rs:9-30    */
+  MOLE_OPT_MOMENTUM = 1, /* MomentumDescent            optimizers.rs:32-60   */
+  MOLE_OPT_NESTEROV = 2, /* NesterovMomentum           optimizers.rs:62-94   */
+  MOLE_OPT_LBFGS = 3,    /* OnlineLbfgs                optimizers.rs:96-179  */
+  MOLE_OPT_SR = 4        /* StochasticReconfiguration  optimizers.rs:181-253 */
+};
+int32_t mole_opt_create(int32_t kind, int32_t n_params, double step_size, double momentum_parameter,
+                        int32_t history, uint32_t compat, mole_opt_t* opt);
+int32_t mole_opt_destroy(mole_opt_t opt);
+/* Optimizer::compute_parameter_update (optimize/src/traits.rs:18-25) from the reduced moments */
+int32_t mole_opt_step(mole_opt_t opt, const double* pars, const mole_acc_host* acc, double* deltap);
+/* the regularised SR matrix the solve uses (P*P row-major), for parity tests */
+int32_t mole_opt_sr_matrix(mole_opt_t opt, const mole_acc_host* acc, double* S);
+
+/* ---- drivers ------------------------------------------------------------------------------------ */
+/* Runner::run (montecarlo.rs:24-46): steps sweeps in blocks of block_size, block 0 discarded.
+ * Accumulators are NOT reset.  Trace pointers as in mole_sweep_args (may be NULL). */
+int32_t mole_runner_run(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, uint32_t observables,
+                        uint32_t compat, int32_t steps, int32_t block_size, double* energy_trace,
+                        double* wfvalue_trace, double* kinetic_trace, double* pgrad_trace, uint8_t* accept_trace);
+
+/* VmcRunner::run_optimization (vmc.rs:43-106).  n_walkers of `ens` plays the role of nworkers:
+ * every walker runs total_samples/nworkers sweeps; flags bit0: restart every iteration from the
+ * ensemble's configurations at entry (reference behaviour, vmc.rs:56); 0 = carry walkers over.
+ * Outputs: energies[iters], errors[iters], acceptance[iters] (nullable), param_history[iters*P]. */
+enum { MOLE_VMC_RESTART_EACH_ITER = 1 };
+int32_t mole_vmc_run_optimization(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, mole_opt_t opt,
+                                  const uint8_t master_seed[32], int32_t iters, int64_t total_samples,
+                                  int32_t block_size, uint32_t compat, uint32_t flags, double* energies,
+                                  double* errors, double* acceptance, double* param_history);
+
+/* ---- DMC (src/dmc/src/dmc.rs, branching.rs) ------------------------------------------------------ */
+enum { MOLE_BRANCH_SR = 0 /* SRBrancher branching.rs:7-40 */, MOLE_BRANCH_SIMPLE = 1 /* SimpleBranching :42-92 */ };
+/* one time step of DmcRunner::diffuse's walker loop (dmc.rs:87-130) for all walkers; returns the
+ * LOCAL (this rank) sums: sum_w_e = sum w_i E_L,i(old), sum_w = sum w_i (pre-update weights). */
+int32_t mole_dmc_step(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step,
+                      double reference_energy, double* sum_w_e, double* sum_w);
+/* BranchingAlgorithm::branch (dmc/src/traits.rs:4-7) on the device (scan + search + gather).
+ * Branching is the last operation of a time step (dmc.rs:139-140): it draws with the current step
+ * counter and then advances it by one. */
+int32_t mole_branch(mole_ens_t ens, int32_t kind);
+/* source walker index of every walker after the last mole_branch (parity tests) */
+int32_t mole_branch_sources(mole_ens_t ens, int32_t* src);
+/* DmcRunner::diffuse (dmc.rs:69-153): returns n_out running energies and errors */
+int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind,
+                         double time_step, double* reference_energy /* in/out */, int32_t num_iterations,
+                         int32_t block_size, int32_t num_eq_blocks, double* energies, double* errors,
+                         int32_t* n_out, double* step_energies /* nullable, num_iterations */);
+
+/* ---- measurement helpers ---------------------------------------------------------------------- */
+/* sustained DFMA throughput of the device (TFLOP/s) measured with a register-resident FMA chain */
+int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops);
+/* number of kernels this library has launched on ctx since creation */
+int32_t mole_ctx_launch_count(mole_ctx_t ctx, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLE_B200_H */

@@ -1,0 +1,654 @@
+// C ABI (include/mole_b200.h): device-touching entry points.  Host-only logic (optimizers,
+// finaliser, drivers) lives in mole_host.cpp.  There is no CPU fallback anywhere in this file:
+// every entry point either launches the sm_100a kernels or returns an error status.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include "mole_internal.h"
+#include "mole_kernels.cuh"
+#include "mole_branch.cuh"
+#include "mole_sj.cuh"
+
+static std::string g_last_error;
+
+int mole_set_error(mole_ctx_s* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return mole_set_error(ctx, e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver         \
+                                     ? MOLE_ERR_NO_DEVICE : MOLE_ERR_CUDA,                              \
+                            std::string(#call) + ": " + cudaGetErrorString(e__));                       \
+  } while (0)
+
+#define STREAM(ctx) ((cudaStream_t)(ctx)->stream)
+#define KERNEL_CHECK(ctx)                 \
+  do {                                    \
+    (ctx)->launches++;                    \
+    CU(ctx, cudaGetLastError());          \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+extern "C" {
+
+int32_t mole_version(void) { return 100; }
+
+const char* mole_last_error_string(mole_ctx_t ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+// ------------------------------------------------------------------ context
+int32_t mole_ctx_create(int32_t device, mole_ctx_t* out) {
+  if (!out) return mole_set_error(nullptr, MOLE_ERR_INVALID_ARG, "ctx out pointer is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return mole_set_error(nullptr, MOLE_ERR_NO_DEVICE,
+                          std::string("no CUDA device: the mole_b200 hot path has no CPU fallback (") +
+                              cudaGetErrorString(e) + ")");
+  if (device < 0 || device >= n) return mole_set_error(nullptr, MOLE_ERR_INVALID_ARG, "bad device index");
+  CU(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return mole_set_error(nullptr, MOLE_ERR_NO_DEVICE,
+                          "device is not sm_100 (B200): this library ships sm_100a code only");
+  mole_ctx_s* c = new mole_ctx_s();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  cudaStream_t s;
+  CU(nullptr, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  c->stream = (void*)s;
+  *out = c;
+  return MOLE_OK;
+}
+
+int32_t mole_ctx_destroy(mole_ctx_t ctx) {
+  if (!ctx) return MOLE_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(STREAM(ctx));
+  delete ctx;
+  return MOLE_OK;
+}
+
+int32_t mole_ctx_synchronize(mole_ctx_t ctx) {
+  if (!ctx) return MOLE_ERR_INVALID_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+  return MOLE_OK;
+}
+
+int32_t mole_ctx_stream(mole_ctx_t ctx, void** stream) {
+  if (!ctx || !stream) return MOLE_ERR_INVALID_ARG;
+  *stream = ctx->stream;
+  return MOLE_OK;
+}
+
+int32_t mole_ctx_launch_count(mole_ctx_t ctx, int64_t* n) {
+  if (!ctx || !n) return MOLE_ERR_INVALID_ARG;
+  *n = ctx->launches;
+  return MOLE_OK;
+}
+
+// ------------------------------------------------------------------ wavefunction descriptors
+static int wf_kind_ne(const mole_wf_desc* d) {
+  switch (d->kind) {
+    case MOLE_WF_STO_1S: case MOLE_WF_GAUSSIAN: case MOLE_WF_H2P_PRODUCT: case MOLE_WF_CONSTANT: return 1;
+    case MOLE_WF_STO_PRODUCT: case MOLE_WF_H2_HL_STO: return 2;
+    case MOLE_WF_SLATER_JASTROW: return (int)d->geom[1] + (int)d->geom[2];
+  }
+  return -1;
+}
+static int wf_kind_np(int kind) {
+  switch (kind) {
+    case MOLE_WF_STO_1S: case MOLE_WF_GAUSSIAN: case MOLE_WF_STO_PRODUCT: case MOLE_WF_H2_HL_STO: return 1;
+    case MOLE_WF_H2P_PRODUCT: case MOLE_WF_CONSTANT: return 0;
+    case MOLE_WF_SLATER_JASTROW: return 7;
+  }
+  return -1;
+}
+
+int32_t mole_wf_create(mole_ctx_t ctx, const mole_wf_desc* d, mole_wf_t* out) {
+  if (!ctx || !d || !out) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "mole_wf_create: NULL argument");
+  const int ne = wf_kind_ne(d), np = wf_kind_np(d->kind);
+  if (ne < 0) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
+  if (d->n_elec != ne) return mole_set_error(ctx, MOLE_ERR_SHAPE, "n_elec does not match the wavefunction kind");
+  if (d->n_params != np) return mole_set_error(ctx, MOLE_ERR_SHAPE, "n_params does not match the wavefunction kind");
+  if (d->kind == MOLE_WF_SLATER_JASTROW) {
+    const int nu = (int)d->geom[1], nd = (int)d->geom[2];
+    if (nu < 0 || nd < 0 || nu > 5 || nd > 5 || nu + nd < 1 || !(d->geom[0] > 0.0))
+      return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "Slater-Jastrow needs kappa>0 and 0<=n_up,n_dn<=5");
+  }
+  mole_wf_s* w = new mole_wf_s();
+  w->ctx = ctx;
+  w->p.kind = d->kind; w->p.ne = ne; w->p.np = np; w->p.pad = 0;
+  for (int i = 0; i < MOLE_WF_MAX_PARAMS; ++i) w->p.p[i] = d->params[i];
+  for (int i = 0; i < MOLE_WF_MAX_GEOM; ++i) w->p.geom[i] = d->geom[i];
+  *out = w;
+  return MOLE_OK;
+}
+int32_t mole_wf_destroy(mole_wf_t wf) { delete wf; return MOLE_OK; }
+int32_t mole_wf_num_electrons(mole_wf_t wf, int32_t* n) { if (!wf || !n) return MOLE_ERR_INVALID_ARG; *n = wf->p.ne; return MOLE_OK; }
+int32_t mole_wf_num_parameters(mole_wf_t wf, int32_t* n) { if (!wf || !n) return MOLE_ERR_INVALID_ARG; *n = wf->p.np; return MOLE_OK; }
+int32_t mole_wf_get_parameters(mole_wf_t wf, double* p) {
+  if (!wf || !p) return MOLE_ERR_INVALID_ARG;
+  // H2P carries alpha in params[0] although it exposes no Optimize impl
+  for (int i = 0; i < wf->p.np; ++i) p[i] = wf->p.p[i];
+  return MOLE_OK;
+}
+int32_t mole_wf_update_parameters(mole_wf_t wf, const double* dp) {
+  if (!wf || !dp) return MOLE_ERR_INVALID_ARG;
+  for (int i = 0; i < wf->p.np; ++i) wf->p.p[i] += dp[i];
+  return MOLE_OK;
+}
+int32_t mole_wf_set_parameters(mole_wf_t wf, const double* p) {
+  if (!wf || !p) return MOLE_ERR_INVALID_ARG;
+  for (int i = 0; i < wf->p.np; ++i) wf->p.p[i] = p[i];
+  return MOLE_OK;
+}
+
+// ------------------------------------------------------------------ operators
+int32_t mole_op_create(mole_ctx_t ctx, const mole_op_desc* d, mole_op_t* out) {
+  if (!ctx || !d || !out) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "mole_op_create: NULL argument");
+  if (d->kind < MOLE_OP_KINETIC || d->kind > MOLE_OP_HARMONIC) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown operator kind");
+  if (d->n_ions < 0 || d->n_ions > MOLE_OP_MAX_IONS) return mole_set_error(ctx, MOLE_ERR_SHAPE, "too many ions");
+  mole_op_s* o = new mole_op_s();
+  o->ctx = ctx;
+  o->p.kind = d->kind; o->p.n_ions = d->n_ions; o->p.frequency = d->frequency;
+  for (int i = 0; i < MOLE_OP_MAX_IONS * 3; ++i) o->p.ion_pos[i] = d->ion_pos[i];
+  for (int i = 0; i < MOLE_OP_MAX_IONS; ++i) o->p.ion_z[i] = (double)d->ion_charge[i];
+  double pot = 0.0;  // IonicPotential::new, operator.rs:40-55
+  for (int i = 0; i < d->n_ions; ++i)
+    for (int j = i + 1; j < d->n_ions; ++j) {
+      double s2 = 0.0;
+      for (int k = 0; k < 3; ++k) { const double t = d->ion_pos[3 * j + k] - d->ion_pos[3 * i + k]; s2 += t * t; }
+      pot += (double)(d->ion_charge[i] * d->ion_charge[j]) / std::sqrt(s2);
+    }
+  o->p.ionic_repulsion = pot;
+  *out = o;
+  return MOLE_OK;
+}
+int32_t mole_op_destroy(mole_op_t op) { delete op; return MOLE_OK; }
+
+// ------------------------------------------------------------------ ensemble
+static int ens_grid_rows(mole_ctx_s* ctx) { return ctx->sm_count * 16; }
+
+int32_t mole_ensemble_create(mole_ctx_t ctx, int64_t W, int32_t ne, const uint8_t seed[32], uint64_t walker_offset,
+                             mole_ens_t* out) {
+  if (!ctx || !out || !seed) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "mole_ensemble_create: NULL argument");
+  if (W < 1 || W > (int64_t)1 << 30 || ne < 1 || ne > MOLE_WF_MAX_ELEC)
+    return mole_set_error(ctx, MOLE_ERR_SHAPE, "ensemble shape out of range");
+  CU(ctx, cudaSetDevice(ctx->device));
+  mole_ens_s* e = new mole_ens_s();
+  e->ctx = ctx; e->W = W; e->ne = ne; e->walker_offset = walker_offset;
+  e->key = mole_key_from_seed(seed); e->step = 0;
+  const size_t nx = (size_t)3 * ne * W;
+  CU(ctx, cudaMalloc(&e->x, nx * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->x2, nx * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->w, W * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->w2, W * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->el, W * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->el2, W * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->blk, W * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->acc, ACC_LEN * sizeof(double)));
+  e->partial_rows = ens_grid_rows(ctx);
+  CU(ctx, cudaMalloc(&e->partials, (size_t)e->partial_rows * ACC_LEN * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->ticket, sizeof(unsigned int)));
+  CU(ctx, cudaMalloc(&e->red, 8 * sizeof(double)));
+  e->n_scan_blocks = cdiv(W, SCAN_TILE);
+  CU(ctx, cudaMalloc(&e->cum, (size_t)W * sizeof(unsigned long long)));
+  CU(ctx, cudaMalloc(&e->blocksums, (size_t)(e->n_scan_blocks + 1) * sizeof(unsigned long long)));
+  CU(ctx, cudaMalloc(&e->src, (size_t)W * sizeof(int32_t)));
+  CU(ctx, cudaMemsetAsync(e->x, 0, nx * sizeof(double), STREAM(ctx)));
+  CU(ctx, cudaMemsetAsync(e->blk, 0, W * sizeof(double), STREAM(ctx)));
+  CU(ctx, cudaMemsetAsync(e->acc, 0, ACC_LEN * sizeof(double), STREAM(ctx)));
+  CU(ctx, cudaMemsetAsync(e->ticket, 0, sizeof(unsigned int), STREAM(ctx)));
+  fill_kernel<<<cdiv(W, 256), 256, 0, STREAM(ctx)>>>(e->w, W, 1.0);   // dmc.rs:51 initial weight 1.0
+  KERNEL_CHECK(ctx);
+  *out = e;
+  return MOLE_OK;
+}
+
+int32_t mole_ensemble_destroy(mole_ens_t e) {
+  if (!e) return MOLE_OK;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(STREAM(e->ctx));
+  cudaFree(e->x0);
+  cudaFree(e->x); cudaFree(e->x2); cudaFree(e->w); cudaFree(e->w2); cudaFree(e->el); cudaFree(e->el2);
+  cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
+  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src);
+  delete e;
+  return MOLE_OK;
+}
+
+int32_t mole_ensemble_num_walkers(mole_ens_t e, int64_t* n) { if (!e || !n) return MOLE_ERR_INVALID_ARG; *n = e->W; return MOLE_OK; }
+
+static int32_t ens_init(mole_ens_t e, int normal, double a, double b, int broadcast) {
+  if (!e) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  init_kernel<<<cdiv(e->W, 256), 256, 0, STREAM(ctx)>>>(e->x, e->W, e->ne, e->walker_offset, e->key, normal, a, b, broadcast);
+  KERNEL_CHECK(ctx);
+  e->el_cached = 0;
+  return MOLE_OK;
+}
+int32_t mole_ensemble_init_uniform(mole_ens_t e, double lo, double hi, int32_t bc) { return ens_init(e, 0, lo, hi, bc); }
+int32_t mole_ensemble_init_normal(mole_ens_t e, double sigma, int32_t bc) { return ens_init(e, 1, sigma, 0.0, bc); }
+
+static int32_t ens_set(mole_ens_t e, const double* host, int broadcast) {
+  if (!e || !host) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int n = 3 * e->ne;
+  const size_t cnt = broadcast ? (size_t)n : (size_t)n * e->W;
+  // stage through x2 (AoS), transpose into x (SoA)
+  CU(ctx, cudaMemcpyAsync(e->x2, host, cnt * sizeof(double), cudaMemcpyHostToDevice, STREAM(ctx)));
+  aos_to_soa_kernel<<<cdiv((int64_t)n * e->W, 256), 256, 0, STREAM(ctx)>>>(e->x2, e->x, e->W, n, broadcast);
+  KERNEL_CHECK(ctx);
+  CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+  e->el_cached = 0;
+  return MOLE_OK;
+}
+int32_t mole_ensemble_set_configs(mole_ens_t e, const double* cfgs) { return ens_set(e, cfgs, 0); }
+int32_t mole_ensemble_set_configs_broadcast(mole_ens_t e, const double* cfg) { return ens_set(e, cfg, 1); }
+
+int32_t mole_ensemble_get_configs(mole_ens_t e, double* cfgs) {
+  if (!e || !cfgs) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int n = 3 * e->ne;
+  soa_to_aos_kernel<<<cdiv((int64_t)n * e->W, 256), 256, 0, STREAM(ctx)>>>(e->x, e->x2, e->W, n);
+  KERNEL_CHECK(ctx);
+  CU(ctx, cudaMemcpyAsync(cfgs, e->x2, (size_t)n * e->W * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+  return MOLE_OK;
+}
+int32_t mole_ensemble_set_weights(mole_ens_t e, const double* w) {
+  if (!e || !w) return MOLE_ERR_INVALID_ARG;
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  CU(e->ctx, cudaMemcpyAsync(e->w, w, e->W * sizeof(double), cudaMemcpyHostToDevice, STREAM(e->ctx)));
+  CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
+  return MOLE_OK;
+}
+int32_t mole_ensemble_get_weights(mole_ens_t e, double* w) {
+  if (!e || !w) return MOLE_ERR_INVALID_ARG;
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  CU(e->ctx, cudaMemcpyAsync(w, e->w, e->W * sizeof(double), cudaMemcpyDeviceToHost, STREAM(e->ctx)));
+  CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
+  return MOLE_OK;
+}
+int32_t mole_ensemble_snapshot(mole_ens_t e) {
+  if (!e) return MOLE_ERR_INVALID_ARG;
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  const size_t bytes = (size_t)3 * e->ne * e->W * sizeof(double);
+  if (!e->x0) CU(e->ctx, cudaMalloc(&e->x0, bytes));
+  CU(e->ctx, cudaMemcpyAsync(e->x0, e->x, bytes, cudaMemcpyDeviceToDevice, STREAM(e->ctx)));
+  return MOLE_OK;
+}
+int32_t mole_ensemble_restore(mole_ens_t e) {
+  if (!e) return MOLE_ERR_INVALID_ARG;
+  if (!e->x0) return mole_set_error(e->ctx, MOLE_ERR_EMPTY_CACHE, "mole_ensemble_restore without a snapshot");
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  const size_t bytes = (size_t)3 * e->ne * e->W * sizeof(double);
+  CU(e->ctx, cudaMemcpyAsync(e->x, e->x0, bytes, cudaMemcpyDeviceToDevice, STREAM(e->ctx)));
+  e->el_cached = 0;
+  return MOLE_OK;
+}
+int32_t mole_ensemble_reseed(mole_ens_t e, const uint8_t seed[32]) {
+  if (!e || !seed) return MOLE_ERR_INVALID_ARG;
+  e->key = mole_key_from_seed(seed);
+  e->step = 0;
+  return MOLE_OK;
+}
+int32_t mole_ensemble_set_step(mole_ens_t e, uint32_t s) { if (!e) return MOLE_ERR_INVALID_ARG; e->step = s; return MOLE_OK; }
+int32_t mole_ensemble_get_step(mole_ens_t e, uint32_t* s) { if (!e || !s) return MOLE_ERR_INVALID_ARG; *s = e->step; return MOLE_OK; }
+
+// ------------------------------------------------------------------ batched evaluation
+static int32_t eval_device(mole_ctx_s* ctx, const WfParams& wp, const HamParams* hp, const double* x_dev, int64_t W,
+                           double* psi, double* grad, double* lap, double* hpsi, double* pgrad) {
+  // outputs are HOST pointers; stage through temporaries
+  const int n = 3 * wp.ne, np = wp.np;
+  double *d_psi = nullptr, *d_grad = nullptr, *d_lap = nullptr, *d_h = nullptr, *d_pg = nullptr;
+  if (psi) CU(ctx, cudaMalloc(&d_psi, W * sizeof(double)));
+  if (grad) CU(ctx, cudaMalloc(&d_grad, (size_t)W * n * sizeof(double)));
+  if (lap) CU(ctx, cudaMalloc(&d_lap, W * sizeof(double)));
+  if (hpsi && hp) CU(ctx, cudaMalloc(&d_h, W * sizeof(double)));
+  if (pgrad && np > 0) CU(ctx, cudaMalloc(&d_pg, (size_t)W * np * sizeof(double)));
+  HamParams h0;
+  memset(&h0, 0, sizeof(h0));
+  const HamParams& h = hp ? *hp : h0;
+  const int blocks = cdiv(W, 128);
+  switch (wp.kind) {
+#define EV(K) case K: eval_kernel<K><<<blocks, 128, 0, STREAM(ctx)>>>(x_dev, W, wp, h, hp != nullptr, d_psi, d_grad, d_lap, d_h, d_pg); break;
+    EV(K_STO_1S) EV(K_GAUSSIAN) EV(K_STO_PRODUCT) EV(K_H2_HL_STO) EV(K_H2P_PRODUCT) EV(K_CONSTANT)
+#undef EV
+    case K_SLATER_JASTROW:
+      sj_eval_launch(STREAM(ctx), x_dev, W, wp, h, hp != nullptr, d_psi, d_grad, d_lap, d_h, d_pg);
+      break;
+    default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
+  }
+  KERNEL_CHECK(ctx);
+  if (psi) CU(ctx, cudaMemcpyAsync(psi, d_psi, W * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  if (grad) CU(ctx, cudaMemcpyAsync(grad, d_grad, (size_t)W * n * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  if (lap) CU(ctx, cudaMemcpyAsync(lap, d_lap, W * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  if (d_h) CU(ctx, cudaMemcpyAsync(hpsi, d_h, W * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  if (d_pg) CU(ctx, cudaMemcpyAsync(pgrad, d_pg, (size_t)W * np * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+  cudaFree(d_psi); cudaFree(d_grad); cudaFree(d_lap); cudaFree(d_h); cudaFree(d_pg);
+  return MOLE_OK;
+}
+
+int32_t mole_eval_vgl(mole_ens_t e, mole_wf_t wf, mole_op_t op, double* psi, double* grad, double* lap, double* hpsi,
+                      double* pgrad) {
+  if (!e || !wf) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  if (wf->p.ne != e->ne) return mole_set_error(ctx, MOLE_ERR_SHAPE, "wavefunction / ensemble electron count mismatch");
+  if (grad && wf->p.kind == MOLE_WF_CONSTANT) return mole_set_error(ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
+  CU(ctx, cudaSetDevice(ctx->device));
+  return eval_device(ctx, wf->p, op ? &op->p : nullptr, e->x, e->W, psi, grad, lap, hpsi, pgrad);
+}
+
+// single-configuration trait calls (Function::value etc.), evaluated on the device
+static int32_t eval_one(mole_wf_t wf, mole_op_t op, const double* cfg, double* psi, double* grad, double* lap, double* hpsi,
+                        double* pgrad) {
+  if (!wf || !cfg) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = wf->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int n = 3 * wf->p.ne;
+  double* d_x = nullptr;
+  CU(ctx, cudaMalloc(&d_x, n * sizeof(double)));
+  CU(ctx, cudaMemcpyAsync(d_x, cfg, n * sizeof(double), cudaMemcpyHostToDevice, STREAM(ctx)));  // W=1: AoS == SoA
+  const int32_t rc = eval_device(ctx, wf->p, op ? &op->p : nullptr, d_x, 1, psi, grad, lap, hpsi, pgrad);
+  cudaFree(d_x);
+  return rc;
+}
+int32_t mole_wf_value(mole_wf_t wf, const double* cfg, double* out) { return eval_one(wf, nullptr, cfg, out, nullptr, nullptr, nullptr, nullptr); }
+int32_t mole_wf_gradient(mole_wf_t wf, const double* cfg, double* out) {
+  if (wf && wf->p.kind == MOLE_WF_CONSTANT) return mole_set_error(wf->ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
+  return eval_one(wf, nullptr, cfg, nullptr, out, nullptr, nullptr, nullptr);
+}
+int32_t mole_wf_laplacian(mole_wf_t wf, const double* cfg, double* out) { return eval_one(wf, nullptr, cfg, nullptr, nullptr, out, nullptr, nullptr); }
+int32_t mole_wf_parameter_gradient(mole_wf_t wf, const double* cfg, double* out) {
+  if (wf && wf->p.np == 0) return mole_set_error(wf->ctx, MOLE_ERR_FUNC, "this wavefunction kind has no Optimize impl");
+  return eval_one(wf, nullptr, cfg, nullptr, nullptr, nullptr, nullptr, out);
+}
+int32_t mole_op_act_on(mole_op_t op, mole_wf_t wf, const double* cfg, double* out) {
+  if (!op) return MOLE_ERR_INVALID_ARG;
+  return eval_one(wf, op, cfg, nullptr, nullptr, nullptr, out, nullptr);
+}
+
+// ------------------------------------------------------------------ Metropolis objects
+int32_t mole_metropolis_create(int32_t kind, double param, mole_metrop_t* out) {
+  if (!out || (kind != MOLE_METROP_BOX && kind != MOLE_METROP_DIFFUSE) || !(param > 0.0))
+    return mole_set_error(nullptr, MOLE_ERR_INVALID_ARG, "mole_metropolis_create: bad kind or parameter");
+  *out = new mole_metrop_s{kind, param};
+  return MOLE_OK;
+}
+int32_t mole_metropolis_destroy(mole_metrop_t m) { delete m; return MOLE_OK; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ fused sweep
+template <int KIND>
+static void launch_sweep_kind(cudaStream_t st, int blocks, const SweepParams& sp, int metrop, bool opt) {
+  if (metrop == MOLE_METROP_BOX) {
+    if (opt) sweep_kernel<KIND, MOLE_METROP_BOX, true><<<blocks, SWEEP_THREADS, 0, st>>>(sp);
+    else sweep_kernel<KIND, MOLE_METROP_BOX, false><<<blocks, SWEEP_THREADS, 0, st>>>(sp);
+  } else {
+    if (opt) sweep_kernel<KIND, MOLE_METROP_DIFFUSE, true><<<blocks, SWEEP_THREADS, 0, st>>>(sp);
+    else sweep_kernel<KIND, MOLE_METROP_DIFFUSE, false><<<blocks, SWEEP_THREADS, 0, st>>>(sp);
+  }
+}
+
+extern "C" {
+
+int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, const mole_sweep_args* a) {
+  if (!e || !wf || !m || !a) return mole_set_error(e ? e->ctx : nullptr, MOLE_ERR_INVALID_ARG, "mole_sweep: NULL argument");
+  mole_ctx_s* ctx = e->ctx;
+  if (wf->p.ne != e->ne) return mole_set_error(ctx, MOLE_ERR_SHAPE, "wavefunction / ensemble electron count mismatch");
+  if (a->n_sweeps < 0 || a->n_discard < 0 || a->n_discard > a->n_sweeps || a->block_size < 1)
+    return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "mole_sweep: bad sweep schedule");
+  if ((a->observables & (MOLE_OBS_ENERGY | MOLE_OBS_KINETIC)) && !op)
+    return mole_set_error(ctx, MOLE_ERR_DATA_ACCESS, "observable needs an operator");
+  const bool opt = (a->observables & MOLE_OBS_PGRAD) != 0;
+  if (opt && wf->p.np == 0) return mole_set_error(ctx, MOLE_ERR_FUNC, "\"Parameter gradient\" needs a wavefunction with an Optimize impl");
+  if (opt && !(a->observables & MOLE_OBS_ENERGY))
+    return mole_set_error(ctx, MOLE_ERR_DATA_ACCESS, "\"Parameter gradient\" moments need the \"Energy\" observable (util.rs:24-27)");
+  if (wf->p.kind == MOLE_WF_CONSTANT && m->kind == MOLE_METROP_DIFFUSE)
+    return mole_set_error(ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
+  if (a->n_sweeps == 0) return MOLE_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+
+  const int64_t W = e->W;
+  const int ne = e->ne, np = wf->p.np;
+  const int64_t nsamp = a->n_sweeps - a->n_discard;
+  if (e->blk_size != a->block_size) {   // a new blocking analysis starts
+    CU(ctx, cudaMemsetAsync(e->blk, 0, W * sizeof(double), STREAM(ctx)));
+    e->blk_size = a->block_size;
+    e->blk_fill = 0;
+  }
+
+  SweepParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.x = e->x; sp.blk = e->blk; sp.acc = e->acc; sp.partials = e->partials; sp.ticket = e->ticket;
+  sp.W = W; sp.walker_offset = e->walker_offset; sp.key = e->key; sp.step0 = e->step;
+  sp.n_sweeps = a->n_sweeps; sp.n_discard = a->n_discard; sp.block_size = a->block_size; sp.blk_fill = e->blk_fill;
+  sp.observables = a->observables; sp.compat = a->compat; sp.metrop_param = m->param;
+  sp.wf = wf->p;
+  if (op) sp.ham = op->p;
+
+  // device staging for the optional traces
+  if (a->energy_trace && nsamp > 0) CU(ctx, cudaMalloc(&sp.tr_energy, (size_t)W * nsamp * sizeof(double)));
+  if (a->wfvalue_trace && nsamp > 0) CU(ctx, cudaMalloc(&sp.tr_wfvalue, (size_t)W * nsamp * sizeof(double)));
+  if (a->kinetic_trace && nsamp > 0) CU(ctx, cudaMalloc(&sp.tr_kinetic, (size_t)W * nsamp * sizeof(double)));
+  if (a->pgrad_trace && nsamp > 0 && opt) CU(ctx, cudaMalloc(&sp.tr_pgrad, (size_t)W * nsamp * np * sizeof(double)));
+  if (a->accept_trace) CU(ctx, cudaMalloc(&sp.tr_accept, (size_t)W * a->n_sweeps * ne));
+
+  if (wf->p.kind == K_SLATER_JASTROW) {
+    const int32_t rc = sj_sweep_launch(ctx, e, sp, m->kind, opt);
+    if (rc != MOLE_OK) return rc;
+  } else {
+    const int blocks = std::min(cdiv(W, SWEEP_THREADS), e->partial_rows);
+    switch (wf->p.kind) {
+#define SW(K) case K: launch_sweep_kind<K>(STREAM(ctx), blocks, sp, m->kind, opt); break;
+      SW(K_STO_1S) SW(K_GAUSSIAN) SW(K_STO_PRODUCT) SW(K_H2_HL_STO) SW(K_H2P_PRODUCT) SW(K_CONSTANT)
+#undef SW
+      default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
+    }
+  }
+  KERNEL_CHECK(ctx);
+  e->step += (uint32_t)a->n_sweeps;
+  if (a->observables & MOLE_OBS_ENERGY) e->blk_fill = (int32_t)((e->blk_fill + nsamp) % a->block_size);
+  if (opt) e->np_last = np;
+  e->el_cached = 0;
+
+  const bool any_trace = sp.tr_energy || sp.tr_wfvalue || sp.tr_kinetic || sp.tr_pgrad || sp.tr_accept;
+  if (any_trace) {
+    if (sp.tr_energy) CU(ctx, cudaMemcpyAsync(a->energy_trace, sp.tr_energy, (size_t)W * nsamp * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+    if (sp.tr_wfvalue) CU(ctx, cudaMemcpyAsync(a->wfvalue_trace, sp.tr_wfvalue, (size_t)W * nsamp * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+    if (sp.tr_kinetic) CU(ctx, cudaMemcpyAsync(a->kinetic_trace, sp.tr_kinetic, (size_t)W * nsamp * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+    if (sp.tr_pgrad) CU(ctx, cudaMemcpyAsync(a->pgrad_trace, sp.tr_pgrad, (size_t)W * nsamp * np * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+    if (sp.tr_accept) CU(ctx, cudaMemcpyAsync(a->accept_trace, sp.tr_accept, (size_t)W * a->n_sweeps * ne, cudaMemcpyDeviceToHost, STREAM(ctx)));
+    CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+    cudaFree(sp.tr_energy); cudaFree(sp.tr_wfvalue); cudaFree(sp.tr_kinetic); cudaFree(sp.tr_pgrad); cudaFree(sp.tr_accept);
+  }
+  return MOLE_OK;
+}
+
+// ------------------------------------------------------------------ accumulators
+int32_t mole_acc_reset(mole_ens_t e) {
+  if (!e) return MOLE_ERR_INVALID_ARG;
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  CU(e->ctx, cudaMemsetAsync(e->acc, 0, ACC_LEN * sizeof(double), STREAM(e->ctx)));
+  CU(e->ctx, cudaMemsetAsync(e->blk, 0, e->W * sizeof(double), STREAM(e->ctx)));
+  e->blk_fill = 0;
+  return MOLE_OK;
+}
+
+int32_t mole_acc_get(mole_ens_t e, mole_acc_host* out) {
+  if (!e || !out) return MOLE_ERR_INVALID_ARG;
+  static_assert(sizeof(mole_acc_host) == ACC_LEN * sizeof(double) + 2 * sizeof(int32_t), "acc layout");
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  CU(e->ctx, cudaMemcpyAsync(out, e->acc, ACC_LEN * sizeof(double), cudaMemcpyDeviceToHost, STREAM(e->ctx)));
+  CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
+  out->n_params = e->np_last;
+  out->reserved = 0;
+  return MOLE_OK;
+}
+
+int32_t mole_acc_device_ptr(mole_ens_t e, void** p, int32_t* n) {
+  if (!e || !p || !n) return MOLE_ERR_INVALID_ARG;
+  *p = e->acc;
+  *n = ACC_LEN;
+  return MOLE_OK;
+}
+
+// ------------------------------------------------------------------ DMC
+int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref,
+                      double* sum_w_e, double* sum_w) {
+  if (!e || !wf || !m || !op) return mole_set_error(e ? e->ctx : nullptr, MOLE_ERR_INVALID_ARG, "mole_dmc_step: NULL argument");
+  mole_ctx_s* ctx = e->ctx;
+  if (m->kind != MOLE_METROP_DIFFUSE) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "DmcRunner takes a MetropolisDiffuse (dmc.rs:28)");
+  if (wf->p.ne != e->ne) return mole_set_error(ctx, MOLE_ERR_SHAPE, "wavefunction / ensemble electron count mismatch");
+  if (wf->p.kind == MOLE_WF_CONSTANT) return mole_set_error(ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
+  CU(ctx, cudaSetDevice(ctx->device));
+  DmcParams dp;
+  memset(&dp, 0, sizeof(dp));
+  dp.x = e->x; dp.w = e->w; dp.el = e->el; dp.red = e->red; dp.partials = e->partials; dp.ticket = e->ticket;
+  dp.W = e->W; dp.walker_offset = e->walker_offset; dp.key = e->key; dp.step = e->step;
+  dp.tau_move = m->param; dp.tau_weight = time_step; dp.e_ref = e_ref; dp.el_cached = e->el_cached;
+  dp.wf = wf->p; dp.ham = op->p;
+  if (wf->p.kind == K_SLATER_JASTROW) {
+    const int32_t rc = sj_dmc_launch(ctx, e, dp);
+    if (rc != MOLE_OK) return rc;
+  } else {
+    const int blocks = std::min(cdiv(e->W, SWEEP_THREADS), e->partial_rows);
+    switch (wf->p.kind) {
+#define DM(K) case K: dmc_step_kernel<K><<<blocks, SWEEP_THREADS, 0, STREAM(ctx)>>>(dp); break;
+      DM(K_STO_1S) DM(K_GAUSSIAN) DM(K_STO_PRODUCT) DM(K_H2_HL_STO) DM(K_H2P_PRODUCT)
+#undef DM
+      default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
+    }
+  }
+  KERNEL_CHECK(ctx);
+  e->el_cached = 1;
+  double red[4];
+  CU(ctx, cudaMemcpyAsync(red, e->red, 4 * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+  if (sum_w_e) *sum_w_e = red[0];
+  if (sum_w) *sum_w = red[1];
+  return MOLE_OK;
+}
+
+
+int32_t mole_branch(mole_ens_t e, int32_t kind) {
+  if (!e) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  if (kind != MOLE_BRANCH_SR && kind != MOLE_BRANCH_SIMPLE) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown brancher");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t W = e->W;
+  const int n = 3 * e->ne;
+  const int tiles = e->n_scan_blocks;
+  cudaStream_t st = STREAM(ctx);
+  if (!e->el_cached) CU(ctx, cudaMemsetAsync(e->el, 0, W * sizeof(double), st));
+  if (kind == MOLE_BRANCH_SR) {
+    // post-update sum and max of the weights come from the last mole_dmc_step reduction (red[2], red[3]);
+    // when the weights were set by hand they are recomputed here.
+    double red[4];
+    if (e->el_cached) {
+      CU(ctx, cudaMemcpyAsync(red, e->red, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CU(ctx, cudaStreamSynchronize(st));
+    } else {
+      std::vector<double> hw(W);
+      CU(ctx, cudaMemcpyAsync(hw.data(), e->w, W * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CU(ctx, cudaStreamSynchronize(st));
+      red[2] = 0.0; red[3] = 0.0;
+      for (int64_t i = 0; i < W; ++i) { red[2] = red[2] + hw[i]; red[3] = std::max(red[3], hw[i]); }
+    }
+    double local_sum = red[2], gmax = red[3], gcount = (double)W;
+    {
+      double sums[1] = {gcount}, maxs[1] = {gmax};
+      const int32_t rc = mole_comm_allreduce_host(ctx, sums, 1, maxs, 1);
+      if (rc != MOLE_OK) return rc;
+      gcount = sums[0]; gmax = maxs[0];
+    }
+    const double norm_factor = gcount / gmax;                 // branching.rs:24 (global N, global w_max)
+    const double new_weight = local_sum / (double)W;          // branching.rs:21 (stratified per rank)
+    sr_weights_scan_kernel<<<tiles, SCAN_THREADS, 0, st>>>(e->w, W, norm_factor, e->cum, e->blocksums);
+    KERNEL_CHECK(ctx);
+    scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(e->blocksums, tiles);
+    KERNEL_CHECK(ctx);
+    add_tile_offsets_kernel<<<cdiv(W, 256), 256, 0, st>>>(e->cum, W, e->blocksums);
+    KERNEL_CHECK(ctx);
+    sr_pick_gather_kernel<<<cdiv(W, 128), 128, 0, st>>>(e->cum, e->blocksums, tiles, W, n, e->walker_offset, e->key, e->step,
+                                                        e->x, e->x2, e->el, e->el2, e->w2, new_weight, e->src);
+    KERNEL_CHECK(ctx);
+  } else {
+    int32_t* list = nullptr; int32_t* fen = nullptr; uint32_t* mask = nullptr;
+    const int64_t cap = 3 * W;
+    CU(ctx, cudaMalloc(&list, cap * sizeof(int32_t)));
+    CU(ctx, cudaMalloc(&mask, (cap / 32 + 2) * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc(&fen, (cap / 32 + 3) * sizeof(int32_t)));
+    simple_copies_scan_kernel<<<tiles, SCAN_THREADS, 0, st>>>(e->w, W, e->walker_offset, e->key, e->step, e->cum, e->blocksums);
+    KERNEL_CHECK(ctx);
+    scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(e->blocksums, tiles);
+    KERNEL_CHECK(ctx);
+    add_tile_offsets_kernel<<<cdiv(W, 256), 256, 0, st>>>(e->cum, W, e->blocksums);
+    KERNEL_CHECK(ctx);
+    simple_build_list_kernel<<<cdiv(W, 256), 256, 0, st>>>(e->cum, e->blocksums, tiles, W, e->walker_offset, e->key, e->step, list);
+    KERNEL_CHECK(ctx);
+    simple_remove_kernel<<<1, 1024, 0, st>>>(list, e->blocksums, tiles, W, e->walker_offset, e->key, e->step, mask, fen, e->src);
+    KERNEL_CHECK(ctx);
+    gather_by_list_kernel<<<cdiv(W, 128), 128, 0, st>>>(e->src, W, n, e->x, e->x2, e->el, e->el2, e->w, e->w2, e->src);
+    KERNEL_CHECK(ctx);
+    CU(ctx, cudaStreamSynchronize(st));
+    cudaFree(list); cudaFree(mask); cudaFree(fen);
+  }
+  std::swap(e->x, e->x2);
+  std::swap(e->w, e->w2);
+  std::swap(e->el, e->el2);
+  e->step += 1;
+  return MOLE_OK;
+}
+
+int32_t mole_branch_sources(mole_ens_t e, int32_t* src) {
+  if (!e || !src) return MOLE_ERR_INVALID_ARG;
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  CU(e->ctx, cudaMemcpyAsync(src, e->src, e->W * sizeof(int32_t), cudaMemcpyDeviceToHost, STREAM(e->ctx)));
+  CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
+  return MOLE_OK;
+}
+
+// ------------------------------------------------------------------ FP64 peak probe
+int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops) {
+  if (!ctx || !tflops) return MOLE_ERR_INVALID_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 16;
+  double* out = nullptr;
+  CU(ctx, cudaMalloc(&out, blocks * sizeof(double)));
+  cudaEvent_t a, b;
+  CU(ctx, cudaEventCreate(&a));
+  CU(ctx, cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(ctx, cudaEventRecord(a, STREAM(ctx)));
+    dfma_peak_kernel<<<blocks, threads, 0, STREAM(ctx)>>>(out, iters, 1.0 + rep);
+    KERNEL_CHECK(ctx);
+    CU(ctx, cudaEventRecord(b, STREAM(ctx)));
+    CU(ctx, cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, a, b));
+    const double fl = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  *tflops = best;
+  return MOLE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Internal structures shared by the CUDA translation units and the host-side C++.
+// Product code: never includes anything from oracle/.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/mole_b200.h"
+
+#if defined(__CUDACC__)
+#define MOLE_HD __host__ __device__ __forceinline__
+#define MOLE_D __device__ __forceinline__
+#else
+#define MOLE_HD inline
+#define MOLE_D inline
+#endif
+
+// ---- packed accumulator layout (doubles); mirrors mole_acc_host field order -----------------
+enum {
+  ACC_N = 0, ACC_E = 1, ACC_E2 = 2, ACC_B = 3, ACC_B2 = 4, ACC_NB = 5, ACC_NACC = 6, ACC_NMOVE = 7,
+  ACC_T = 8, ACC_PSI = 9,
+  ACC_O = 10,                                  // 8 slots
+  ACC_OE = ACC_O + MOLE_ACC_MAX_PARAMS,        // 8 slots
+  ACC_OO = ACC_OE + MOLE_ACC_MAX_PARAMS,       // 36 slots, (k<=l) packed row-major over the ACTUAL P
+  ACC_LEN = ACC_OO + MOLE_ACC_MAX_PARAMS * (MOLE_ACC_MAX_PARAMS + 1) / 2
+};
+
+// ---- POD parameter blocks passed to kernels by value -------------------------------------------
+struct WfParams {
+  int32_t kind, ne, np, pad;
+  double p[MOLE_WF_MAX_PARAMS];
+  double geom[MOLE_WF_MAX_GEOM];
+};
+
+struct HamParams {
+  int32_t kind, n_ions;
+  double ion_pos[MOLE_OP_MAX_IONS * 3];
+  double ion_z[MOLE_OP_MAX_IONS];
+  double ionic_repulsion;  // IonicPotential::new precomputes it (operator.rs:40-55)
+  double frequency;
+};
+
+struct RngKey { uint32_t k0, k1; };
+
+struct SweepParams {
+  // ensemble
+  double* x;          // [3*ne][W]
+  double* blk;        // [W] partial block sums
+  double* acc;        // [ACC_LEN] global accumulators
+  double* partials;   // [grid][ACC_LEN]
+  unsigned int* ticket;
+  int64_t W;
+  uint64_t walker_offset;
+  RngKey key;
+  uint32_t step0;
+  // schedule
+  int32_t n_sweeps, n_discard, block_size, blk_fill;
+  uint32_t observables, compat;
+  double metrop_param;   // box side | tau
+  // traces (device pointers, nullable)
+  double* tr_energy; double* tr_wfvalue; double* tr_kinetic; double* tr_pgrad; uint8_t* tr_accept;
+  WfParams wf;
+  HamParams ham;
+};
+
+struct DmcParams {
+  double* x; double* w; double* el; uint8_t* el_valid_flag;
+  double* red;        // [4] sum_w_e, sum_w, sum_w_new, max_w_new (atomics-free: partials + ticket)
+  double* partials; unsigned int* ticket;
+  int64_t W; uint64_t walker_offset; RngKey key; uint32_t step;
+  double tau_move, tau_weight, e_ref;
+  int32_t el_cached;
+  WfParams wf; HamParams ham;
+};
+
+// ---- host-side objects behind the opaque handles ----------------------------------------------
+struct mole_ctx_s {
+  int device = -1;
+  void* stream = nullptr;   // cudaStream_t
+  int sm_count = 0;
+  std::string last_error;
+  int64_t launches = 0;
+  // NCCL (dlopen'ed lazily, see mole_comm.cpp)
+  void* nccl_comm = nullptr;
+  double* comm_scratch = nullptr;  // device, 16 doubles
+  int nranks = 1, rank = 0;
+};
+
+struct mole_wf_s { mole_ctx_s* ctx; WfParams p; };
+struct mole_op_s { mole_ctx_s* ctx; HamParams p; };
+struct mole_metrop_s { int32_t kind; double param; };
+
+struct mole_ens_s {
+  mole_ctx_s* ctx;
+  int64_t W; int32_t ne; uint64_t walker_offset;
+  RngKey key; uint32_t step;
+  double* x = nullptr;      // [3*ne][W]
+  double* x2 = nullptr;     // gather target for branching (swapped with x)
+  double* x0 = nullptr;     // snapshot (lazily allocated)
+  double* w = nullptr; double* w2 = nullptr;
+  double* el = nullptr; double* el2 = nullptr; int el_cached = 0;
+  double* blk = nullptr; int32_t blk_fill = 0; int32_t blk_size = 0;
+  double* acc = nullptr;    // [ACC_LEN]
+  double* partials = nullptr; int partial_rows = 0;
+  unsigned int* ticket = nullptr;
+  double* red = nullptr;    // [8] dmc reductions
+  unsigned long long* cum = nullptr;  // [W] branching prefix sums
+  unsigned long long* blocksums = nullptr; int n_scan_blocks = 0;
+  int32_t* src = nullptr;   // [W] branching source indices
+  int32_t np_last = 0;      // P of the last sweep that touched acc
+};
+
+// ---- host-only helpers (mole_host.cpp) ---------------------------------------------------------
+RngKey mole_key_from_seed(const uint8_t seed[32]);
+int mole_set_error(mole_ctx_s* ctx, int code, const std::string& msg);
+int mole_oo_index(int P, int k, int l);  // k<=l
+// mole_comm.cpp: sum/max allreduce of a few host scalars over the ctx communicator (no-op for one rank)
+int32_t mole_comm_allreduce_host(mole_ctx_s* ctx, double* sum_vals, int n_sum, double* max_vals, int n_max);

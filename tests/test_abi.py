@@ -1,0 +1,141 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/mole_b200.h declares, fails loudly (no CPU fallback) on device entry points, and its
+host-only logic (seed derivation, finaliser, optimizers) agrees with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import SEED0
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "mole_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mole_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(mole):
+    lib = mole.ffi.lib()
+    declared = _header_symbols()
+    assert len(declared) >= 55
+    for name in declared:
+        assert hasattr(lib, name), "libmole_b200.so does not export %s" % name
+    assert sorted(mole.ffi.SYMBOLS) == declared
+
+
+def test_struct_layouts_match_header(mole):
+    assert C.sizeof(mole.ffi.WfDesc) == 16 + 16 * 8
+    assert C.sizeof(mole.ffi.OpDesc) == 8 + 24 * 8 + 8 * 4 + 8
+    assert C.sizeof(mole.ffi.AccHost) == 62 * 8 + 8
+    assert C.sizeof(mole.ffi.SweepArgs) == 24 + 5 * 8
+
+
+def test_no_cpu_fallback(mole):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mole.MoleError) as ei:
+        mole.Context(0)
+    assert ei.value.code == mole.ffi.ERR_NO_DEVICE
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mole_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                code = "\n".join(l for l in txt.splitlines() if "oracle/" not in l or "#include" in l or "import" in l)
+                assert not re.search(r"^\s*(import|from)\s+oracle", code, flags=re.M), f
+                assert not re.search(r"#include\s+[\"<].*oracle", code), f
+                assert "libmole_oracle" not in txt, f
+
+
+def test_derive_seed_matches_oracle(mole, orc):
+    for master in (SEED0, bytes(range(32)), bytes([1] * 32)):
+        for n in (0, 1, 2, 77):
+            assert mole.derive_seed(master, n) == orc.derive_seed(master, n)
+
+
+def _acc_from_samples(mole, en, o, block_size, n_accept=0, n_moves=0):
+    """Packs raw per-walker sample series [W, ns] (+ O [W, ns, P]) into reduced moments."""
+    a = mole.ffi.AccHost()
+    W, ns = en.shape
+    P = o.shape[2]
+    a.n_params = P
+    a.n_samples = en.size
+    a.sum_e = en.sum()
+    a.sum_e2 = (en ** 2).sum()
+    bm = en.reshape(W, ns // block_size, block_size).mean(axis=2)
+    a.sum_b, a.sum_b2, a.n_blocks = bm.sum(), (bm ** 2).sum(), bm.size
+    a.n_accept, a.n_moves = n_accept, n_moves
+    q = 0
+    for k in range(P):
+        a.sum_o[k] = o[:, :, k].sum()
+        a.sum_oe[k] = (o[:, :, k] * en).sum()
+        for l in range(k, P):
+            a.sum_oo[q] = (o[:, :, k] * o[:, :, l]).sum()
+            q += 1
+    return a
+
+
+def test_finaliser_matches_reference_statistics(mole, orc):
+    rng = np.random.default_rng(3)
+    W, ns, bs = 8, 240, 10
+    en = -1.1 + 0.3 * rng.normal(size=(W, ns))
+    o = rng.normal(size=(W, ns, 1))
+    acc = _acc_from_samples(mole, en, o, bs, 700, 1000)
+    e, err, accp, g = mole.acc_finalize(acc)
+    flat = en.reshape(-1)    # concatenate_worker_data order (vmc.rs:108-130)
+    mean = orc.mean_fold(flat)
+    assert abs(e - mean) < 1e-13
+    assert abs(err - orc.blocking_error(flat, bs, mean)) < 1e-11
+    assert accp == 0.7
+    # with psi == 1 the stored samples are O itself
+    gref = orc.energy_gradient(np.ones(flat.size), o.reshape(-1, 1), flat, mean)
+    assert np.allclose(g, gref, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("P", [1, 3, 7])
+def test_optimizers_match_oracle(mole, orc, P):
+    rng = np.random.default_rng(10 + P)
+    W, ns, bs = 4, 200, 10
+    kinds = [(mole.SteepestDescent(1e-2, P), orc.Optimizer(orc.OPT_SD, P, 1e-2)),
+             (mole.MomentumDescent(1e-2, 0.9, P), orc.Optimizer(orc.OPT_MOMENTUM, P, 1e-2, 0.9)),
+             (mole.NesterovMomentum(1e-2, 0.8, P), orc.Optimizer(orc.OPT_NESTEROV, P, 1e-2, 0.8)),
+             (mole.OnlineLbfgs(1e-1, 3, P), orc.Optimizer(orc.OPT_LBFGS, P, 1e-1, history=3)),
+             (mole.StochasticReconfiguration(0.5, P), orc.Optimizer(orc.OPT_SR, P, 0.5, quirk_sr_subtract=0)),
+             (mole.StochasticReconfiguration(0.5, P, compat=mole.ffi.COMPAT_SR_SUBTRACT),
+              orc.Optimizer(orc.OPT_SR, P, 0.5, quirk_sr_subtract=1))]
+    for mine, ref in kinds:
+        pars = rng.normal(size=P)
+        for it in range(5):   # several steps: the optimizers are stateful
+            en = -2.0 + 0.5 * rng.normal(size=(W, ns))
+            o = rng.normal(size=(W, ns, P)) + 0.3 * en[:, :, None]
+            acc = _acc_from_samples(mole, en, o, bs)
+            mean = orc.mean_fold(en.reshape(-1))
+            dp_ref = ref.step(pars, mean, np.ones(en.size), o.reshape(-1, P), en.reshape(-1))
+            dp = mine.compute_parameter_update(pars, acc)
+            scale = max(1.0, np.max(np.abs(dp_ref)))
+            assert np.max(np.abs(dp - dp_ref)) < 1e-8 * scale, (type(mine).__name__, it)
+            pars = pars + dp_ref
+    S = kinds[4][0].sr_matrix(acc)
+    Sref = kinds[4][1].sr_matrix(np.ones(en.size), o.reshape(-1, P))
+    assert np.allclose(S, Sref, rtol=1e-10, atol=1e-12)
+
+
+def test_optimizer_errors(mole):
+    opt = mole.StochasticReconfiguration(1.0, 2)
+    acc = mole.ffi.AccHost()
+    acc.n_params = 1
+    with pytest.raises(mole.MoleError) as ei:   # Error::DataAccessError
+        opt.compute_parameter_update(np.zeros(2), acc)
+    assert ei.value.code == mole.ffi.ERR_DATA_ACCESS
+    acc.n_params, acc.n_samples = 2, 10.0      # all-zero moments -> singular S -> Error::LinalgError
+    with pytest.raises(mole.MoleError) as ei:
+        opt.compute_parameter_update(np.zeros(2), acc)
+    assert ei.value.code == mole.ffi.ERR_LINALG

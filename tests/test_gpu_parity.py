@@ -1,0 +1,340 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical
+walker configurations and a shared Philox stream.  Bars (BASELINE.json north_star):
+psi, grad psi, lap psi, E_L, parameter gradients within 1e-10 relative; accept/reject bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import CFG2, SEED0, cases, random_cfgs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wf_golden.json")))
+SMALL = ["h2", "he", "h2p", "gauss_sho", "gauss_h", "sto_h"]
+
+
+def close(a, b, tol=TOL):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b)) if b.size else 1.0)
+    return np.max(np.abs(a - b) / scale) < tol if a.size else True
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_eval_vgl_matches_oracle(mole, orc, name):
+    c = cases()[name]
+    wf, op = c["make"](mole)
+    W = 4096
+    cfgs = random_cfgs(W, c["ne"], seed=5)
+    ens = mole.Ensemble(W, c["ne"], SEED0)
+    ens.set_configs(cfgs)
+    assert np.array_equal(ens.get_configs(), cfgs)
+    got = ens.eval_vgl(wf, op)
+    ref = orc.eval_batch(c["owf"], c["oham"], cfgs)
+    assert rel_err(got["psi"], ref["psi"]) < TOL
+    assert close(got["grad"], ref["grad"])
+    assert close(got["lap"], ref["lap"])
+    assert close(got["hpsi"], ref["hpsi"])
+    assert close(got["hpsi"] / got["psi"], ref["hpsi"] / ref["psi"])   # E_L
+    if c["np"]:
+        assert close(got["pgrad"], ref["pgrad"])
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_pointwise_traits_match_mpmath_golden(mole, name):
+    g = GOLD[name]
+    wf, op = cases()[name]["make"](mole)
+    for e in g["entries"]:
+        cfg = np.array(e["cfg"]).reshape(-1, 3)
+        assert rel_err(wf.value(cfg), float(e["psi"])) < TOL
+        gref = np.array([float(t) for t in e["grad"]]).reshape(-1, 3)
+        assert np.max(np.abs(wf.gradient(cfg) - gref)) < TOL * max(1.0, np.max(np.abs(gref)))
+        assert abs(wf.laplacian(cfg) - float(e["lap"])) < TOL * max(1.0, abs(float(e["lap"])))
+        if g["n_params"]:
+            assert rel_err(wf.parameter_gradient(cfg), [float(t) for t in e["pgrad"]]) < TOL
+        assert abs(op.act_on(wf, cfg) / wf.value(cfg) - float(e["eloc"])) < TOL * max(1.0, abs(float(e["eloc"])))
+
+
+def test_init_draws_match_oracle(mole, orc):
+    W, ne = 300, 2
+    seed = bytes(range(32))
+    ens = mole.Ensemble(W, ne, seed, walker_offset=1000)
+    ens.init_uniform(-1.0, 1.0)
+    got = ens.get_configs()
+    ref = np.array([orc.init_uniform(seed, 1000 + w, ne) for w in range(W)])
+    assert np.array_equal(got, ref)          # integer -> double conversion and one mul/add: bit-exact
+    ens.init_normal(1.0)
+    got = ens.get_configs()
+    ref = np.array([orc.init_normal(seed, 1000 + w, ne) for w in range(W)])
+    assert np.max(np.abs(got - ref)) < 1e-14  # log/sincos differ in the last ulp between libm and CUDA
+    ens.init_uniform(-1.0, 1.0, broadcast_walker0=True)   # vmc.rs:56: clones of ONE sampler
+    got = ens.get_configs()
+    assert np.array_equal(got, np.broadcast_to(orc.init_uniform(seed, 0, ne), got.shape))
+
+
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("metrop", ["box", "diffuse"])
+def test_sweep_parity_shared_philox(mole, orc, name, metrop):
+    """Identical starting walkers + shared Philox stream: accept/reject decisions bit-exact,
+    E_L traces, stored observables and final configurations within 1e-10."""
+    c = cases()[name]
+    wf, op = c["make"](mole)
+    W, steps, bs = 256, 60, 10
+    seed = bytes([7] * 32)
+    param = 1.0 if metrop == "box" else 0.25
+    m = mole.MetropolisBox(param, seed) if metrop == "box" else mole.MetropolisDiffuse(param, seed)
+    cfgs = np.array([orc.init_uniform(seed, w, c["ne"]) for w in range(W)])
+    obs = orc.OBS_ENERGY | orc.OBS_WFVALUE | orc.OBS_KINETIC | (orc.OBS_PGRAD if c["np"] else 0)
+    ref = orc.ensemble_run(c["owf"], c["oham"], orc.run_options(orc.METROP_BOX if metrop == "box" else orc.METROP_DIFFUSE,
+                                                                 param, obs), cfgs, seed, steps, bs)
+    ens = mole.Ensemble(W, c["ne"], seed)
+    ens.init_uniform(-1.0, 1.0)
+    got = ens.sweep(wf, m, op, n_sweeps=steps, n_discard=bs, block_size=bs, observables=obs,
+                    traces=("energy", "wfvalue", "kinetic", "pgrad", "accept"))
+    assert np.array_equal(got["accept"], ref["accept"]), "accept/reject decisions differ"
+    assert 0.05 < got["accept"].mean() <= 1.0
+    assert close(ens.get_configs(), ref["cfgs"])
+    assert close(got["energy"], ref["energy"], 1e-9)
+    assert close(got["wfvalue"], ref["wfvalue"])
+    assert close(got["kinetic"], ref["kinetic"], 1e-9)
+    if c["np"]:
+        assert close(got["pgrad"], ref["pgrad"][:, :, :c["np"]])
+    # accumulators against the raw series
+    acc = ens.acc_get()
+    en = got["energy"]
+    assert acc.n_samples == en.size and acc.n_moves == W * steps * c["ne"]
+    assert acc.n_accept == got["accept"].sum()
+    assert abs(acc.sum_e - en.sum()) < 1e-9 * abs(en.sum())
+    assert abs(acc.sum_e2 - (en ** 2).sum()) < 1e-9 * (en ** 2).sum()
+    bm = en.reshape(W, -1, bs).mean(axis=2)
+    assert acc.n_blocks == bm.size and abs(acc.sum_b2 - (bm ** 2).sum()) < 1e-9 * (bm ** 2).sum()
+    e, err, accp, g = mole.acc_finalize(acc)
+    flat = ref["energy"].reshape(-1)
+    assert abs(e - orc.mean_fold(flat)) < 1e-9 * abs(e)
+    assert abs(err - orc.blocking_error(flat, bs, orc.mean_fold(flat))) < 1e-7 * err
+    if c["np"]:
+        o = ref["pgrad"][:, :, :c["np"]] / ref["wfvalue"][:, :, None]
+        assert abs(acc.sum_o[0] - o.sum()) < 1e-9 * abs(o.sum())
+        assert abs(acc.sum_oe[0] - (o[:, :, 0] * ref["energy"]).sum()) < 1e-9 * abs((o[:, :, 0] * ref["energy"]).sum())
+        assert abs(acc.sum_oo[0] - (o ** 2).sum()) < 1e-9 * (o ** 2).sum()
+        gref = orc.energy_gradient(ref["wfvalue"].reshape(-1), ref["pgrad"].reshape(-1, max(c["np"], 1))[:, :c["np"]],
+                                   flat, orc.mean_fold(flat))
+        assert np.max(np.abs(g - gref)) < 1e-8 * max(1.0, np.max(np.abs(gref)))
+
+
+def test_sweep_is_independent_of_launch_split_and_sharding(mole, orc):
+    """Philox keys are (walker, step): splitting the sweeps over launches, or the walkers over
+    ensembles (ranks), must not change a single bit of the trajectory."""
+    c = cases()["h2"]
+    wf, op = c["make"](mole)
+    m = mole.MetropolisDiffuse(0.25, SEED0)
+    W, steps = 512, 40
+    a = mole.Ensemble(W, 2, SEED0); a.init_uniform()
+    a.sweep(wf, m, op, n_sweeps=steps, block_size=10)
+    b = mole.Ensemble(W, 2, SEED0); b.init_uniform()
+    for _ in range(4):
+        b.sweep(wf, m, op, n_sweeps=steps // 4, block_size=10)
+    assert np.array_equal(a.get_configs(), b.get_configs())
+    accA, accB = a.acc_get(), b.acc_get()
+    assert accA.n_samples == accB.n_samples and accA.n_blocks == accB.n_blocks == W * steps // 10
+    assert abs(accA.sum_e - accB.sum_e) < 1e-9 * abs(accA.sum_e) and abs(accA.sum_b2 - accB.sum_b2) < 1e-9 * accA.sum_b2
+    h0 = mole.Ensemble(W // 2, 2, SEED0, walker_offset=0); h0.init_uniform()
+    h1 = mole.Ensemble(W // 2, 2, SEED0, walker_offset=W // 2); h1.init_uniform()
+    for h in (h0, h1):
+        h.sweep(wf, m, op, n_sweeps=steps, block_size=10)
+    assert np.array_equal(np.concatenate([h0.get_configs(), h1.get_configs()]), a.get_configs())
+    s0, s1 = h0.acc_get(), h1.acc_get()
+    assert abs((s0.sum_e + s1.sum_e) - accA.sum_e) < 1e-9 * abs(accA.sum_e)
+
+
+def test_compat_vector_div_quirk(mole, orc):
+    """MOLE_COMPAT_VECTOR_DIV reproduces operator/src/traits.rs:149-150 (Vector/Scalar = scalar/array)."""
+    c = cases()["he"]
+    wf, op = c["make"](mole)
+    W, steps, bs = 64, 30, 10
+    m = mole.MetropolisDiffuse(0.25, SEED0)
+    obs = orc.OBS_ENERGY | orc.OBS_WFVALUE | orc.OBS_PGRAD
+    cfgs = np.array([orc.init_uniform(SEED0, w, 2) for w in range(W)])
+    ref = orc.ensemble_run(c["owf"], c["oham"], orc.run_options(orc.METROP_DIFFUSE, 0.25, obs, quirk_vector_div=1), cfgs,
+                           SEED0, steps, bs)
+    ens = mole.Ensemble(W, 2, SEED0); ens.init_uniform()
+    got = ens.sweep(wf, m, op, n_sweeps=steps, n_discard=bs, block_size=bs, observables=obs,
+                    compat=mole.ffi.COMPAT_VECTOR_DIV, traces=("pgrad",))
+    assert close(got["pgrad"], ref["pgrad"])
+    acc = ens.acc_get()
+    o = ref["pgrad"][:, :, 0] / ref["wfvalue"]
+    assert abs(acc.sum_o[0] - o.sum()) < 1e-9 * abs(o.sum())
+
+
+def test_runner_known_answers(mole):
+    """The reference's integration tests re-expressed with proper error bars."""
+    # tests/helium_lcao.rs:89-138 (He, alpha=1.69, Diffuse(0.1), run(1000,100)), many chains
+    wf = mole.HeliumAtomWaveFunction(1.69)
+    h = mole.ElectronicHamiltonian(mole.KineticEnergy(), mole.IonicPotential([[0, 0, 0]], [2]), mole.ElectronicPotential())
+    s = mole.Sampler(wf, mole.MetropolisDiffuse.from_rng(0.1, SEED0), mole.operators(Energy=h), n_walkers=4096, independent=True)
+    r = mole.Runner(s).run(1000, 100)
+    en = r.data["Energy"]
+    assert en.shape == (4096, 900)
+    exact = 0.5 * 1.5 ** 6 * (-0.5)
+    chain_means = en.mean(axis=1)
+    err = chain_means.std() / np.sqrt(len(chain_means))
+    assert abs(chain_means.mean() - exact) < 5 * err and err < 5e-3
+    assert abs(en.mean() - exact) < 2.0 * en.std()      # the reference's own (loose) assertion, :137
+    # tests/hydrogen_molecular_ion_lcao.rs:100-142 (H2+, Box(1.0), run(10000,100)) on 256 chains of 2000 steps
+    wf = mole.H2WF(2.5, 1.0)
+    h = mole.ElectronicHamiltonian(mole.KineticEnergy(), mole.IonicPotential([[-1.25, 0, 0], [1.25, 0, 0]], [1, 1]),
+                                   mole.ElectronicPotential())
+    s = mole.Sampler(wf, mole.MetropolisBox.from_rng(1.0, SEED0), mole.operators(Energy=h), n_walkers=256, independent=True)
+    en = mole.Runner(s).run(2000, 100).data["Energy"]
+    assert abs(en.mean() - (-0.565)) < en.std()          # :141
+    # examples/custom_operator.rs:100-139: exact eigenstate, zero variance
+    wf = mole.GaussianWaveFunction(np.sqrt(2.0))
+    s = mole.Sampler(wf, mole.MetropolisBox.from_rng(1.0, SEED0), mole.operators(Energy=mole.HarmonicHamiltonian(1.0)), n_walkers=64,
+                     independent=True)
+    r = mole.Runner(s).run(1000, 1)
+    en = r.data["Energy"]
+    assert abs(en.mean() - 1.5) < 1e-14 and en.std() < 1e-14
+    assert 0.0 < r.acceptance <= 64 * 1000
+
+
+def test_runner_assert_and_errors(mole):
+    wf = mole.GaussianWaveFunction(1.0)
+    s = mole.Sampler(wf, mole.MetropolisBox(1.0, SEED0), mole.operators(Energy=mole.HarmonicHamiltonian(1.0)))
+    with pytest.raises(mole.MoleError) as ei:            # montecarlo.rs:29
+        mole.Runner(s).run(10, 10)
+    assert ei.value.code == mole.ffi.ERR_ASSERT
+    mock = mole.WaveFunctionMock(1.0)
+    with pytest.raises(mole.MoleError) as ei:            # metrop.rs:248-250 unimplemented!()
+        mock.gradient([[0.0, 0.0, 0.0]])
+    assert ei.value.code == mole.ffi.ERR_FUNC
+    ens = mole.Ensemble(4, 1, SEED0)
+    with pytest.raises(mole.MoleError):
+        ens.sweep(mock, mole.MetropolisDiffuse(0.1, SEED0), None, n_sweeps=2, observables=0)
+    with pytest.raises(mole.MoleError) as ei:            # shape mismatch
+        mole.Ensemble(4, 2, SEED0).sweep(wf, mole.MetropolisBox(1.0, SEED0), None, n_sweeps=2, observables=0)
+    assert ei.value.code == mole.ffi.ERR_SHAPE
+
+
+def test_uniform_wf_always_accepted(mole):
+    """proptest of metrop.rs:259-269: for psi == 1 every MetropolisBox proposal is accepted."""
+    mock = mole.WaveFunctionMock(1.0)
+    W = 1024
+    ens = mole.Ensemble(W, 1, SEED0)
+    rng = np.random.default_rng(0)
+    ens.set_configs(rng.normal(size=(W, 1, 3)) * 10.0 ** rng.integers(-30, 30, size=(W, 1, 1)))
+    got = ens.sweep(mock, mole.MetropolisBox(1.0, SEED0), None, n_sweeps=8, observables=0, traces=("accept",))
+    assert got["accept"].all()
+
+
+@pytest.mark.parametrize("compat", [0, 3])
+def test_vmc_run_optimization_matches_oracle(mole, orc, compat):
+    """VmcRunner::run_optimization on the H2 example's shape (hydrogen_molecule.rs:171-199,235-273),
+    8 workers, restart-from-master semantics, SR; energies/errors/parameters per iteration."""
+    c = cases()["h2"]
+    iters, total, bs, nw = 4, 4000, 10, 8
+    step = 0.05
+    cfg0 = orc.init_uniform(SEED0, 0, 2)
+    opts = orc.run_options(orc.METROP_DIFFUSE, 0.25, quirk_vector_div=1 if compat else 0)
+    ropt = orc.Optimizer(orc.OPT_SR, 1, step, quirk_sr_subtract=1 if compat else 0)
+    ref = orc.vmc_run_optimization(c["owf"], c["oham"], opts, ropt, SEED0, cfg0, iters, total, bs, nw)
+    wf, op = c["make"](mole)
+    obs = mole.operators(**{"Energy": op, "Parameter gradient": mole.ParameterGradient, "Wavefunction value": mole.WavefunctionValue})
+    sampler = mole.Sampler.new(wf, mole.MetropolisDiffuse.from_rng(0.25, SEED0), obs, compat=compat)
+    vmc = mole.VmcRunner.__new__(mole.VmcRunner)
+    vmc.__init__(sampler, mole.StochasticReconfiguration(step, 1, compat=compat))
+    wf_out, en, er = vmc.run_optimization(iters, total, bs, nw)
+    assert np.max(np.abs(en - ref["energies"])) < 1e-8
+    assert np.max(np.abs(er - ref["errors"]) / ref["errors"]) < 1e-6
+    assert np.max(np.abs(vmc.acceptance - ref["acceptance"])) < 1e-12
+    assert np.max(np.abs(vmc.param_history - ref["param_history"])) < 1e-7 * max(1.0, np.max(np.abs(ref["param_history"])))
+    assert abs(wf_out.parameters()[0] - ref["params"][0]) < 1e-7 * max(1.0, abs(ref["params"][0]))
+
+
+def test_sho_optimize(mole):
+    """tests/sho_optimize.rs:117-141 with enough walkers for a meaningful error bar."""
+    wf = mole.GaussianWaveFunction(1.0)
+    obs = mole.operators(**{"Energy": mole.HarmonicHamiltonian(1.0), "Parameter gradient": mole.ParameterGradient,
+                            "Wavefunction value": mole.WavefunctionValue})
+    sampler = mole.Sampler(wf, mole.MetropolisDiffuse.from_rng(0.1, SEED0), obs)
+    vmc = mole.VmcRunner(sampler, mole.SteepestDescent(2e-1))
+    _, en, er = vmc.run_optimization(40, 4096 * 200, 10, 4096, restart_each_iter=False)
+    assert abs(wf.parameters()[0] - np.sqrt(2.0)) < 0.02
+    assert abs(en[-1] - 1.5) < max(5 * er[-1], 1e-3)
+    assert en[-1] < en[0]
+
+
+def _dmc_setup(mole, orc, W, identical):
+    c = cases()["gauss_h"]
+    wf, op = c["make"](mole)
+    seed = bytes([1] * 32)        # examples/dmc.rs:198
+    m = mole.MetropolisDiffuse.from_rng(0.025, seed).fix_nodes()
+    cfgs = np.array([orc.init_normal(seed, 0 if identical else w, 1) for w in range(W)])
+    return c, wf, op, m, seed, cfgs
+
+
+def test_dmc_step_and_sr_branch_match_oracle(mole, orc):
+    W = 2048
+    c, wf, op, m, seed, cfgs = _dmc_setup(mole, orc, W, identical=False)
+    dmc = mole.DmcRunner(wf, W, 0.6, op, m, mole.SRBrancher.new(), identical_start=False)
+    assert np.max(np.abs(dmc.ensemble.get_configs() - cfgs)) < 1e-14
+    dmc.ensemble.set_configs(cfgs)
+    w, x, e_ref = np.ones(W), cfgs.copy(), 0.6
+    for t in range(5):
+        e_o, tw_o, w, x = orc.dmc_step(c["owf"], c["oham"], w, x, 0.025, 0.025, e_ref, seed, t)
+        swe, sw = dmc.ensemble.dmc_step(wf, m, op, 0.025, e_ref)
+        assert abs(swe / sw - e_o) < 1e-10 * abs(e_o) and abs(sw - tw_o) < 1e-10 * tw_o
+        assert close(dmc.ensemble.get_weights(), w) and close(dmc.ensemble.get_configs(), x)
+        w, x = orc.branch(orc.BRANCH_SR, 1, w, x, seed, t)
+        dmc.ensemble.branch(mole.ffi.BRANCH_SR)
+        assert close(dmc.ensemble.get_weights(), w)
+        assert close(dmc.ensemble.get_configs(), x)      # same walkers picked (integer weights + draws bit-exact)
+        assert dmc.ensemble.step == t + 1
+
+
+def test_simple_branching_matches_oracle(mole, orc):
+    W = 3000
+    rng = np.random.default_rng(4)
+    cfgs = rng.normal(size=(W, 1, 3))
+    for trial, scale in enumerate((1.0, 0.7, 1.4)):     # balanced, shrinking (clone), growing (random removal)
+        w = rng.gamma(4.0, 0.25, size=W) * scale
+        ens = mole.Ensemble(W, 1, SEED0)
+        ens.set_configs(cfgs); ens.set_weights(w); ens.step = 11 + trial
+        wo, xo = orc.branch(orc.BRANCH_SIMPLE, 1, w, cfgs, SEED0, 11 + trial)
+        ens.branch(mole.ffi.BRANCH_SIMPLE)
+        assert np.array_equal(ens.get_weights(), wo)
+        assert np.array_equal(ens.get_configs(), xo)
+    # SR on hand-set weights
+    w = rng.gamma(2.0, 0.5, size=W)
+    ens = mole.Ensemble(W, 1, SEED0)
+    ens.set_configs(cfgs); ens.set_weights(w); ens.step = 3
+    wo, xo = orc.branch(orc.BRANCH_SR, 1, w, cfgs, SEED0, 3)
+    ens.branch(mole.ffi.BRANCH_SR)
+    assert np.array_equal(ens.get_configs(), xo) and close(ens.get_weights(), wo)
+    src = ens.branch_sources()
+    assert np.array_equal(cfgs[src], xo)
+
+
+@pytest.mark.parametrize("identical", [True, False])
+def test_dmc_diffuse_matches_oracle(mole, orc, identical):
+    """DmcRunner::diffuse on the examples/dmc.rs shape (100 walkers, tau=0.025, SRBrancher)."""
+    W, iters, bs, neq = 100, 600, 50, 3
+    c, wf, op, m, seed, cfgs = _dmc_setup(mole, orc, W, identical)
+    ref = orc.dmc_diffuse(c["owf"], c["oham"], np.ones(W), cfgs, 0.025, 0.62, orc.BRANCH_SR, seed, 0.025, iters, bs, neq)
+    dmc = mole.DmcRunner.new(wf, W, 0.62, op, m, mole.SRBrancher.new(), identical_start=identical)
+    en, er = dmc.diffuse(0.025, iters, bs, neq, want_steps=True)
+    assert len(en) == len(ref["energies"]) == iters // bs - neq
+    assert np.max(np.abs(dmc.step_energies - ref["step_energies"])) < 1e-8
+    assert np.max(np.abs(en - ref["energies"])) < 1e-9 and np.max(np.abs(er - ref["errors"])) < 1e-8
+    assert abs(dmc.reference_energy - ref["reference_energy"]) < 1e-9
+
+
+def test_dmc_hydrogen_energy(mole):
+    """examples/dmc.rs:224: DMC with a nodeless guiding function converges to the exact -0.5 Ha."""
+    wf = mole.GaussianWaveFunction(1.3)
+    op = mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1])
+    m = mole.MetropolisDiffuse.from_rng(0.01, bytes([1] * 32)).fix_nodes()
+    dmc = mole.DmcRunner.new(wf, 8192, -0.45, op, m, mole.SRBrancher.new(), identical_start=False)
+    en, er = dmc.diffuse(0.01, 3000, 100, 10)
+    assert abs(en[-1] + 0.5) < max(6 * er[-1], 3e-3)
