@@ -273,6 +273,7 @@ int32_t mole_ensemble_set_weights(mole_ens_t e, const double* w) {
   CU(e->ctx, cudaSetDevice(e->ctx->device));
   CU(e->ctx, cudaMemcpyAsync(e->w, w, e->W * sizeof(double), cudaMemcpyHostToDevice, STREAM(e->ctx)));
   CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
+  e->wstats_valid = 0;
   return MOLE_OK;
 }
 int32_t mole_ensemble_get_weights(mole_ens_t e, double* w) {
@@ -537,6 +538,7 @@ int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op,
   }
   KERNEL_CHECK(ctx);
   e->el_cached = 1;
+  e->wstats_valid = 1;
   double red[4];
   CU(ctx, cudaMemcpyAsync(red, e->red, 4 * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
   CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
@@ -560,7 +562,7 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
     // post-update sum and max of the weights come from the last mole_dmc_step reduction (red[2], red[3]);
     // when the weights were set by hand they are recomputed here.
     double red[4];
-    if (e->el_cached) {
+    if (e->wstats_valid) {
       CU(ctx, cudaMemcpyAsync(red, e->red, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
       CU(ctx, cudaStreamSynchronize(st));
     } else {
@@ -612,6 +614,7 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
   std::swap(e->x, e->x2);
   std::swap(e->w, e->w2);
   std::swap(e->el, e->el2);
+  e->wstats_valid = 0;
   e->step += 1;
   return MOLE_OK;
 }

@@ -98,6 +98,7 @@ struct mole_ens_s {
   double* x0 = nullptr;     // snapshot (lazily allocated)
   double* w = nullptr; double* w2 = nullptr;
   double* el = nullptr; double* el2 = nullptr; int el_cached = 0;
+  int wstats_valid = 0;      // red[2..3] hold sum/max of the CURRENT weights
   double* blk = nullptr; int32_t blk_fill = 0; int32_t blk_size = 0;
   double* acc = nullptr;    // [ACC_LEN]
   double* partials = nullptr; int partial_rows = 0;
