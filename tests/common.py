@@ -30,6 +30,13 @@ def cases(mole=None):
         lambda m: (m.GaussianWaveFunction(1.0), m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1])))
     add("sto_h", O.wf_desc(O.WF_STO_1S, [0.8]), O.ham_desc(O.HAM_ELECTRONIC, [[0, 0, 0]], [1]),
         lambda m: (m.STO(0.8), m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1])))
+    def sj(name, nup, ndn, params, kappa, Z):
+        add(name, O.wf_desc(O.WF_SLATER_JASTROW, params, [kappa, nup, ndn]), O.ham_desc(O.HAM_ELECTRONIC, [[0, 0, 0]], [Z]),
+            lambda m: (m.SlaterJastrow(nup, ndn, params[:3], params[3:], kappa), m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [Z])))
+
+    sj("sj_ne", 5, 5, [9.64, 2.88, 2.88, 0.5, 1.0, 0.1, -0.05], 1.0, 10)     # SURVEY.md §8(c) synthetic config 5
+    sj("sj_be", 2, 2, [3.68, 0.96, 0.96, 0.5, 1.0, 0.2, 0.1], 1.0, 4)
+    sj("sj_li", 2, 1, [2.69, 0.64, 0.64, 0.4, 0.8, 0.0, 0.0], 1.5, 3)
     return c
 
 
