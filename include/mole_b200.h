@@ -163,6 +163,9 @@ int32_t mole_eval_vgl(mole_ens_t ens, mole_wf_t wf, mole_op_t op, double* psi, d
 enum { MOLE_METROP_BOX = 0 /* metrop.rs:22-101 */, MOLE_METROP_DIFFUSE = 1 /* metrop.rs:103-217 */ };
 int32_t mole_metropolis_create(int32_t kind, double param /* box_side | time_step */, mole_metrop_t* m);
 int32_t mole_metropolis_destroy(mole_metrop_t m);
+/* MOLE_COMPAT_* bits that concern the sampler itself (MOLE_COMPAT_NAN_ACCEPT); OR-ed with the
+ * per-call compat of mole_sweep and used by mole_dmc_step */
+int32_t mole_metropolis_set_compat(mole_metrop_t m, uint32_t compat);
 
 /* ---- fused sweep: Sampler::move_state + Sampler::sample + Runner::run's block loop -------------
  * (samplers.rs:81-117, montecarlo.rs:24-46) for all walkers, n_sweeps sweeps in ONE launch. */
@@ -179,7 +182,13 @@ enum {
    * the intended O_k = (d psi/d p)/psi. */
   MOLE_COMPAT_VECTOR_DIV = 1,
   /* reproduce optimizers.rs:219-224, which subtracts <O_i><O_j> from EVERY element of S */
-  MOLE_COMPAT_SR_SUBTRACT = 2
+  MOLE_COMPAT_SR_SUBTRACT = 2,
+  /* reproduce `acceptance.min(1.0)` with Rust's NaN-dropping f64::min (metrop.rs:80,195): a NaN
+   * acceptance ratio (0/0 when t_high and t_low both underflow next to a node, or psi = 0) becomes 1.0
+   * and the move is ACCEPTED.  Default (0): a NaN ratio is rejected, which is what keeps 2^20-walker
+   * ensembles of nodal wavefunctions finite (DESIGN.md "deliberate deviations").  Identical results
+   * whenever the reference's own ratio is not NaN. */
+  MOLE_COMPAT_NAN_ACCEPT = 4
 };
 
 typedef struct {

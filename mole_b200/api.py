@@ -357,6 +357,11 @@ class _Metropolis:
         self.seed = bytes(seed32(s))
         self._n_seeds = 0
 
+    def set_compat(self, compat):
+        """MOLE_COMPAT_NAN_ACCEPT: reproduce Rust's NaN-dropping `acceptance.min(1.0)` (metrop.rs:80,195)."""
+        check(lib().mole_metropolis_set_compat(self.handle, C.c_uint32(compat)))
+        return self
+
     def generate_seed(self):
         s = derive_seed(self.seed, self._n_seeds)
         self._n_seeds += 1

@@ -387,7 +387,12 @@ int32_t mole_op_act_on(mole_op_t op, mole_wf_t wf, const double* cfg, double* ou
 int32_t mole_metropolis_create(int32_t kind, double param, mole_metrop_t* out) {
   if (!out || (kind != MOLE_METROP_BOX && kind != MOLE_METROP_DIFFUSE) || !(param > 0.0))
     return mole_set_error(nullptr, MOLE_ERR_INVALID_ARG, "mole_metropolis_create: bad kind or parameter");
-  *out = new mole_metrop_s{kind, param};
+  *out = new mole_metrop_s{kind, param, 0u};
+  return MOLE_OK;
+}
+int32_t mole_metropolis_set_compat(mole_metrop_t m, uint32_t compat) {
+  if (!m) return MOLE_ERR_INVALID_ARG;
+  m->compat = compat;
   return MOLE_OK;
 }
 int32_t mole_metropolis_destroy(mole_metrop_t m) { delete m; return MOLE_OK; }
@@ -439,7 +444,7 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
   sp.x = e->x; sp.blk = e->blk; sp.acc = e->acc; sp.partials = e->partials; sp.ticket = e->ticket;
   sp.W = W; sp.walker_offset = e->walker_offset; sp.key = e->key; sp.step0 = e->step;
   sp.n_sweeps = a->n_sweeps; sp.n_discard = a->n_discard; sp.block_size = a->block_size; sp.blk_fill = e->blk_fill;
-  sp.observables = a->observables; sp.compat = a->compat; sp.metrop_param = m->param;
+  sp.observables = a->observables; sp.compat = a->compat | m->compat; sp.metrop_param = m->param;
   sp.wf = wf->p;
   if (op) sp.ham = op->p;
 
@@ -522,7 +527,7 @@ int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op,
   memset(&dp, 0, sizeof(dp));
   dp.x = e->x; dp.w = e->w; dp.el = e->el; dp.red = e->red; dp.partials = e->partials; dp.ticket = e->ticket;
   dp.W = e->W; dp.walker_offset = e->walker_offset; dp.key = e->key; dp.step = e->step;
-  dp.tau_move = m->param; dp.tau_weight = time_step; dp.e_ref = e_ref; dp.el_cached = e->el_cached;
+  dp.tau_move = m->param; dp.tau_weight = time_step; dp.e_ref = e_ref; dp.el_cached = e->el_cached; dp.compat = m->compat;
   dp.wf = wf->p; dp.ham = op->p;
   if (wf->p.kind == K_SLATER_JASTROW) {
     const int32_t rc = sj_dmc_launch(ctx, e, dp);

@@ -69,6 +69,7 @@ struct DmcParams {
   int64_t W; uint64_t walker_offset; RngKey key; uint32_t step;
   double tau_move, tau_weight, e_ref;
   int32_t el_cached;
+  uint32_t compat;
   WfParams wf; HamParams ham;
 };
 
@@ -87,7 +88,7 @@ struct mole_ctx_s {
 
 struct mole_wf_s { mole_ctx_s* ctx; WfParams p; };
 struct mole_op_s { mole_ctx_s* ctx; HamParams p; };
-struct mole_metrop_s { int32_t kind; double param; };
+struct mole_metrop_s { int32_t kind; double param; uint32_t compat; };
 
 struct mole_ens_s {
   mole_ctx_s* ctx;

@@ -79,12 +79,20 @@ struct Walker {
   }
 };
 
+// `acceptance.min(1.0)` (metrop.rs:80,195).  Rust's f64::min drops a NaN operand, so upstream a NaN
+// ratio becomes 1.0 and is accepted; that is reproduced only under MOLE_COMPAT_NAN_ACCEPT, by default a
+// NaN ratio is rejected (include/mole_b200.h).
+MOLE_D double mole_clamp_acceptance(double a, uint32_t compat) {
+  if (isnan(a)) return (compat & MOLE_COMPAT_NAN_ACCEPT) ? 1.0 : 0.0;
+  return fmin(a, 1.0);
+}
+
 // Metropolis::move_state for electron e.  BOX: metrop.rs:60-96; DIFFUSE: metrop.rs:150-212.
 // psi(x), grad psi(x) are cached in the walker instead of being re-evaluated (the reference
 // evaluates them three times per diffusion move); the values are identical.
 template <class WF, int METROP>
 MOLE_D bool mole_move_state(const WfParams& p, Walker<WF>& wk, int e, double param, double sd, RngKey key,
-                            uint64_t wid, uint32_t step) {
+                            uint64_t wid, uint32_t step, uint32_t compat) {
   constexpr int NE = WF::NE;
   double xn[3];
   if (METROP == MOLE_METROP_BOX) {
@@ -96,7 +104,7 @@ MOLE_D bool mole_move_state(const WfParams& p, Walker<WF>& wk, int e, double par
     typename WF::State tr = wk.st;
     WF::move(p, tr, e, xn);
     const double pn = WF::psi(p, tr);
-    const double A = fmin((pn * pn) / (wk.psi * wk.psi), 1.0);   // metrop.rs:80 (fmin drops NaN like f64::min)
+    const double A = mole_clamp_acceptance((pn * pn) / (wk.psi * wk.psi), compat);   // metrop.rs:80
     if (A > d.u) {
       wk.st = tr;
       wk.psi = pn;
@@ -127,7 +135,7 @@ MOLE_D bool mole_move_state(const WfParams& p, Walker<WF>& wk, int e, double par
       sl = fma(b, b, sl);
     }
     const double th = exp(-sh / (2.0 * param)), tl = exp(-sl / (2.0 * param));
-    const double A = fmin(th * (pn * pn) / (tl * (wk.psi * wk.psi)), 1.0);     // :195
+    const double A = mole_clamp_acceptance(th * (pn * pn) / (tl * (wk.psi * wk.psi)), compat);     // :195
     if (A > d.u) {
       wk.st = tr;
       wk.psi = pn;
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepParams 
       const uint32_t step = sp.step0 + (uint32_t)s;
 #pragma unroll
       for (int e = 0; e < NE; ++e) {                            // Sampler::move_state, samplers.rs:106-117
-        const bool ok = mole_move_state<WF, METROP>(p, wk, e, sp.metrop_param, sd, sp.key, wid, step);
+        const bool ok = mole_move_state<WF, METROP>(p, wk, e, sp.metrop_param, sd, sp.key, wid, step, sp.compat);
         acc.v[ACC_NACC] += ok ? 1.0 : 0.0;
         acc.v[ACC_NMOVE] += 1.0;
         if (sp.tr_accept) sp.tr_accept[((size_t)s * NE + e) * W + w] = ok ? 1 : 0;
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams
     const double e_old = dp.el_cached ? dp.el[w] : mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);
     const uint64_t wid = dp.walker_offset + (uint64_t)w;
 #pragma unroll
-    for (int e = 0; e < NE; ++e) mole_move_state<WF, MOLE_METROP_DIFFUSE>(p, wk, e, dp.tau_move, sd, dp.key, wid, dp.step);
+    for (int e = 0; e < NE; ++e) mole_move_state<WF, MOLE_METROP_DIFFUSE>(p, wk, e, dp.tau_move, sd, dp.key, wid, dp.step, dp.compat);
     const double wt = dp.w[w];
     s_we = fma(wt, e_old, s_we);                                // dmc.rs:112-113
     s_w += wt;

@@ -79,6 +79,12 @@ MOLE_D double sj_gsum(double v, const SjLane& L) {
 
 struct SjPair { double u, gr, lt, R, iden, ir; };
 
+// acceptance.min(1.0) with the NaN policy of include/mole_b200.h (MOLE_COMPAT_NAN_ACCEPT)
+MOLE_D double sj_clamp_acceptance(double a, uint32_t compat) {
+  if (isnan(a)) return (compat & MOLE_COMPAT_NAN_ACCEPT) ? 1.0 : 0.0;
+  return fmin(a, 1.0);
+}
+
 // pair function from the squared distance (theory/jastrow.tex:23-31,45-48,68-71,82-97)
 MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   SjPair o;
@@ -263,7 +269,8 @@ MOLE_D void sj_refresh(const SjConst& c, SjLane& L, const SjShared& sm) {
 // Metropolis::move_state for electron `el` of spin slot S.  d = the pre-generated draws of THIS lane's
 // slot-S electron (only the owner's are used).  Returns the accept decision (uniform over the group).
 template <int S, int METROP>
-MOLE_D bool sj_move(const SjConst& c, SjLane& L, const SjShared& sm, int el, const MoveDraw& d, double param, double sd) {
+MOLE_D bool sj_move(const SjConst& c, SjLane& L, const SjShared& sm, int el, const MoveDraw& d, double param, double sd,
+                    uint32_t compat) {
   const int n = S == 0 ? c.nup : c.ndn;
   const int own = L.base + el;
   const bool isown = (L.gl == el);
@@ -377,12 +384,12 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, const SjShared& sm, int el, con
     const double tl = __shfl_sync(SJ_FULL, e3, L.base + 2);
     const double q = ratio * ef;                               // psi'/psi
     node = !(ratio > 0.0);                                     // signum(psi') != signum(psi) or NaN, :178-180
-    A = fmin(th * (q * q) / tl, 1.0);                          // :195
+    A = sj_clamp_acceptance(th * (q * q) / tl, compat);        // :195
     if (!node && A > u_acc) L.psi *= q;
   } else {
     const double q = ratio * exp(df);
     node = false;
-    A = fmin(q * q, 1.0);                                      // metrop.rs:80
+    A = sj_clamp_acceptance(q * q, compat);                    // metrop.rs:80
     if (A > u_acc) L.psi *= q;
   }
   const bool acc = !node && (A > u_acc);
@@ -608,7 +615,7 @@ MOLE_D void sj_sweep_spin(const SjConst& c, SjLane& L, const SjShared& sm, const
   if (METROP == MOLE_METROP_BOX) d = mole_draw_uniform4(sp.key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
   else d = mole_draw_normal3_uniform1(sp.key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
   for (int el = 0; el < n; ++el) {                                   // Sampler::move_state, samplers.rs:106-117
-    const bool ok = sj_move<S, METROP>(c, L, sm, el, d, sp.metrop_param, sd);
+    const bool ok = sj_move<S, METROP>(c, L, sm, el, d, sp.metrop_param, sd, sp.compat);
     if (L.act) {
       if (L.gl == 1) accv[1] += ok ? 1.0 : 0.0;                      // ACC_NACC = 6 -> lane 1, idx 1
       if (L.gl == 2) accv[1] += 1.0;                                 // ACC_NMOVE = 7 -> lane 2, idx 1
@@ -780,8 +787,8 @@ __global__ void __launch_bounds__(SJ_THREADS, 2) sj_dmc_kernel(const DmcParams d
       const int cfg_e = S == 0 ? L.gl : c.nup + L.gl;
       const MoveDraw d = mole_draw_normal3_uniform1(dp.key, wid, dp.step, DOM_MOVE, (uint32_t)cfg_e);
       for (int el = 0; el < n; ++el) {
-        if (S == 0) sj_move<0, MOLE_METROP_DIFFUSE>(c, L, sm, el, d, dp.tau_move, sd);
-        else sj_move<1, MOLE_METROP_DIFFUSE>(c, L, sm, el, d, dp.tau_move, sd);
+        if (S == 0) sj_move<0, MOLE_METROP_DIFFUSE>(c, L, sm, el, d, dp.tau_move, sd, dp.compat);
+        else sj_move<1, MOLE_METROP_DIFFUSE>(c, L, sm, el, d, dp.tau_move, sd, dp.compat);
       }
     }
     sj_refresh(c, L, sm);

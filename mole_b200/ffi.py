@@ -22,7 +22,7 @@ WF_STO_1S, WF_GAUSSIAN, WF_STO_PRODUCT, WF_H2_HL_STO, WF_H2P_PRODUCT, WF_SLATER_
 OP_KINETIC, OP_IONIC_POT, OP_ELEC_POT, OP_IONIC, OP_ELECTRONIC, OP_HARMONIC = range(6)
 METROP_BOX, METROP_DIFFUSE = 0, 1
 OBS_ENERGY, OBS_PGRAD, OBS_WFVALUE, OBS_KINETIC = 1, 2, 4, 8
-COMPAT_VECTOR_DIV, COMPAT_SR_SUBTRACT = 1, 2
+COMPAT_VECTOR_DIV, COMPAT_SR_SUBTRACT, COMPAT_NAN_ACCEPT = 1, 2, 4
 OPT_SD, OPT_MOMENTUM, OPT_NESTEROV, OPT_LBFGS, OPT_SR = range(5)
 BRANCH_SR, BRANCH_SIMPLE = 0, 1
 VMC_RESTART_EACH_ITER = 1
@@ -81,7 +81,7 @@ SYMBOLS = [
     "mole_ensemble_set_configs_broadcast", "mole_ensemble_get_configs", "mole_ensemble_set_weights",
     "mole_ensemble_get_weights", "mole_ensemble_snapshot", "mole_ensemble_restore", "mole_ensemble_reseed",
     "mole_ensemble_set_step", "mole_ensemble_get_step", "mole_derive_seed", "mole_eval_vgl",
-    "mole_metropolis_create", "mole_metropolis_destroy", "mole_sweep", "mole_acc_reset", "mole_acc_get",
+    "mole_metropolis_create", "mole_metropolis_destroy", "mole_metropolis_set_compat", "mole_sweep", "mole_acc_reset", "mole_acc_get",
     "mole_acc_allreduce", "mole_acc_device_ptr", "mole_acc_finalize", "mole_comm_get_unique_id", "mole_comm_init",
     "mole_comm_destroy", "mole_opt_create", "mole_opt_destroy", "mole_opt_step", "mole_opt_sr_matrix",
     "mole_runner_run", "mole_vmc_run_optimization", "mole_dmc_step", "mole_branch", "mole_branch_sources",

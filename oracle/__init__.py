@@ -41,7 +41,7 @@ class HamDesc(C.Structure):
 
 class RunOptions(C.Structure):
     _fields_ = [("metrop_kind", C.c_int32), ("metrop_param", C.c_double), ("observables", C.c_uint32),
-                ("quirk_vector_div", C.c_int32)]
+                ("quirk_vector_div", C.c_int32), ("nan_reject", C.c_int32)]
 
 
 def build(force=False):
@@ -109,8 +109,8 @@ def ham_desc(kind, ion_pos=(), ion_charge=(), frequency=0.0):
     return h
 
 
-def run_options(metrop_kind, metrop_param, observables=OBS_ENERGY, quirk_vector_div=0):
-    return RunOptions(metrop_kind, metrop_param, observables, quirk_vector_div)
+def run_options(metrop_kind, metrop_param, observables=OBS_ENERGY, quirk_vector_div=0, nan_reject=0):
+    return RunOptions(metrop_kind, metrop_param, observables, quirk_vector_div, nan_reject)
 
 
 # ------------------------------------------------------------------ RNG

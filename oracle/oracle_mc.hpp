@@ -22,7 +22,7 @@ enum MetropKind : int32_t { METROP_BOX = 0, METROP_DIFFUSE = 1 };
 // MetropolisBox: metrop.rs:60-96.  Returns true and overwrites cfg when accepted.
 template <class R>
 bool box_move_state(const Wf<R>& wf, R* cfg, int idx, double box_side, Key key, uint64_t walker,
-                    uint32_t step) {
+                    uint32_t step, bool nan_reject = false) {
   const int n = 3 * wf.ne;
   std::vector<R> prop(cfg, cfg + n);
   const MoveDraw d = draw_uniform4(key, walker, step, DOM_MOVE, (uint32_t)idx);
@@ -35,7 +35,7 @@ bool box_move_state(const Wf<R>& wf, R* cfg, int idx, double box_side, Key key, 
   const R old = orc::wf_value(wf, cfg);
   R acc = (wf_value * wf_value) / (old * old);
   if (r_val(acc) > 1.0) acc = R(1.0);  // f64::min(1.0); NaN.min(1.0)=1.0 in Rust, see note below
-  if (r_val(acc) != r_val(acc)) acc = R(1.0);
+  if (r_val(acc) != r_val(acc)) acc = R(nan_reject ? 0.0 : 1.0);
   if (r_val(acc) > d.u) {
     for (int i = 0; i < n; ++i) cfg[i] = prop[i];
     return true;
@@ -49,7 +49,7 @@ bool box_move_state(const Wf<R>& wf, R* cfg, int idx, double box_side, Key key, 
 // MetropolisDiffuse: metrop.rs:150-212.
 template <class R>
 bool diffuse_move_state(const Wf<R>& wf, R* cfg, int idx, double tau, Key key, uint64_t walker,
-                        uint32_t step, double* ratio_out = nullptr) {
+                        uint32_t step, double* ratio_out = nullptr, bool nan_reject = false) {
   const int n = 3 * wf.ne;
   std::vector<R> prop(cfg, cfg + n), grad(n), grad_old(n);
   const MoveDraw d = draw_normal3_uniform1(key, walker, step, DOM_MOVE, (uint32_t)idx);
@@ -86,7 +86,8 @@ bool diffuse_move_state(const Wf<R>& wf, R* cfg, int idx, double tau, Key key, u
   const R t_low = r_exp(-(nl * nl) / R(2.0 * tau));
   R acc = t_high * (wf_value * wf_value) / (t_low * (wf_value_old * wf_value_old));  // :195
   if (ratio_out) *ratio_out = r_val(acc);
-  if (r_val(acc) > 1.0 || r_val(acc) != r_val(acc)) acc = R(1.0);
+  if (r_val(acc) != r_val(acc)) acc = R(nan_reject ? 0.0 : 1.0);
+  if (r_val(acc) > 1.0) acc = R(1.0);
   if (r_val(acc) > d.u) {
     for (int i = 0; i < n; ++i) cfg[i] = prop[i];
     return true;
@@ -107,6 +108,7 @@ struct RunOptions {
   double metrop_param;    // box_side | time_step
   uint32_t observables;
   int32_t quirk_vector_div;  // 1: reproduce OperatorValue Vector/Scalar = scalar/array (operator/src/traits.rs:149-150)
+  int32_t nan_reject;        // 0: Rust's NaN-dropping min (a NaN acceptance is accepted); 1: the product's default (rejected)
 };
 
 struct RunResult {
@@ -157,9 +159,9 @@ inline RunResult runner_run(const Wf<double>& wf, const Ham<double>& ham, const 
       for (int e = 0; e < ne; ++e) {
         bool acc;
         if (o.metrop_kind == METROP_BOX)
-          acc = box_move_state(wf, out.cfg.data(), e, o.metrop_param, key, walker, step);
+          acc = box_move_state(wf, out.cfg.data(), e, o.metrop_param, key, walker, step, o.nan_reject != 0);
         else
-          acc = diffuse_move_state(wf, out.cfg.data(), e, o.metrop_param, key, walker, step);
+          acc = diffuse_move_state(wf, out.cfg.data(), e, o.metrop_param, key, walker, step, nullptr, o.nan_reject != 0);
         if (acc) out.acceptance += 1.0 / (double)ne;
         if (want_trace) out.accept.push_back(acc ? 1 : 0);
       }

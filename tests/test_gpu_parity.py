@@ -77,20 +77,27 @@ def test_init_draws_match_oracle(mole, orc):
 
 
 @pytest.mark.parametrize("name", ALL)
-@pytest.mark.parametrize("metrop", ["box", "diffuse"])
+@pytest.mark.parametrize("metrop", ["box", "diffuse", "diffuse_nan_accept"])
 def test_sweep_parity_shared_philox(mole, orc, name, metrop):
     """Identical starting walkers + shared Philox stream: accept/reject decisions bit-exact,
-    E_L traces, stored observables and final configurations within 1e-10."""
+    E_L traces, stored observables and final configurations within 1e-10.  "diffuse_nan_accept" runs
+    the reference-faithful NaN policy (MOLE_COMPAT_NAN_ACCEPT); it matters for the nodal Slater-Jastrow
+    kinds, whose far-from-equilibrium start puts walkers next to nodes (t_high = t_low = 0)."""
     c = cases()[name]
     wf, op = c["make"](mole)
     W, steps, bs = (256, 60, 10) if name in SMALL else (100, 30, 10)
     seed = bytes([7] * 32)
+    nan_accept = metrop.endswith("nan_accept")
+    metrop = metrop.split("_")[0]
     param = (1.0 if metrop == "box" else 0.25) if name in SMALL else (0.4 if metrop == "box" else 0.02)
     m = mole.MetropolisBox(param, seed) if metrop == "box" else mole.MetropolisDiffuse(param, seed)
+    if nan_accept:
+        m.set_compat(mole.ffi.COMPAT_NAN_ACCEPT)
     cfgs = np.array([orc.init_uniform(seed, w, c["ne"]) for w in range(W)])
     obs = orc.OBS_ENERGY | orc.OBS_WFVALUE | orc.OBS_KINETIC | (orc.OBS_PGRAD if c["np"] else 0)
     ref = orc.ensemble_run(c["owf"], c["oham"], orc.run_options(orc.METROP_BOX if metrop == "box" else orc.METROP_DIFFUSE,
-                                                                 param, obs), cfgs, seed, steps, bs)
+                                                                 param, obs, nan_reject=0 if nan_accept else 1),
+                           cfgs, seed, steps, bs)
     ens = mole.Ensemble(W, c["ne"], seed)
     ens.init_uniform(-1.0, 1.0)
     got = ens.sweep(wf, m, op, n_sweeps=steps, n_discard=bs, block_size=bs, observables=obs,
