@@ -3,15 +3,19 @@
 //   f_ee = sum_{i<j} u(R_ij), u(R) = b1 R/(1+b2 R) + b3 R^2 + b4 R^3, R = (1-exp(-kappa r))/kappa
 //   (theory/jastrow.tex:23-31 with the erratum of SURVEY.md §8(c)).
 //
-// Layout: FIVE lanes cooperate on one walker (six walkers per warp, lanes 30/31 idle).  Lane gl owns
-// the up electron gl and the down electron gl: position, cached orbital exponentials, its column of
-// each inverse Slater matrix, grad f and grad ln D live in registers; the pair cache (u, g/r,
-// laplacian term, R, 1/(1+b2 R), 1/r for the 45 pairs), the orbital gradients and a copy of the
-// positions live in shared memory.  A single-electron move re-evaluates only what changed: one
-// orbital row, a Sherman-Morrison update of one 5x5 inverse (refreshed from scratch every sweep),
-// nine Jastrow pairs.  Reductions over the five lanes are warp shuffles in a fixed order.
-// The Metropolis semantics are the reference's (src/metropolis/src/metrop.rs:60-96,150-212),
-// including the Frobenius norm over ALL electrons' drift in t_high / t_low.
+// Layout (v2): FIVE lanes cooperate on one walker, six walkers per warp (lanes 30/31 idle).  Lane gl
+// owns one electron of each spin.  Registers hold the positions, the radial cache (r, 1/r and the three
+// orbital exponentials) and grad f of the two own electrons; shared memory holds, per walker, the pair
+// cache (u, g/r, laplacian term, 1/r, R for the 45 pairs), both inverse Slater matrices, a copy of
+// the positions and a mailbox for the intra-walker exchanges.  The spin being moved always sits in
+// register slot 0 (the slots are swapped between the two halves of a sweep), so there is one copy of
+// the move code.  A single-electron move re-evaluates only what changed: one orbital row, a
+// Sherman-Morrison update of one 5x5 inverse (rebuilt from scratch every sweep), nine Jastrow pairs.
+// All reductions over the five lanes go through the mailbox in a fixed order (deterministic).
+// The per-walker shared-memory stride is 5 (mod 16) doubles, so the unit-stride-in-lane accesses of a
+// warp's 30 active lanes fall on distinct 8-byte banks.
+// Metropolis semantics are the reference's (src/metropolis/src/metrop.rs:60-96,150-212), including
+// the Frobenius norm over ALL electrons' drift in t_high / t_low.
 #pragma once
 #include <cuda_runtime.h>
 #include "mole_internal.h"
@@ -21,15 +25,23 @@ constexpr int SJ_WPW = 6;                       // walkers per warp
 constexpr int SJ_WARPS = 4;
 constexpr int SJ_THREADS = 32 * SJ_WARPS;
 constexpr int SJ_WPB = SJ_WPW * SJ_WARPS;       // walkers per CTA
+constexpr int SJ_MIN_CTAS = 3;                  // CTAs per SM the register budget is tuned for
 constexpr int SJ_NPAIR = 45;
-// shared memory per walker, in doubles
-constexpr int SJ_PC = 6 * SJ_NPAIR;             // pair cache: u, g/r, lap term, R, 1/(1+b2R), 1/r
-constexpr int SJ_GPH = 2 * 15 * 5;              // grad phi_k at every electron, [slot][3k+c][lane]
-constexpr int SJ_XS = 30;                       // positions by slot id
-constexpr int SJ_TSC = 25;                      // transpose scratch for the inverse
-constexpr int SJ_OS = 8;                        // O_k of the current sample
-constexpr int SJ_SMEM_PER_WALKER = SJ_PC + SJ_GPH + SJ_XS + SJ_TSC + SJ_OS;
-constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_SMEM_PER_WALKER * SJ_WPB * sizeof(double);
+constexpr int SJ_PCV = 5;                       // cached values per pair: u, g/r, lap term, 1/r, R
+// shared memory per walker (offsets in doubles)
+constexpr int SJ_OFF_PC = 0;                               // [SJ_PCV][45]
+constexpr int SJ_OFF_XS = SJ_OFF_PC + SJ_PCV * SJ_NPAIR;   // [10][3] positions by slot id (spin*5 + lane)
+constexpr int SJ_OFF_MINV = SJ_OFF_XS + 30;                // [2][5][5] inverse Slater matrices, (spin, k, j)
+constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 48 doubles
+constexpr int SJ_MB = 48;
+constexpr int SJ_STRIDE = 357;                             // >= SJ_OFF_MB + SJ_MB and == 5 (mod 16)
+static_assert(SJ_STRIDE >= SJ_OFF_MB + SJ_MB && SJ_STRIDE % 16 == 5, "per-walker stride");
+constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
+// mailbox slots
+constexpr int MB_XN = 0;      // [3] trial position, [3] = accept uniform
+constexpr int MB_E = 4;       // [3] orbital exponentials at the trial position / exp(df), t_high, t_low
+constexpr int MB_RIN = 8;     // [4][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles)
+constexpr int MB_ROUT = 40;   // [4] reduction outputs / O_k staging (8 doubles)
 constexpr int SJ_NP = 7;
 constexpr int SJ_NACC = 10 + 2 * SJ_NP + SJ_NP * (SJ_NP + 1) / 2;   // 52 compact accumulator entries
 constexpr int SJ_ACC_PER_LANE = (SJ_NACC + 4) / 5;                   // 11
@@ -48,42 +60,41 @@ MOLE_D int sj_pidx(int a, int b) {              // unordered pair of slot ids (0
   return lo * (19 - lo) / 2 + (hi - lo - 1);
 }
 
-struct SjShared {
-  double* pc; double* gph; double* xs; double* tsc; double* os;
-};
-
 struct SjLane {
   int lane, gl, base;
+  int ph;              // spin held in register slot 0 (slot t holds spin t ^ ph)
   bool act;            // this 5-lane group holds a real walker
   bool wr;             // lanes 30/31 alias group 0's shared memory and must never store to it
-  bool val[2];         // slot validity: gl < n_up / gl < n_dn
+  bool val[2];         // slot validity (lane index < number of electrons of that spin)
   double x[2][3];      // own electrons
-  double ec[2][3];     // exp(-zeta_m r) at own electrons
-  double minv[2][5];   // column gl of the inverse Slater matrices
+  double orb[2][5];    // r, 1/r, exp(-z1 r), exp(-z2 r), exp(-z3 r) at own electrons
   double gf[2][3];     // grad_i f
-  double G[2][3];      // grad_i ln D
-  double psi, f;       // replicated over the group
-  double det[2];
+  double psi;          // replicated over the group
+  double* sm;          // this walker's shared-memory region
 };
 
-// sum over the five lanes of a group, fixed order ((v0+v4)+v2)+(v1+v3), result replicated
-MOLE_D double sj_gsum(double v, const SjLane& L) {
-  double y = __shfl_sync(SJ_FULL, v, L.lane + 4);
-  if (L.gl == 0) v += y;
-  y = __shfl_sync(SJ_FULL, v, L.lane + 2);
-  if (L.gl < 2) v += y;
-  y = __shfl_sync(SJ_FULL, v, L.lane + 1);
-  if (L.gl == 0) v += y;
-  return __shfl_sync(SJ_FULL, v, L.base);
-}
-
-struct SjPair { double u, gr, lt, R, iden, ir; };
+MOLE_D int sj_spin_n(const SjConst& c, int spin) { return spin == 0 ? c.nup : c.ndn; }
+MOLE_D bool sj_slot_valid(const SjConst& c, int sid) { return sid < 5 ? sid < c.nup : (sid - 5) < c.ndn; }
+MOLE_D void sj_sync() { __syncwarp(); }
 
 // acceptance.min(1.0) with the NaN policy of include/mole_b200.h (MOLE_COMPAT_NAN_ACCEPT)
 MOLE_D double sj_clamp_acceptance(double a, uint32_t compat) {
   if (isnan(a)) return (compat & MOLE_COMPAT_NAN_ACCEPT) ? 1.0 : 0.0;
   return fmin(a, 1.0);
 }
+
+// sum over the five lanes of a group through the mailbox, lane order 0..4, result replicated
+MOLE_D double sj_gsum(double v, const SjLane& L) {
+  if (L.wr) L.sm[SJ_OFF_MB + MB_RIN + L.gl] = v;
+  sj_sync();
+  double s = L.sm[SJ_OFF_MB + MB_RIN];
+#pragma unroll
+  for (int i = 1; i < 5; ++i) s += L.sm[SJ_OFF_MB + MB_RIN + i];
+  sj_sync();
+  return s;
+}
+
+struct SjPair { double u, gr, lt, ir, R; };
 
 // pair function from the squared distance (theory/jastrow.tex:23-31,45-48,68-71,82-97)
 MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
@@ -93,39 +104,45 @@ MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   o.R = (1.0 - E) * c.ikappa;
   const double den = fma(c.b2, o.R, 1.0);
   const double inv = 1.0 / (den * r);
-  o.iden = inv * r;
+  const double iden = inv * r;
   o.ir = inv * den;
   const double R2 = o.R * o.R;
-  o.u = fma(c.b1 * o.R, o.iden, fma(c.b4 * R2, o.R, c.b3 * R2));
-  const double id2 = o.iden * o.iden;
+  o.u = fma(c.b1 * o.R, iden, fma(c.b4 * R2, o.R, c.b3 * R2));
+  const double id2 = iden * iden;
   const double du = fma(c.b1, id2, fma(3.0 * c.b4, R2, 2.0 * c.b3 * o.R));
-  const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * o.iden, fma(6.0 * c.b4, o.R, 2.0 * c.b3));
+  const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden, fma(6.0 * c.b4, o.R, 2.0 * c.b3));
   const double g = E * du;
   o.gr = g * o.ir;
   o.lt = fma(2.0, o.gr, fma(E * E, d2u, -c.kappa * g));   // div(rhat g) = 2 g/r + dg/dr
   return o;
 }
 
-// orbital values at a point from r and the three exponentials; entries k >= n are zero (padding)
-MOLE_D void sj_phi(const double* x, double r, const double* e, int n, double* phi) {
-  phi[0] = n > 0 ? e[0] : 0.0;
-  phi[1] = n > 1 ? r * e[1] : 0.0;
-  phi[2] = n > 2 ? x[0] * e[2] : 0.0;
-  phi[3] = n > 3 ? x[1] * e[2] : 0.0;
-  phi[4] = n > 4 ? x[2] * e[2] : 0.0;
+// orbital values from the radial cache; entries k >= n are zero (identity padding of the Slater matrix)
+MOLE_D void sj_phi(const double* x, const double* o, int n, double* phi) {
+  phi[0] = n > 0 ? o[2] : 0.0;
+  phi[1] = n > 1 ? o[0] * o[3] : 0.0;
+  phi[2] = n > 2 ? x[0] * o[4] : 0.0;
+  phi[3] = n > 3 ? x[1] * o[4] : 0.0;
+  phi[4] = n > 4 ? x[2] * o[4] : 0.0;
 }
-// grad phi_k, laid out [3k+c]
-MOLE_D void sj_gphi(const SjConst& c, const double* x, double r, double ir, const double* e, double* g) {
-  const double c0 = -c.z1 * e[0] * ir, c1 = (1.0 - c.z2 * r) * e[1] * ir, c2 = -c.z3 * ir;
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    g[q] = c0 * x[q];
-    g[3 + q] = c1 * x[q];
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int q = 0; q < 3; ++q) g[6 + 3 * a + q] = e[2] * (c2 * x[a] * x[q] + (a == q ? 1.0 : 0.0));
+
+// grad_i ln D = sum_k grad phi_k(r_i) Minv[k][i] from the radial cache and the electron's column m[]:
+//   grad phi_0 = -z1 e1 x/r,  grad phi_1 = (1 - z2 r) e2 x/r,  grad phi_{2+a} = e3 (e_a - z3 x_a x/r)
+MOLE_D void sj_gradlnD(const SjConst& c, const double* x, const double* o, const double* m, double* G) {
+  const double xm = fma(x[2], m[4], fma(x[1], m[3], x[0] * m[2]));
+  const double s = (fma(-c.z1 * o[2], m[0], (1.0 - c.z2 * o[0]) * o[3] * m[1]) - c.z3 * o[4] * xm) * o[1];
+  G[0] = fma(s, x[0], o[4] * m[2]);
+  G[1] = fma(s, x[1], o[4] * m[3]);
+  G[2] = fma(s, x[2], o[4] * m[4]);
+}
+
+MOLE_D void sj_radial(const SjConst& c, const double* x, bool valid, double* o) {
+  const double r2 = fma(x[2], x[2], fma(x[1], x[1], x[0] * x[0]));
+  o[0] = valid ? sqrt(r2) : 1.0;
+  o[1] = 1.0 / o[0];
+  o[2] = exp(-c.z1 * o[0]);
+  o[3] = exp(-c.z2 * o[0]);
+  o[4] = exp(-c.z3 * o[0]);
 }
 
 // Gauss-Jordan inverse of the 5x5 matrix whose row gl is M[] (row = lane), partial pivoting by
@@ -177,171 +194,148 @@ MOLE_D void sj_invert(double* M, double* out, double& det, const SjLane& L) {
   det = (inv & 1) ? -d : d;
 }
 
-// inverse Slater matrix, determinant and grad ln D of spin slot T from the cached exponentials
-template <int T>
-MOLE_D void sj_refresh_spin(const SjConst& c, SjLane& L, const SjShared& sm) {
-  const int n = T == 0 ? c.nup : c.ndn;
+// rebuild the inverse Slater matrix of register slot t from scratch; returns the determinant
+MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t) {
+  const int spin = t ^ L.ph;
+  const int n = sj_spin_n(c, spin);
   double phi[5];
-  const double r = sqrt(fma(L.x[T][2], L.x[T][2], fma(L.x[T][1], L.x[T][1], L.x[T][0] * L.x[T][0])));
-  sj_phi(L.x[T], r, L.ec[T], n, phi);
+  sj_phi(L.x[t], L.orb[t], n, phi);
+  double* tsc = L.sm + SJ_OFF_MB + MB_RIN;
 #pragma unroll
   for (int k = 0; k < 5; ++k)
-    if (L.wr) sm.tsc[L.gl * 5 + k] = L.val[T] ? phi[k] : (k == L.gl ? 1.0 : 0.0);   // A[i=gl][k], identity padding
-  __syncwarp();
-  double M[5];
+    if (L.wr) tsc[L.gl * 5 + k] = L.val[t] ? phi[k] : (k == L.gl ? 1.0 : 0.0);   // A[i=gl][k], identity padding
+  sj_sync();
+  double M[5], out[5], det;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) M[i] = sm.tsc[i * 5 + L.gl];   // row gl of A^T
-  __syncwarp();
-  sj_invert(M, L.minv[T], L.det[T], L);
+  for (int i = 0; i < 5; ++i) M[i] = tsc[i * 5 + L.gl];   // row gl of A^T
+  sj_sync();
+  sj_invert(M, out, det, L);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) s = fma(sm.gph[(T * 15 + 3 * k + q) * 5 + L.gl], L.minv[T][k], s);
-    L.G[T][q] = s;
-  }
+  for (int k = 0; k < 5; ++k)
+    if (L.wr) L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl] = out[k];          // Minv[k][j = gl]
+  sj_sync();
+  return det;
 }
 
-MOLE_D bool sj_slot_valid(const SjConst& c, int sid) { return sid < 5 ? sid < c.nup : (sid - 5) < c.ndn; }
+// once per sweep: both inverses from scratch (bounds the Sherman-Morrison round-off), psi re-derived
+MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
+  const double d0 = sj_refresh_slot(c, L, 0);
+  const double d1 = sj_refresh_slot(c, L, 1);
+  double fl = 0.0;
+  for (int p = L.gl; p < SJ_NPAIR; p += 5)
+    if (sj_slot_valid(c, c_sj_pair_a[p]) && sj_slot_valid(c, c_sj_pair_b[p])) fl += L.sm[SJ_OFF_PC + p];
+  L.psi = d0 * d1 * exp(sj_gsum(fl, L));
+}
 
-// full (re)initialisation of the cooperative state from the positions in L.x
-MOLE_D void sj_init(const SjConst& c, SjLane& L, const SjShared& sm) {
+// full initialisation of the cooperative state from the positions in L.x (slot t = spin t)
+MOLE_D void sj_init(const SjConst& c, SjLane& L) {
+  L.ph = 0;
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const double r = sqrt(fma(L.x[t][2], L.x[t][2], fma(L.x[t][1], L.x[t][1], L.x[t][0] * L.x[t][0])));
-    const double rs = L.val[t] ? r : 1.0;
-    const double ir = 1.0 / rs;
-    L.ec[t][0] = exp(-c.z1 * rs);
-    L.ec[t][1] = exp(-c.z2 * rs);
-    L.ec[t][2] = exp(-c.z3 * rs);
-    double g[15];
-    sj_gphi(c, L.x[t], rs, ir, L.ec[t], g);
-#pragma unroll
-    for (int q = 0; q < 15; ++q)
-      if (L.wr) sm.gph[(t * 15 + q) * 5 + L.gl] = g[q];
+    sj_radial(c, L.x[t], L.val[t], L.orb[t]);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-      if (L.wr) sm.xs[(t * 5 + L.gl) * 3 + q] = L.x[t][q];
+      if (L.wr) L.sm[SJ_OFF_XS + (t * 5 + L.gl) * 3 + q] = L.x[t][q];
   }
-  __syncwarp();
-  sj_refresh_spin<0>(c, L, sm);
-  sj_refresh_spin<1>(c, L, sm);
+  sj_sync();
   // Jastrow from scratch: every lane sums over the partners of its own electrons
-  double fl = 0.0;
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int a = t * 5 + L.gl;
     double gx = 0.0, gy = 0.0, gz = 0.0;
     for (int b = 0; b < 10; ++b) {
       const bool pv = L.val[t] && b != a && sj_slot_valid(c, b);
-      const double dx = L.x[t][0] - sm.xs[b * 3], dy = L.x[t][1] - sm.xs[b * 3 + 1], dz = L.x[t][2] - sm.xs[b * 3 + 2];
+      const double* xb = L.sm + SJ_OFF_XS + b * 3;
+      const double dx = L.x[t][0] - xb[0], dy = L.x[t][1] - xb[1], dz = L.x[t][2] - xb[2];
       const double r2 = pv ? fma(dz, dz, fma(dy, dy, dx * dx)) : 1.0;
       const SjPair P = sj_pair(c, r2);
       if (pv) {
         gx = fma(P.gr, dx, gx); gy = fma(P.gr, dy, gy); gz = fma(P.gr, dz, gz);
         if (a < b && L.wr) {
-          const int p = sj_pidx(a, b);
-          sm.pc[p] = P.u; sm.pc[SJ_NPAIR + p] = P.gr; sm.pc[2 * SJ_NPAIR + p] = P.lt;
-          sm.pc[3 * SJ_NPAIR + p] = P.R; sm.pc[4 * SJ_NPAIR + p] = P.iden; sm.pc[5 * SJ_NPAIR + p] = P.ir;
-          fl += P.u;
+          double* pc = L.sm + SJ_OFF_PC + sj_pidx(a, b);
+          pc[0] = P.u; pc[SJ_NPAIR] = P.gr; pc[2 * SJ_NPAIR] = P.lt; pc[3 * SJ_NPAIR] = P.ir; pc[4 * SJ_NPAIR] = P.R;
         }
       }
     }
     L.gf[t][0] = gx; L.gf[t][1] = gy; L.gf[t][2] = gz;
   }
-  __syncwarp();
-  L.f = sj_gsum(fl, L);
-  L.psi = L.det[0] * L.det[1] * exp(L.f);
+  sj_sync();
+  sj_refresh(c, L);
 }
 
-// once per sweep: rebuild the inverses from scratch (bounds the Sherman-Morrison round-off) and
-// re-sum the Jastrow exponent from the pair cache
-MOLE_D void sj_refresh(const SjConst& c, SjLane& L, const SjShared& sm) {
-  sj_refresh_spin<0>(c, L, sm);
-  sj_refresh_spin<1>(c, L, sm);
-  double fl = 0.0;
-  for (int p = L.gl; p < SJ_NPAIR; p += 5)
-    if (sj_slot_valid(c, c_sj_pair_a[p]) && sj_slot_valid(c, c_sj_pair_b[p])) fl += sm.pc[p];
-  L.f = sj_gsum(fl, L);
-  L.psi = L.det[0] * L.det[1] * exp(L.f);
-}
-
-// Metropolis::move_state for electron `el` of spin slot S.  d = the pre-generated draws of THIS lane's
-// slot-S electron (only the owner's are used).  Returns the accept decision (uniform over the group).
-template <int S, int METROP>
-MOLE_D bool sj_move(const SjConst& c, SjLane& L, const SjShared& sm, int el, const MoveDraw& d, double param, double sd,
-                    uint32_t compat) {
-  const int n = S == 0 ? c.nup : c.ndn;
-  const int own = L.base + el;
-  const bool isown = (L.gl == el);
-  const int sid_e = S * 5 + el;
-  double xo[3], xn[3];
+// exchange the two register slots (the spin to be moved must sit in slot 0)
+MOLE_D void sj_swap_slots(SjLane& L) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
-    xo[q] = L.x[S][q];
-    if (METROP == MOLE_METROP_BOX) {
-      const double lo = -0.5 * param, scale = 0.5 * param - lo;
-      const double u = q == 0 ? d.a : (q == 1 ? d.b : d.c);
-      xn[q] = xo[q] + (lo + scale * u);                                   // metrop.rs:63-68
-    } else {
+    double t = L.x[0][q]; L.x[0][q] = L.x[1][q]; L.x[1][q] = t;
+    t = L.gf[0][q]; L.gf[0][q] = L.gf[1][q]; L.gf[1][q] = t;
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) { const double t = L.orb[0][q]; L.orb[0][q] = L.orb[1][q]; L.orb[1][q] = t; }
+  const bool v = L.val[0]; L.val[0] = L.val[1]; L.val[1] = v;
+  L.ph ^= 1;
+}
+
+// Metropolis::move_state for electron `el` of the spin in slot 0.  d = the pre-generated draws of THIS
+// lane's slot-0 electron (only the owner's are used).  Returns the accept decision (uniform over the group).
+template <int METROP>
+MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, double param, double sd, double inv2tau,
+                    uint32_t compat) {
+  const int spin = L.ph;
+  const int n = sj_spin_n(c, spin);
+  const bool isown = (L.gl == el);
+  const int sid_e = spin * 5 + el;
+  double* const mb = L.sm + SJ_OFF_MB;
+  const double* const minv = L.sm + SJ_OFF_MINV + spin * 25;
+  // this lane's column (cg) and the moved electron's column (ce) of the inverse
+  double cg[5], ce[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { cg[k] = minv[k * 5 + L.gl]; ce[k] = minv[k * 5 + el]; }
+  // drift of this lane's slot-0 electron at the current configuration
+  double Gown[3];
+  sj_gradlnD(c, L.x[0], L.orb[0], cg, Gown);
+  // ---- owner proposes, everybody reads the trial point
+  if (isown && L.wr) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
       const double xi = q == 0 ? d.a : (q == 1 ? d.b : d.c);
-      xn[q] = (xo[q] + (L.G[S][q] + L.gf[S][q]) * param) + sd * xi;       // metrop.rs:155-160
-    }
-    xn[q] = __shfl_sync(SJ_FULL, xn[q], own);
-    xo[q] = __shfl_sync(SJ_FULL, xo[q], own);
-  }
-  const double u_acc = __shfl_sync(SJ_FULL, d.u, own);
-  // orbitals of the moved electron at the trial position (one exponential per lane, then shared)
-  const double rn = sqrt(fma(xn[2], xn[2], fma(xn[1], xn[1], xn[0] * xn[0])));
-  const double irn = 1.0 / rn;
-  const double zm = L.gl == 0 ? c.z1 : (L.gl == 1 ? c.z2 : c.z3);
-  const double ex = exp(-zm * rn);
-  double en[3];
-  en[0] = __shfl_sync(SJ_FULL, ex, L.base);
-  en[1] = __shfl_sync(SJ_FULL, ex, L.base + 1);
-  en[2] = __shfl_sync(SJ_FULL, ex, L.base + 2);
-  double phin[5];
-  sj_phi(xn, rn, en, n, phin);
-  // determinant ratio and Sherman-Morrison update of this lane's column
-  double v = 0.0;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) v = fma(phin[k], L.minv[S][k], v);
-  const double ratio = __shfl_sync(SJ_FULL, v, own);
-  const double inv_ratio = 1.0 / ratio;
-  const double vr = v * inv_ratio;
-  double mt[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const double ce = __shfl_sync(SJ_FULL, L.minv[S][k], own);
-    mt[k] = isown ? ce * inv_ratio : fma(-ce, vr, L.minv[S][k]);
-  }
-  // trial grad ln D of this lane's slot-S electron
-  double gn[15];
-  sj_gphi(c, xn, rn, irn, en, gn);
-  double Gt[3] = {0.0, 0.0, 0.0};
-  if (METROP == MOLE_METROP_DIFFUSE) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const double gk = isown ? gn[3 * k + q] : sm.gph[(S * 15 + 3 * k + q) * 5 + L.gl];
-        Gt[q] = fma(gk, mt[k], Gt[q]);
+      if (METROP == MOLE_METROP_BOX) {
+        const double lo = -0.5 * param, scale = 0.5 * param - lo;
+        mb[MB_XN + q] = L.x[0][q] + (lo + scale * xi);                              // metrop.rs:63-68
+      } else {
+        mb[MB_XN + q] = (L.x[0][q] + (Gown[q] + L.gf[0][q]) * param) + sd * xi;     // metrop.rs:155-160
       }
+    }
+    mb[MB_XN + 3] = d.u;
   }
-  // nine Jastrow pairs of the moved electron, two per lane
+  sj_sync();
+  double xn[3], xo[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { xn[q] = mb[MB_XN + q]; xo[q] = L.sm[SJ_OFF_XS + sid_e * 3 + q]; }
+  const double u_acc = mb[MB_XN + 3];
+  // ---- orbitals of the moved electron at the trial point: one exponential per lane, then shared
+  double on[5];
+  on[0] = sqrt(fma(xn[2], xn[2], fma(xn[1], xn[1], xn[0] * xn[0])));
+  on[1] = 1.0 / on[0];
+  {
+    const double zm = L.gl == 0 ? c.z1 : (L.gl == 1 ? c.z2 : c.z3);
+    const double ex = exp(-zm * on[0]);
+    if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = ex;
+  }
+  // ---- nine Jastrow pairs of the moved electron, two per lane (independent of the exchange above)
   double dfl = 0.0, ge[3] = {0.0, 0.0, 0.0}, gft[2][3];
   SjPair P[2];
   int pid[2];
   bool pv[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const int b = t * 5 + L.gl;
-    pv[t] = L.val[t] && !(t == S && isown);
+    const int b = (t ^ L.ph) * 5 + L.gl;
+    pv[t] = L.val[t] && !(t == 0 && isown);
     pid[t] = pv[t] ? sj_pidx(sid_e, b) : 0;
     const double dnx = xn[0] - L.x[t][0], dny = xn[1] - L.x[t][1], dnz = xn[2] - L.x[t][2];
     const double r2 = pv[t] ? fma(dnz, dnz, fma(dny, dny, dnx * dnx)) : 1.0;
     P[t] = sj_pair(c, r2);
-    const double u_old = sm.pc[pid[t]], gr_old = sm.pc[SJ_NPAIR + pid[t]];
+    const double u_old = L.sm[SJ_OFF_PC + pid[t]], gr_old = L.sm[SJ_OFF_PC + SJ_NPAIR + pid[t]];
     const double m = pv[t] ? 1.0 : 0.0;
     dfl = fma(m, P[t].u - u_old, dfl);
     const double gn_ = m * P[t].gr, go_ = m * gr_old;
@@ -351,155 +345,168 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, const SjShared& sm, int el, con
     gft[t][2] = L.gf[t][2] + go_ * (xo[2] - L.x[t][2]) - gn_ * dnz;
     ge[0] = fma(gn_, dnx, ge[0]); ge[1] = fma(gn_, dny, ge[1]); ge[2] = fma(gn_, dnz, ge[2]);
   }
-  const double df = sj_gsum(dfl, L);
-  bool node;
-  double A;
-  if (METROP == MOLE_METROP_DIFFUSE) {
+  // reduction round 1 inputs: df and grad_e f at the trial point (summed from scratch)
+  if (L.wr) {
+    mb[MB_RIN + L.gl] = dfl;
+    mb[MB_RIN + 5 + L.gl] = ge[0];
+    mb[MB_RIN + 10 + L.gl] = ge[1];
+    mb[MB_RIN + 15 + L.gl] = ge[2];
+  }
+  sj_sync();
+  on[2] = mb[MB_E]; on[3] = mb[MB_E + 1]; on[4] = mb[MB_E + 2];
+  if (L.gl < 4) {
+    const double* r = mb + MB_RIN + 5 * L.gl;
+    const double s = (((r[0] + r[1]) + r[2]) + r[3]) + r[4];
+    if (L.wr) mb[MB_ROUT + L.gl] = s;
+  }
+  // ---- determinant ratio and Sherman-Morrison update of this lane's column
+  double phin[5];
+  sj_phi(xn, on, n, phin);
+  double v = 0.0, ratio = 0.0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const double t = sj_gsum(ge[q], L);           // grad_e f at the trial position, summed from scratch
-      if (isown) gft[S][q] = t;
-    }
+  for (int k = 0; k < 5; ++k) { v = fma(phin[k], cg[k], v); ratio = fma(phin[k], ce[k], ratio); }
+  const double inv_ratio = 1.0 / ratio;
+  const double vr = v * inv_ratio;
+  double mt[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) mt[k] = isown ? ce[k] * inv_ratio : fma(-ce[k], vr, cg[k]);
+  sj_sync();
+  const double df = mb[MB_ROUT];
+  bool acc;
+  double q;
+  if (METROP == MOLE_METROP_DIFFUSE) {
+    if (isown) { gft[0][0] = mb[MB_ROUT + 1]; gft[0][1] = mb[MB_ROUT + 2]; gft[0][2] = mb[MB_ROUT + 3]; }
     // Frobenius norms over ALL electrons' drift (metrop.rs:182-193)
+    double Gt[3], G1[3], c1[5];
+    sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], mt, Gt);
+    const double* minv1 = L.sm + SJ_OFF_MINV + (spin ^ 1) * 25;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) c1[k] = minv1[k * 5 + L.gl];
+    sj_gradlnD(c, L.x[1], L.orb[1], c1, G1);
     double sh = 0.0, sl = 0.0;
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const double vn = (t == S ? Gt[q] : L.G[t][q]) + gft[t][q];
-        const double vo = L.G[t][q] + L.gf[t][q];
-        const double dx = (t == S && isown) ? xo[q] - xn[q] : 0.0;
-        const double a = dx - vn * param, b = -dx - vo * param;
-        const double m = L.val[t] ? 1.0 : 0.0;
-        sh = fma(m * a, a, sh);
-        sl = fma(m * b, b, sl);
-      }
-    sh = sj_gsum(sh, L);
-    sl = sj_gsum(sl, L);
-    // exp(df), t_high, t_low: one exponential per lane
-    const double arg = L.gl == 0 ? df : (L.gl == 1 ? -sh / (2.0 * param) : -sl / (2.0 * param));
+    for (int qq = 0; qq < 3; ++qq) {
+      const double dx = isown ? xo[qq] - xn[qq] : 0.0;
+      const double a0 = dx - (Gt[qq] + gft[0][qq]) * param, b0 = -dx - (Gown[qq] + L.gf[0][qq]) * param;
+      const double a1 = (G1[qq] + gft[1][qq]) * param, b1 = (G1[qq] + L.gf[1][qq]) * param;
+      const double m0 = L.val[0] ? 1.0 : 0.0, m1 = L.val[1] ? 1.0 : 0.0;
+      sh = fma(m0 * a0, a0, fma(m1 * a1, a1, sh));
+      sl = fma(m0 * b0, b0, fma(m1 * b1, b1, sl));
+    }
+    if (L.wr) { mb[MB_RIN + L.gl] = sh; mb[MB_RIN + 5 + L.gl] = sl; }
+    sj_sync();
+    // exp(df), t_high, t_low: one exponential per lane (lanes 0, 1, 2)
+    double arg = df;
+    if (L.gl == 1 || L.gl == 2) {
+      const double* r = mb + MB_RIN + 5 * (L.gl - 1);
+      arg = -((((r[0] + r[1]) + r[2]) + r[3]) + r[4]) * inv2tau;
+    }
     const double e3 = exp(arg);
-    const double ef = __shfl_sync(SJ_FULL, e3, L.base);
-    const double th = __shfl_sync(SJ_FULL, e3, L.base + 1);
-    const double tl = __shfl_sync(SJ_FULL, e3, L.base + 2);
-    const double q = ratio * ef;                               // psi'/psi
-    node = !(ratio > 0.0);                                     // signum(psi') != signum(psi) or NaN, :178-180
-    A = sj_clamp_acceptance(th * (q * q) / tl, compat);        // :195
-    if (!node && A > u_acc) L.psi *= q;
+    if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = e3;
+    sj_sync();
+    const double ef = mb[MB_E], th = mb[MB_E + 1], tl = mb[MB_E + 2];
+    q = ratio * ef;                                            // psi'/psi
+    const bool node = !(ratio > 0.0);                          // signum(psi') != signum(psi) or NaN, :178-180
+    const double A = sj_clamp_acceptance(th * (q * q) / tl, compat);   // :195
+    acc = !node && (A > u_acc);
   } else {
-    const double q = ratio * exp(df);
-    node = false;
-    A = sj_clamp_acceptance(q * q, compat);                    // metrop.rs:80
-    if (A > u_acc) L.psi *= q;
+    q = ratio * exp(df);
+    acc = sj_clamp_acceptance(q * q, compat) > u_acc;          // metrop.rs:80
+    if (isown) { gft[0][0] = mb[MB_ROUT + 1]; gft[0][1] = mb[MB_ROUT + 2]; gft[0][2] = mb[MB_ROUT + 3]; }
   }
-  const bool acc = !node && (A > u_acc);
   if (acc) {
     if (isown) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) { L.x[S][q] = xn[q]; L.ec[S][q] = en[q]; }
-      if (L.act) {
+      for (int qq = 0; qq < 3; ++qq) L.x[0][qq] = xn[qq];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) sm.xs[sid_e * 3 + q] = xn[q];
+      for (int qq = 0; qq < 5; ++qq) L.orb[0][qq] = on[qq];
+      if (L.act)
 #pragma unroll
-        for (int q = 0; q < 15; ++q) sm.gph[(S * 15 + q) * 5 + L.gl] = gn[q];
-      }
+        for (int qq = 0; qq < 3; ++qq) L.sm[SJ_OFF_XS + sid_e * 3 + qq] = xn[qq];
+    }
+    if (L.act) {
+      double* mw = L.sm + SJ_OFF_MINV + spin * 25;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) mw[k * 5 + L.gl] = mt[k];
     }
 #pragma unroll
-    for (int k = 0; k < 5; ++k) L.minv[S][k] = mt[k];
-    L.det[S] *= ratio;
-    L.f += df;
-    if (METROP == MOLE_METROP_DIFFUSE) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) { L.G[S][q] = Gt[q]; L.gf[0][q] = gft[0][q]; L.gf[1][q] = gft[1][q]; }
-    }
+    for (int qq = 0; qq < 3; ++qq) { L.gf[0][qq] = gft[0][qq]; L.gf[1][qq] = gft[1][qq]; }
+    L.psi *= q;
 #pragma unroll
     for (int t = 0; t < 2; ++t)
       if (pv[t] && L.act) {
-        const int p = pid[t];
-        sm.pc[p] = P[t].u; sm.pc[SJ_NPAIR + p] = P[t].gr; sm.pc[2 * SJ_NPAIR + p] = P[t].lt;
-        sm.pc[3 * SJ_NPAIR + p] = P[t].R; sm.pc[4 * SJ_NPAIR + p] = P[t].iden; sm.pc[5 * SJ_NPAIR + p] = P[t].ir;
+        double* pc = L.sm + SJ_OFF_PC + pid[t];
+        pc[0] = P[t].u; pc[SJ_NPAIR] = P[t].gr; pc[2 * SJ_NPAIR] = P[t].lt; pc[3 * SJ_NPAIR] = P[t].ir; pc[4 * SJ_NPAIR] = P[t].R;
       }
   }
-  __syncwarp();
+  sj_sync();
   return acc;
-}
-
-// For the box sampler grad f / grad ln D are not maintained by the moves; rebuild them before sampling.
-MOLE_D void sj_rebuild_gradients(const SjConst& c, SjLane& L, const SjShared& sm) {
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int a = t * 5 + L.gl;
-    double gx = 0.0, gy = 0.0, gz = 0.0;
-    for (int b = 0; b < 10; ++b) {
-      const bool pv = L.val[t] && b != a && sj_slot_valid(c, b);
-      const double gr = pv ? sm.pc[SJ_NPAIR + sj_pidx(a, b)] : 0.0;
-      gx = fma(gr, L.x[t][0] - sm.xs[b * 3], gx);
-      gy = fma(gr, L.x[t][1] - sm.xs[b * 3 + 1], gy);
-      gz = fma(gr, L.x[t][2] - sm.xs[b * 3 + 2], gz);
-    }
-    L.gf[t][0] = gx; L.gf[t][1] = gy; L.gf[t][2] = gz;
-  }
 }
 
 // Local quantities of the current configuration:
 //   kin = -0.5 sum_i lap_i psi / psi,  pot = V (so that E_L = kin + pot),  O[k] = d ln psi / d p_k
+// Gout (optional): grad ln D of the two own electrons.
 template <bool OPT>
-MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, const SjShared& sm, double& kin, double& pot,
-                       double* O) {
+MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& kin, double& pot, double* O,
+                       double (*Gout)[3] = nullptr) {
   double kl = 0.0, vl = 0.0, dz[3] = {0.0, 0.0, 0.0};
   const bool want_ion = h.kind == MOLE_OP_IONIC_POT || h.kind == MOLE_OP_IONIC || h.kind == MOLE_OP_ELECTRONIC;
   const bool want_ee = h.kind == MOLE_OP_ELEC_POT || h.kind == MOLE_OP_ELECTRONIC;
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const int a = t * 5 + L.gl;
-    const int n = t == 0 ? c.nup : c.ndn;
+    const int spin = t ^ L.ph;
+    const int a = spin * 5 + L.gl;
+    const int n = sj_spin_n(c, spin);
     const double* x = L.x[t];
-    const double r2 = fma(x[2], x[2], fma(x[1], x[1], x[0] * x[0]));
-    const double r = L.val[t] ? sqrt(r2) : 1.0, ir = 1.0 / r;
-    const double* e = L.ec[t];
-    // lap phi_k
-    double lp[5];
-    lp[0] = c.z1 * e[0] * (c.z1 - 2.0 * ir);
-    lp[1] = (c.z2 * c.z2 * r - 4.0 * c.z2 + 2.0 * ir) * e[1];
-    const double cp = e[2] * (c.z3 * c.z3 - 4.0 * c.z3 * ir);
-    lp[2] = x[0] * cp; lp[3] = x[1] * cp; lp[4] = x[2] * cp;
-    double lapD = 0.0;
+    const double* o = L.orb[t];
+    const double r = o[0], ir = o[1];
+    double m[5], G[3];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) lapD = fma(k < n ? lp[k] : 0.0, L.minv[t][k], lapD);
+    for (int k = 0; k < 5; ++k) m[k] = L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl];
+    sj_gradlnD(c, x, o, m, G);
+    if (Gout) { Gout[t][0] = G[0]; Gout[t][1] = G[1]; Gout[t][2] = G[2]; }
+    // lap phi_k
+    const double cp = o[4] * (c.z3 * c.z3 - 4.0 * c.z3 * ir);
+    double lapD = (0 < n ? c.z1 * o[2] * (c.z1 - 2.0 * ir) : 0.0) * m[0];
+    lapD = fma(1 < n ? (c.z2 * c.z2 * r - 4.0 * c.z2 + 2.0 * ir) * o[3] : 0.0, m[1], lapD);
+    lapD = fma(2 < n ? x[0] * cp : 0.0, m[2], lapD);
+    lapD = fma(3 < n ? x[1] * cp : 0.0, m[3], lapD);
+    lapD = fma(4 < n ? x[2] * cp : 0.0, m[4], lapD);
     double Lf = 0.0;
     for (int b = 0; b < 10; ++b) {
       const bool pv = b != a && sj_slot_valid(c, b);
-      Lf += pv ? sm.pc[2 * SJ_NPAIR + sj_pidx(a, b)] : 0.0;
+      Lf += pv ? L.sm[SJ_OFF_PC + 2 * SJ_NPAIR + sj_pidx(a, pv ? b : (a == 0 ? 1 : 0))] : 0.0;
     }
-    const double gg = L.G[t][0] * L.gf[t][0] + L.G[t][1] * L.gf[t][1] + L.G[t][2] * L.gf[t][2];
+    const double gg = G[0] * L.gf[t][0] + G[1] * L.gf[t][1] + G[2] * L.gf[t][2];
     const double ff = L.gf[t][0] * L.gf[t][0] + L.gf[t][1] * L.gf[t][1] + L.gf[t][2] * L.gf[t][2];
-    const double m = L.val[t] ? 1.0 : 0.0;
-    kl = fma(m, lapD + 2.0 * gg + Lf + ff, kl);
+    const double mk = L.val[t] ? 1.0 : 0.0;
+    kl = fma(mk, lapD + 2.0 * gg + Lf + ff, kl);
     if (want_ion) {                                              // IonicPotential::value, operator.rs:25-36
       double p = 0.0;
       for (int i = 0; i < h.n_ions; ++i) {
         const double dx = x[0] - h.ion_pos[3 * i], dy = x[1] - h.ion_pos[3 * i + 1], dzz = x[2] - h.ion_pos[3 * i + 2];
         p -= h.ion_z[i] / sqrt(fma(dzz, dzz, fma(dy, dy, dx * dx)));
       }
-      vl = fma(m, p, vl);
+      vl = fma(mk, p, vl);
     }
-    if (h.kind == MOLE_OP_HARMONIC) vl = fma(m * 0.5 * h.frequency * h.frequency, r2, vl);
+    if (h.kind == MOLE_OP_HARMONIC) vl = fma(mk * 0.5 * h.frequency * h.frequency, r * r, vl);
     if (OPT) {                                                   // d ln D / d zeta = tr(A^-1 dA)
-      const double d0 = -r * e[0], d1 = -r * r * e[1], dp = -r * e[2];
-      dz[0] = fma(m * (0 < n ? d0 : 0.0), L.minv[t][0], dz[0]);
-      dz[1] = fma(m * (1 < n ? d1 : 0.0), L.minv[t][1], dz[1]);
-      dz[2] = fma(m * (2 < n ? dp * x[0] : 0.0), L.minv[t][2], dz[2]);
-      dz[2] = fma(m * (3 < n ? dp * x[1] : 0.0), L.minv[t][3], dz[2]);
-      dz[2] = fma(m * (4 < n ? dp * x[2] : 0.0), L.minv[t][4], dz[2]);
+      const double d0 = -r * o[2], d1 = -r * r * o[3], dp = -r * o[4];
+      dz[0] = fma(mk * (0 < n ? d0 : 0.0), m[0], dz[0]);
+      dz[1] = fma(mk * (1 < n ? d1 : 0.0), m[1], dz[1]);
+      dz[2] = fma(mk * (2 < n ? dp * x[0] : 0.0), m[2], dz[2]);
+      dz[2] = fma(mk * (3 < n ? dp * x[1] : 0.0), m[3], dz[2]);
+      dz[2] = fma(mk * (4 < n ? dp * x[2] : 0.0), m[4], dz[2]);
     }
   }
   // pair sums: V_ee and df/db
   double db[4] = {0.0, 0.0, 0.0, 0.0};
   for (int p = L.gl; p < SJ_NPAIR; p += 5) {
     if (!(sj_slot_valid(c, c_sj_pair_a[p]) && sj_slot_valid(c, c_sj_pair_b[p]))) continue;
-    if (want_ee) vl += sm.pc[5 * SJ_NPAIR + p];                  // ElectronicPotential::value, operator.rs:80-90
+    if (want_ee) vl += L.sm[SJ_OFF_PC + 3 * SJ_NPAIR + p];       // ElectronicPotential::value, operator.rs:80-90
     if (OPT) {
-      const double R = sm.pc[3 * SJ_NPAIR + p], id = sm.pc[4 * SJ_NPAIR + p];
+      const double R = L.sm[SJ_OFF_PC + 4 * SJ_NPAIR + p];
+      const double id = 1.0 / fma(c.b2, R, 1.0);
       db[0] = fma(R, id, db[0]);                                 // jastrow.tex:109-119
       db[1] = fma(-c.b1 * R * R, id * id, db[1]);
       db[2] = fma(R, R, db[2]);
@@ -530,20 +537,21 @@ MOLE_D SjConst sj_const(const WfParams& p) {
   return c;
 }
 
-MOLE_D void sj_lane_setup(SjLane& L, const SjConst& c, SjShared& sm, double* smem, int64_t w, int64_t W) {
+MOLE_D void sj_lane_setup(SjLane& L, const SjConst& c, double* smem, int64_t w, int64_t W) {
   L.lane = threadIdx.x & 31;
   const int g = L.lane / 5;
   L.gl = L.lane - 5 * g;
   L.base = 5 * g;
+  L.ph = 0;
   L.act = (g < SJ_WPW) && (w < W);
   L.wr = g < SJ_WPW;
   L.val[0] = L.gl < c.nup;
   L.val[1] = L.gl < c.ndn;
   const int slot = (threadIdx.x >> 5) * SJ_WPW + (g < SJ_WPW ? g : 0);   // idle lanes alias group 0 (loads only)
-  double* b = smem + (size_t)slot * SJ_SMEM_PER_WALKER;
-  sm.pc = b; sm.gph = b + SJ_PC; sm.xs = sm.gph + SJ_GPH; sm.tsc = sm.xs + SJ_XS; sm.os = sm.tsc + SJ_TSC;
+  L.sm = smem + (size_t)slot * SJ_STRIDE;
 }
 
+// global <-> registers; slot t must hold spin t (L.ph == 0)
 MOLE_D void sj_load(SjLane& L, const SjConst& c, const double* x, int64_t w, int64_t W) {
   const int64_t wc = w < W ? w : W - 1;
 #pragma unroll
@@ -565,6 +573,32 @@ MOLE_D void sj_store(const SjLane& L, const SjConst& c, double* x, int64_t w, in
   }
 }
 
+// one sweep: N_e single-electron moves, spin up then spin down (Sampler::move_state, samplers.rs:106-117)
+// returns the number of accepted moves (uniform over the group)
+template <int METROP>
+MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid, uint32_t step, double param, double sd,
+                          double inv2tau, uint32_t compat, uint8_t* tr_accept, size_t tr_stride) {
+  int n_acc = 0;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int spin = L.ph;
+    const int n = sj_spin_n(c, spin);
+    const int cfg_e = spin == 0 ? L.gl : c.nup + L.gl;
+    // draws of this lane's slot-0 electron, keyed by the electron's index in the configuration
+    MoveDraw d;
+    if (METROP == MOLE_METROP_BOX) d = mole_draw_uniform4(key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
+    else d = mole_draw_normal3_uniform1(key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
+#pragma unroll 1
+    for (int el = 0; el < n; ++el) {
+      const bool ok = sj_move<METROP>(c, L, el, d, param, sd, inv2tau, compat);
+      n_acc += ok ? 1 : 0;
+      if (tr_accept && L.act && L.gl == 0) tr_accept[(size_t)(spin == 0 ? el : c.nup + el) * tr_stride] = ok ? 1 : 0;
+    }
+    sj_swap_slots(L);
+  }
+  return n_acc;
+}
+
 // ------------------------------------------------------------------ batched evaluation (parity entry point)
 __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __restrict__ x, int64_t W, WfParams p, HamParams h,
                                                               int have_ham, double* psi, double* grad, double* lap,
@@ -574,17 +608,16 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
   const int g = (threadIdx.x & 31) / 5;
   const int64_t w = ((int64_t)blockIdx.x * SJ_WARPS + (threadIdx.x >> 5)) * SJ_WPW + g;
   SjLane L;
-  SjShared sm;
-  sj_lane_setup(L, c, sm, sj_smem, w, W);
+  sj_lane_setup(L, c, sj_smem, w, W);
   sj_load(L, c, x, w, W);
-  sj_init(c, L, sm);
+  sj_init(c, L);
   // kinetic-only pass gives lap psi and O_k; a second pass with the caller's operator gives H psi
   HamParams hk = h;
   hk.kind = MOLE_OP_KINETIC;
-  double kin, pot, O[SJ_NP];
-  sj_measure<true>(c, hk, L, sm, kin, pot, O);
+  double kin, pot, O[SJ_NP], G[2][3];
+  sj_measure<true>(c, hk, L, kin, pot, O, G);
   double kin_h = 0.0, pot_h = 0.0, O2[SJ_NP];
-  if (have_ham) sj_measure<false>(c, h, L, sm, kin_h, pot_h, O2);
+  if (have_ham) sj_measure<false>(c, h, L, kin_h, pot_h, O2);
   if (!L.act) return;
   if (grad)
 #pragma unroll
@@ -592,7 +625,7 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
       if (L.val[t]) {
         const int cfg_e = t == 0 ? L.gl : c.nup + L.gl;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) grad[((size_t)w * p.ne + cfg_e) * 3 + q] = L.psi * (L.G[t][q] + L.gf[t][q]);
+        for (int q = 0; q < 3; ++q) grad[((size_t)w * p.ne + cfg_e) * 3 + q] = L.psi * (G[t][q] + L.gf[t][q]);
       }
   if (L.gl == 0) {
     if (psi) psi[w] = L.psi;
@@ -605,64 +638,44 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
 }
 
 // ------------------------------------------------------------------ fused sweep
-template <int S, int METROP>
-MOLE_D void sj_sweep_spin(const SjConst& c, SjLane& L, const SjShared& sm, const SweepParams& sp, uint64_t wid,
-                          uint32_t step, int s_local, int64_t w, double sd, double* accv) {
-  const int n = S == 0 ? c.nup : c.ndn;
-  const int cfg_e = S == 0 ? L.gl : c.nup + L.gl;
-  // draws of this lane's slot-S electron (keyed by the electron's index in the configuration)
-  MoveDraw d;
-  if (METROP == MOLE_METROP_BOX) d = mole_draw_uniform4(sp.key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
-  else d = mole_draw_normal3_uniform1(sp.key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
-  for (int el = 0; el < n; ++el) {                                   // Sampler::move_state, samplers.rs:106-117
-    const bool ok = sj_move<S, METROP>(c, L, sm, el, d, sp.metrop_param, sd, sp.compat);
-    if (L.act) {
-      if (L.gl == 1) accv[1] += ok ? 1.0 : 0.0;                      // ACC_NACC = 6 -> lane 1, idx 1
-      if (L.gl == 2) accv[1] += 1.0;                                 // ACC_NMOVE = 7 -> lane 2, idx 1
-      if (sp.tr_accept && L.gl == 0)
-        sp.tr_accept[((size_t)s_local * (c.nup + c.ndn) + (S == 0 ? el : c.nup + el)) * sp.W + w] = ok ? 1 : 0;
-    }
-  }
-}
-
 template <int METROP, bool OPT>
-__global__ void __launch_bounds__(SJ_THREADS, 2) sj_sweep_kernel(const SweepParams sp) {
+__global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const SweepParams sp) {
   extern __shared__ double sj_smem[];
   const SjConst c = sj_const(sp.wf);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / 5;
-  const double sd = sqrt(sp.metrop_param);
+  const double sd = sqrt(sp.metrop_param), inv2tau = 1.0 / (2.0 * sp.metrop_param);
   const bool want_e = (sp.observables & MOLE_OBS_ENERGY) != 0;
   const int64_t W = sp.W;
+  const int ne = c.nup + c.ndn;
   double accv[SJ_ACC_PER_LANE];
 #pragma unroll
   for (int i = 0; i < SJ_ACC_PER_LANE; ++i) accv[i] = 0.0;
   SjLane L;
-  SjShared sm;
 
   const int64_t n_chunks = (W + SJ_WPW - 1) / SJ_WPW;
   for (int64_t chunk = (int64_t)blockIdx.x * SJ_WARPS + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * SJ_WARPS) {
     const int64_t w = chunk * SJ_WPW + g;
-    sj_lane_setup(L, c, sm, sj_smem, w, W);
+    sj_lane_setup(L, c, sj_smem, w, W);
     sj_load(L, c, sp.x, w, W);
-    sj_init(c, L, sm);
+    sj_init(c, L);
     const uint64_t wid = sp.walker_offset + (uint64_t)(w < W ? w : W - 1);
     double blk = L.act ? sp.blk[w] : 0.0;
     int fill = sp.blk_fill;
+#pragma unroll 1
     for (int s = 0; s < sp.n_sweeps; ++s) {
       const uint32_t step = sp.step0 + (uint32_t)s;
-      if (s > 0) sj_refresh(c, L, sm);
-      sj_sweep_spin<0, METROP>(c, L, sm, sp, wid, step, s, w, sd, accv);
-      sj_sweep_spin<1, METROP>(c, L, sm, sp, wid, step, s, w, sd, accv);
+      if (s > 0) sj_refresh(c, L);
+      uint8_t* tra = sp.tr_accept ? sp.tr_accept + (size_t)s * ne * W + (w < W ? w : 0) : nullptr;
+      const int n_acc = sj_sweep_moves<METROP>(c, L, sp.key, wid, step, sp.metrop_param, sd, inv2tau, sp.compat, tra, (size_t)W);
+      if (L.act) {
+        if (L.gl == 1) accv[1] += (double)n_acc;                      // ACC_NACC = 6 -> lane 1, idx 1
+        if (L.gl == 2) accv[1] += (double)ne;                         // ACC_NMOVE = 7 -> lane 2, idx 1
+      }
       if (s < sp.n_discard) continue;                                 // montecarlo.rs:36
       const int64_t si = s - sp.n_discard;
-      if (METROP == MOLE_METROP_BOX) {
-        sj_rebuild_gradients(c, L, sm);
-        sj_refresh_spin<0>(c, L, sm);
-        sj_refresh_spin<1>(c, L, sm);
-      }
       double kin = 0.0, pot = 0.0, O[SJ_NP];
-      if (want_e || OPT || (sp.observables & MOLE_OBS_KINETIC)) sj_measure<OPT>(c, sp.ham, L, sm, kin, pot, O);
+      if (want_e || OPT || (sp.observables & MOLE_OBS_KINETIC)) sj_measure<OPT>(c, sp.ham, L, kin, pot, O);
       const double el = kin + pot;
       double bm = 0.0;
       bool closed = false;
@@ -685,33 +698,33 @@ __global__ void __launch_bounds__(SJ_THREADS, 2) sj_sweep_kernel(const SweepPara
         }
       }
       if (OPT) {
-        const bool quirk = (sp.compat & MOLE_COMPAT_VECTOR_DIV) != 0;
-        if (quirk) {
+        if (sp.compat & MOLE_COMPAT_VECTOR_DIV) {
           // stored sample 1/d_k psi (operator/src/traits.rs:149-150) => O_k = 1/(psi^2 O_k^intended)
 #pragma unroll
           for (int k = 0; k < SJ_NP; ++k) O[k] = 1.0 / (L.psi * L.psi * O[k]);
         }
+        double* os = L.sm + SJ_OFF_MB + MB_ROUT;
         if (L.act && L.gl == 0) {
 #pragma unroll
           for (int k = 0; k < SJ_NP; ++k) {
-            sm.os[k] = O[k];
+            os[k] = O[k];
             if (sp.tr_pgrad) sp.tr_pgrad[((size_t)si * SJ_NP + k) * W + w] = L.psi * O[k];   // d_k psi, or 1/d_k psi under the quirk
           }
         }
-        __syncwarp();
+        sj_sync();
         if (L.act) {
 #pragma unroll
           for (int idx = 2; idx < SJ_ACC_PER_LANE; ++idx) {
             const int j = L.gl + 5 * idx - 10;                        // 0 .. 2P+NOO-1
-            if (j < SJ_NP) accv[idx] += sm.os[j];
-            else if (j < 2 * SJ_NP) accv[idx] = fma(sm.os[j - SJ_NP], el, accv[idx]);
+            if (j < SJ_NP) accv[idx] += os[j];
+            else if (j < 2 * SJ_NP) accv[idx] = fma(os[j - SJ_NP], el, accv[idx]);
             else if (j < 2 * SJ_NP + 28) {
               const int q = j - 2 * SJ_NP;
-              accv[idx] = fma(sm.os[c_sj_oo_k[q]], sm.os[c_sj_oo_l[q]], accv[idx]);
+              accv[idx] = fma(os[c_sj_oo_k[q]], os[c_sj_oo_l[q]], accv[idx]);
             }
           }
         }
-        __syncwarp();
+        sj_sync();
       }
     }
     sj_store(L, c, sp.x, w, W);
@@ -760,39 +773,29 @@ __global__ void __launch_bounds__(SJ_THREADS, 2) sj_sweep_kernel(const SweepPara
 }
 
 // ------------------------------------------------------------------ DMC time step (dmc.rs:87-130)
-__global__ void __launch_bounds__(SJ_THREADS, 2) sj_dmc_kernel(const DmcParams dp) {
+__global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_dmc_kernel(const DmcParams dp) {
   extern __shared__ double sj_smem[];
   const SjConst c = sj_const(dp.wf);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / 5;
-  const double sd = sqrt(dp.tau_move);
+  const double sd = sqrt(dp.tau_move), inv2tau = 1.0 / (2.0 * dp.tau_move);
   const int64_t W = dp.W;
   double s_we = 0.0, s_w = 0.0, s_wn = 0.0, m_wn = 0.0;
   SjLane L;
-  SjShared sm;
   const int64_t n_chunks = (W + SJ_WPW - 1) / SJ_WPW;
   for (int64_t chunk = (int64_t)blockIdx.x * SJ_WARPS + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * SJ_WARPS) {
     const int64_t w = chunk * SJ_WPW + g;
-    sj_lane_setup(L, c, sm, sj_smem, w, W);
+    sj_lane_setup(L, c, sj_smem, w, W);
     sj_load(L, c, dp.x, w, W);
-    sj_init(c, L, sm);
+    sj_init(c, L);
     const uint64_t wid = dp.walker_offset + (uint64_t)(w < W ? w : W - 1);
     double kin, pot, O[SJ_NP];
     double e_old;
     if (dp.el_cached) e_old = L.act ? dp.el[w] : 0.0;
-    else { sj_measure<false>(c, dp.ham, L, sm, kin, pot, O); e_old = kin + pot; }
-#pragma unroll
-    for (int S = 0; S < 2; ++S) {
-      const int n = S == 0 ? c.nup : c.ndn;
-      const int cfg_e = S == 0 ? L.gl : c.nup + L.gl;
-      const MoveDraw d = mole_draw_normal3_uniform1(dp.key, wid, dp.step, DOM_MOVE, (uint32_t)cfg_e);
-      for (int el = 0; el < n; ++el) {
-        if (S == 0) sj_move<0, MOLE_METROP_DIFFUSE>(c, L, sm, el, d, dp.tau_move, sd, dp.compat);
-        else sj_move<1, MOLE_METROP_DIFFUSE>(c, L, sm, el, d, dp.tau_move, sd, dp.compat);
-      }
-    }
-    sj_refresh(c, L, sm);
-    sj_measure<false>(c, dp.ham, L, sm, kin, pot, O);
+    else { sj_measure<false>(c, dp.ham, L, kin, pot, O); e_old = kin + pot; }
+    sj_sweep_moves<MOLE_METROP_DIFFUSE>(c, L, dp.key, wid, dp.step, dp.tau_move, sd, inv2tau, dp.compat, nullptr, 0);
+    sj_refresh(c, L);
+    sj_measure<false>(c, dp.ham, L, kin, pot, O);
     const double e_new = kin + pot;
     if (L.act && L.gl == 0) {
       const double wt = dp.w[w];
@@ -868,7 +871,7 @@ static inline cudaError_t sj_upload_tables() {
 
 static inline int sj_grid(mole_ctx_s* ctx, int64_t W, int rows) {
   const int64_t ctas = (W + SJ_WPB - 1) / SJ_WPB;
-  const int64_t cap = std::min<int64_t>(rows, (int64_t)ctx->sm_count * 2);
+  const int64_t cap = std::min<int64_t>(rows, (int64_t)ctx->sm_count * SJ_MIN_CTAS);
   return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, cap));
 }
 
