@@ -48,6 +48,13 @@ class Context:
         check(lib().mole_bench_fp64_peak(self.handle, C.byref(t)), self.handle)
         return t.value
 
+    def math_probe(self, which, x):
+        """Device evaluation of the kernels' branch-free exp / rcp / rsqrt / sqrt (which = 0..3)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        check(lib().mole_math_probe(self.handle, C.c_int32(which), _dp(x), C.c_int64(x.size), _dp(out)), self.handle)
+        return out
+
     def comm_init(self, nranks, rank, unique_id):
         buf = (C.c_uint8 * ffi.NCCL_UNIQUE_ID_BYTES)(*bytes(unique_id))
         check(lib().mole_comm_init(self.handle, C.c_int32(nranks), C.c_int32(rank), buf), self.handle)

@@ -632,6 +632,22 @@ int32_t mole_branch_sources(mole_ens_t e, int32_t* src) {
   return MOLE_OK;
 }
 
+// ------------------------------------------------------------------ math probe (accuracy tests)
+int32_t mole_math_probe(mole_ctx_t ctx, int32_t which, const double* in, int64_t n, double* out) {
+  if (!ctx || !in || !out || n < 1 || which < 0 || which > 3) return MOLE_ERR_INVALID_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  double *d_in = nullptr, *d_out = nullptr;
+  CU(ctx, cudaMalloc(&d_in, n * sizeof(double)));
+  CU(ctx, cudaMalloc(&d_out, n * sizeof(double)));
+  CU(ctx, cudaMemcpyAsync(d_in, in, n * sizeof(double), cudaMemcpyHostToDevice, STREAM(ctx)));
+  math_probe_kernel<<<cdiv(n, 256), 256, 0, STREAM(ctx)>>>(which, d_in, n, d_out);
+  KERNEL_CHECK(ctx);
+  CU(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+  CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+  cudaFree(d_in); cudaFree(d_out);
+  return MOLE_OK;
+}
+
 // ------------------------------------------------------------------ FP64 peak probe
 int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops) {
   if (!ctx || !tflops) return MOLE_ERR_INVALID_ARG;

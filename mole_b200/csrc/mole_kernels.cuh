@@ -8,6 +8,7 @@
 #pragma once
 #include "mole_internal.h"
 #include "mole_rng.cuh"
+#include "mole_math.cuh"
 #include "mole_wf.cuh"
 
 constexpr int SWEEP_THREADS = 128;
@@ -393,6 +394,21 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams
       dp.red[threadIdx.x] = s;
     }
   }
+}
+
+// ------------------------------------------------------------------ math probe
+__global__ void math_probe_kernel(int which, const double* __restrict__ in, int64_t n, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = in[i];
+  double r, y;
+  switch (which) {
+    case 0: y = m_exp(x); break;
+    case 1: y = m_rcp(x); break;
+    case 2: y = m_rsqrt(x); break;
+    default: y = m_sqrt_rsqrt(x, r); break;
+  }
+  out[i] = y;
 }
 
 // ------------------------------------------------------------------ FP64 peak probe

@@ -20,8 +20,9 @@
 #include <cuda_runtime.h>
 #include "mole_internal.h"
 #include "mole_rng.cuh"
+#include "mole_math.cuh"
 
-constexpr int SJ_WPW = 6;                       // walkers per warp
+constexpr int SJ_WPW = 6;                      // walkers per warp
 constexpr int SJ_WARPS = 4;
 constexpr int SJ_THREADS = 32 * SJ_WARPS;
 constexpr int SJ_WPB = SJ_WPW * SJ_WARPS;       // walkers per CTA
@@ -99,13 +100,10 @@ struct SjPair { double u, gr, lt, ir, R; };
 // pair function from the squared distance (theory/jastrow.tex:23-31,45-48,68-71,82-97)
 MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   SjPair o;
-  const double r = sqrt(r2);
-  const double E = exp(-c.kappa * r);
+  const double r = m_sqrt_rsqrt(r2, o.ir);
+  const double E = m_exp(-c.kappa * r);
   o.R = (1.0 - E) * c.ikappa;
-  const double den = fma(c.b2, o.R, 1.0);
-  const double inv = 1.0 / (den * r);
-  const double iden = inv * r;
-  o.ir = inv * den;
+  const double iden = m_rcp(fma(c.b2, o.R, 1.0));
   const double R2 = o.R * o.R;
   o.u = fma(c.b1 * o.R, iden, fma(c.b4 * R2, o.R, c.b3 * R2));
   const double id2 = iden * iden;
@@ -138,11 +136,10 @@ MOLE_D void sj_gradlnD(const SjConst& c, const double* x, const double* o, const
 
 MOLE_D void sj_radial(const SjConst& c, const double* x, bool valid, double* o) {
   const double r2 = fma(x[2], x[2], fma(x[1], x[1], x[0] * x[0]));
-  o[0] = valid ? sqrt(r2) : 1.0;
-  o[1] = 1.0 / o[0];
-  o[2] = exp(-c.z1 * o[0]);
-  o[3] = exp(-c.z2 * o[0]);
-  o[4] = exp(-c.z3 * o[0]);
+  o[0] = m_sqrt_rsqrt(valid ? r2 : 1.0, o[1]);
+  o[2] = m_exp(-c.z1 * o[0]);
+  o[3] = m_exp(-c.z2 * o[0]);
+  o[4] = m_exp(-c.z3 * o[0]);
 }
 
 // Gauss-Jordan inverse of the 5x5 matrix whose row gl is M[] (row = lane), partial pivoting by
@@ -166,7 +163,7 @@ MOLE_D void sj_invert(double* M, double* out, double& det, const SjLane& L) {
     }
     const double pv = __shfl_sync(SJ_FULL, M[c], L.base + who);
     d *= pv;
-    const double ipv = 1.0 / pv;
+    const double ipv = m_rcp(pv);
     const bool me = (L.gl == who);
     const double fac = M[c];
 #pragma unroll
@@ -224,7 +221,7 @@ MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
   double fl = 0.0;
   for (int p = L.gl; p < SJ_NPAIR; p += 5)
     if (sj_slot_valid(c, c_sj_pair_a[p]) && sj_slot_valid(c, c_sj_pair_b[p])) fl += L.sm[SJ_OFF_PC + p];
-  L.psi = d0 * d1 * exp(sj_gsum(fl, L));
+  L.psi = d0 * d1 * m_exp(sj_gsum(fl, L));
 }
 
 // full initialisation of the cooperative state from the positions in L.x (slot t = spin t)
@@ -315,11 +312,10 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   const double u_acc = mb[MB_XN + 3];
   // ---- orbitals of the moved electron at the trial point: one exponential per lane, then shared
   double on[5];
-  on[0] = sqrt(fma(xn[2], xn[2], fma(xn[1], xn[1], xn[0] * xn[0])));
-  on[1] = 1.0 / on[0];
+  on[0] = m_sqrt_rsqrt(fma(xn[2], xn[2], fma(xn[1], xn[1], xn[0] * xn[0])), on[1]);
   {
     const double zm = L.gl == 0 ? c.z1 : (L.gl == 1 ? c.z2 : c.z3);
-    const double ex = exp(-zm * on[0]);
+    const double ex = m_exp(-zm * on[0]);
     if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = ex;
   }
   // ---- nine Jastrow pairs of the moved electron, two per lane (independent of the exchange above)
@@ -365,7 +361,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   double v = 0.0, ratio = 0.0;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { v = fma(phin[k], cg[k], v); ratio = fma(phin[k], ce[k], ratio); }
-  const double inv_ratio = 1.0 / ratio;
+  const double inv_ratio = m_rcp(ratio);
   const double vr = v * inv_ratio;
   double mt[5];
 #pragma unroll
@@ -401,7 +397,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
       const double* r = mb + MB_RIN + 5 * (L.gl - 1);
       arg = -((((r[0] + r[1]) + r[2]) + r[3]) + r[4]) * inv2tau;
     }
-    const double e3 = exp(arg);
+    const double e3 = m_exp(arg);
     if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = e3;
     sj_sync();
     const double ef = mb[MB_E], th = mb[MB_E + 1], tl = mb[MB_E + 2];
@@ -410,7 +406,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     const double A = sj_clamp_acceptance(th * (q * q) / tl, compat);   // :195
     acc = !node && (A > u_acc);
   } else {
-    q = ratio * exp(df);
+    q = ratio * m_exp(df);
     acc = sj_clamp_acceptance(q * q, compat) > u_acc;          // metrop.rs:80
     if (isown) { gft[0][0] = mb[MB_ROUT + 1]; gft[0][1] = mb[MB_ROUT + 2]; gft[0][2] = mb[MB_ROUT + 3]; }
   }
@@ -485,7 +481,7 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
       double p = 0.0;
       for (int i = 0; i < h.n_ions; ++i) {
         const double dx = x[0] - h.ion_pos[3 * i], dy = x[1] - h.ion_pos[3 * i + 1], dzz = x[2] - h.ion_pos[3 * i + 2];
-        p -= h.ion_z[i] / sqrt(fma(dzz, dzz, fma(dy, dy, dx * dx)));
+        p = fma(-h.ion_z[i], m_rsqrt(fma(dzz, dzz, fma(dy, dy, dx * dx))), p);
       }
       vl = fma(mk, p, vl);
     }
@@ -506,7 +502,7 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     if (want_ee) vl += L.sm[SJ_OFF_PC + 3 * SJ_NPAIR + p];       // ElectronicPotential::value, operator.rs:80-90
     if (OPT) {
       const double R = L.sm[SJ_OFF_PC + 4 * SJ_NPAIR + p];
-      const double id = 1.0 / fma(c.b2, R, 1.0);
+      const double id = m_rcp(fma(c.b2, R, 1.0));
       db[0] = fma(R, id, db[0]);                                 // jastrow.tex:109-119
       db[1] = fma(-c.b1 * R * R, id * id, db[1]);
       db[2] = fma(R, R, db[2]);

@@ -85,7 +85,7 @@ SYMBOLS = [
     "mole_acc_allreduce", "mole_acc_device_ptr", "mole_acc_finalize", "mole_comm_get_unique_id", "mole_comm_init",
     "mole_comm_destroy", "mole_opt_create", "mole_opt_destroy", "mole_opt_step", "mole_opt_sr_matrix",
     "mole_runner_run", "mole_vmc_run_optimization", "mole_dmc_step", "mole_branch", "mole_branch_sources",
-    "mole_dmc_diffuse", "mole_bench_fp64_peak", "mole_ctx_launch_count",
+    "mole_dmc_diffuse", "mole_bench_fp64_peak", "mole_ctx_launch_count", "mole_math_probe",
 ]
 
 _lib = None
