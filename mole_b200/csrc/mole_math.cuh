@@ -1,78 +1,143 @@
-// Branch-free fp64 elementary functions for the hot kernels.
+// Branch-free, batched fp64 elementary functions for the hot kernels.
 //
-// CUDA's exp(), sqrt() and '/' each carry a rarely-taken slow path; the branch splits the basic block,
-// so independent chains (the two Jastrow pairs, the orbital exponential, the accept exponentials of one
-// Metropolis move) cannot be interleaved by the scheduler and the FP64 pipe idles on dependent-issue
-// latency.  The versions below are straight-line code: a MUFU seed refined by Newton steps in DFMA, and
-// a degree-9 polynomial for exp.  Accuracy is ~1 ulp (not correctly rounded), far inside the 1e-10
-// parity bar; domains are stated per function.  tests/test_math_device.py checks them on the device.
+// Why: (1) CUDA's exp(), sqrt() and '/' each carry a rarely-taken slow path whose branch splits the
+// basic block; (2) ptxas schedules a Horner / Newton chain as one serial run of DFMAs, and a dependent
+// DFMA issues only every ~9.4 cycles on B200 (measured, scratch/ubench/dfma.cu) while the FP64 pipe
+// accepts one per 2 cycles per SM sub-partition.  With the 3 warps per scheduler the Slater-Jastrow
+// kernel affords, a serial chain leaves the pipe ~75% idle.  The functions below are straight-line
+// code, take N independent arguments at once and are written stage-major, so the N chains (and the
+// Estrin sub-terms inside exp) are adjacent independent instructions.
+// Accuracy ~1-2 ulp (not correctly rounded), far inside the 1e-10 parity bar; checked on the device
+// by tests/test_math_device.py.
 #pragma once
 #include "mole_internal.h"
 
 #if defined(__CUDACC__)
 
-// 1/x for finite normal x != 0  (MUFU.RCP64H seed, two Newton steps, ~1 ulp)
+// 1/x for finite normal x != 0  (MUFU.RCP64H seed, cubic + quadratic Newton step)
+template <int N>
+MOLE_D void m_rcp_n(const double (&x)[N], double (&y)[N]) {
+  double e[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-x[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);          // y (1 + e + e^2)
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-x[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+}
 MOLE_D double m_rcp(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, fma(e, e, e), y);          // cubic step: y (1 + e + e^2)
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double a[1] = {x};
+  double y[1];
+  m_rcp_n<1>(a, y);
+  return y[0];
 }
 
-// a/b for finite normal b != 0
-MOLE_D double m_div(double a, double b) {
-  const double y = m_rcp(b);
-  const double q = a * y;
-  return fma(fma(-b, q, a), y, q);
+// 1/sqrt(x) for finite normal x > 0  (MUFU.RSQ64H seed, cubic + quadratic Newton step)
+template <int N>
+MOLE_D void m_rsqrt_n(const double (&x)[N], double (&y)[N]) {
+  double hx[N], e[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) hx[i] = 0.5 * x[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-hx[i] * y[i], y[i], 0.5);   // (1 - x y^2)/2
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], fma(1.5 * e[i], e[i], e[i]), y[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-hx[i] * y[i], y[i], 0.5);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
 }
-
-// 1/sqrt(x) for finite normal x > 0  (MUFU.RSQ64H seed, two Newton steps)
 MOLE_D double m_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  double e = fma(-hx * y, y, 0.5);      // (1 - x y^2)/2
-  y = fma(y, fma(1.5 * e, e, e), y);    // cubic step: y (1 + e' + 1.5 e'^2), e' = e
-  e = fma(-hx * y, y, 0.5);
-  y = fma(y, e, y);
-  return y;
+  const double a[1] = {x};
+  double y[1];
+  m_rsqrt_n<1>(a, y);
+  return y[0];
 }
 
 // sqrt(x) and 1/sqrt(x) together, x > 0 finite normal
+template <int N>
+MOLE_D void m_sqrt_rsqrt_n(const double (&x)[N], double (&s)[N], double (&rinv)[N]) {
+  m_rsqrt_n<N>(x, rinv);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = x[i] * rinv[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = fma(fma(-s[i], s[i], x[i]), 0.5 * rinv[i], s[i]);
+}
 MOLE_D double m_sqrt_rsqrt(double x, double& rinv) {
-  rinv = m_rsqrt(x);
-  const double s = x * rinv;
-  return fma(fma(-s, s, x), 0.5 * rinv, s);
+  const double a[1] = {x};
+  double s[1], r[1];
+  m_sqrt_rsqrt_n<1>(a, s, r);
+  rinv = r[0];
+  return s[0];
 }
 
-// exp(x) on the whole real line, branch-free: 0 below -745.2, +inf above 709.8, NaN propagates
+// exp(x) on the whole real line, branch-free: 0 below -745.2, +inf above 709.8, NaN propagates.
+// exp(r) = 1 + r + r^2 q(r) on |r| <= ln2/2 with q a degree-9 near-minimax polynomial (max relative
+// error 1.6e-17) evaluated in Estrin form (dependent depth 5 instead of 10).
+// The argument is clamped to [-1400, 710] with data selects (NOT a select on the result: the compiler
+// turns that into a branch around the whole evaluation, which serialises a batch again); the two-step
+// 2^n scaling then underflows to 0 / overflows to +inf by itself.  NEG_ONLY: caller guarantees x <= 0.
+template <int N, bool NEG_ONLY = false>
+MOLE_D void m_exp_n(const double (&xin)[N], double (&y)[N]) {
+  double x[N], t[N], r[N], r2[N], a0[N], a1[N], a2[N], a3[N], a4[N];
+  int n[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    x[i] = xin[i] < -1400.0 ? -1400.0 : xin[i];
+    if (!NEG_ONLY) x[i] = x[i] > 710.0 ? 710.0 : x[i];
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = fma(x[i], 1.4426950408889634, 6755399441055744.0);   // 1.5*2^52: low word = round(x log2 e)
+#pragma unroll
+  for (int i = 0; i < N; ++i) { n[i] = __double2loint(t[i]); t[i] -= 6755399441055744.0; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(t[i], -6.93147180369123816490e-01, x[i]);         // ln2 hi (32 trailing zero bits)
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(t[i], -1.90821492927058770002e-10, r[i]);         // ln2 lo
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    r2[i] = r[i] * r[i];
+    a0[i] = fma(0.16666666666666669, r[i], 0.5000000000000001);
+    a1[i] = fma(0.008333333333330062, r[i], 0.04166666666662413);
+    a2[i] = fma(0.00019841269863053618, r[i], 0.0013888888917213717);
+    a3[i] = fma(2.7557268459997064e-06, r[i], 2.4801521295954376e-05);
+    a4[i] = fma(2.510038549551032e-08, r[i], 2.7620088445409746e-07);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    a0[i] = fma(a1[i], r2[i], a0[i]);
+    a2[i] = fma(a3[i], r2[i], a2[i]);
+    t[i] = r2[i] * r2[i];                                                                  // r^4
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    a0[i] = fma(a2[i], t[i], a0[i]);
+    t[i] = t[i] * t[i];                                                                    // r^8
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) a0[i] = fma(a4[i], t[i], a0[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) a0[i] = fma(r2[i], a0[i], r[i]) + 1.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int n1 = n[i] >> 1, n2 = n[i] - n1;                                              // two-step scaling covers denormals / overflow
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0), s2 = __hiloint2double((n2 + 1023) << 20, 0);
+    y[i] = (a0[i] * s1) * s2;
+  }
+}
 MOLE_D double m_exp(double x) {
-  const double xc = fmin(fmax(x, -746.0), 710.0);
-  const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);     // 1.5 * 2^52: low word = round(x log2 e)
-  const int n = __double2loint(t);
-  const double nf = t - 6755399441055744.0;
-  double r = fma(nf, -6.93147180369123816490e-01, xc);                  // ln2 hi (32 trailing zero bits)
-  r = fma(nf, -1.90821492927058770002e-10, r);                          // ln2 lo
-  // exp(r) = 1 + r + r^2 q(r), |r| <= ln2/2; q = degree-9 near-minimax (max rel. error 1.6e-17)
-  double q = 2.510038549551032e-08;
-  q = fma(q, r, 2.7620088445409746e-07);
-  q = fma(q, r, 2.7557268459997064e-06);
-  q = fma(q, r, 2.4801521295954376e-05);
-  q = fma(q, r, 0.00019841269863053618);
-  q = fma(q, r, 0.0013888888917213717);
-  q = fma(q, r, 0.008333333333330062);
-  q = fma(q, r, 0.04166666666662413);
-  q = fma(q, r, 0.16666666666666669);
-  q = fma(q, r, 0.5000000000000001);
-  const double p = fma(r * r, q, r) + 1.0;
-  const int n1 = n >> 1, n2 = n - n1;                                   // two-step scaling covers denormals / overflow
-  const double s1 = __hiloint2double((n1 + 1023) << 20, 0);
-  const double s2 = __hiloint2double((n2 + 1023) << 20, 0);
-  const double res = (p * s1) * s2;
-  return isnan(x) ? x : res;
+  const double a[1] = {x};
+  double y[1];
+  m_exp_n<1>(a, y);
+  return y[0];
 }
 
 #endif  // __CUDACC__

@@ -34,15 +34,15 @@ constexpr int SJ_OFF_PC = 0;                               // [SJ_PCV][45]
 constexpr int SJ_OFF_XS = SJ_OFF_PC + SJ_PCV * SJ_NPAIR;   // [10][3] positions by slot id (spin*5 + lane)
 constexpr int SJ_OFF_MINV = SJ_OFF_XS + 30;                // [2][5][5] inverse Slater matrices, (spin, k, j)
 constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 48 doubles
-constexpr int SJ_MB = 48;
+constexpr int SJ_MB = 50;
 constexpr int SJ_STRIDE = 357;                             // >= SJ_OFF_MB + SJ_MB and == 5 (mod 16)
 static_assert(SJ_STRIDE >= SJ_OFF_MB + SJ_MB && SJ_STRIDE % 16 == 5, "per-walker stride");
 constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
 // mailbox slots
-constexpr int MB_XN = 0;      // [3] trial position, [3] = accept uniform
-constexpr int MB_E = 4;       // [3] orbital exponentials at the trial position / exp(df), t_high, t_low
-constexpr int MB_RIN = 8;     // [4][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles)
-constexpr int MB_ROUT = 40;   // [4] reduction outputs / O_k staging (8 doubles)
+constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] old position of the moved electron
+constexpr int MB_E = 8;       // [3] orbital exponentials at the trial position
+constexpr int MB_RIN = 12;    // [6][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles)
+constexpr int MB_ROUT = 42;   // [8] O_k staging (v2 move: reduction outputs)
 constexpr int SJ_NP = 7;
 constexpr int SJ_NACC = 10 + 2 * SJ_NP + SJ_NP * (SJ_NP + 1) / 2;   // 52 compact accumulator entries
 constexpr int SJ_ACC_PER_LANE = (SJ_NACC + 4) / 5;                   // 11
@@ -227,6 +227,8 @@ MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
 // full initialisation of the cooperative state from the positions in L.x (slot t = spin t)
 MOLE_D void sj_init(const SjConst& c, SjLane& L) {
   L.ph = 0;
+  for (int p = L.gl; p < SJ_PCV * SJ_NPAIR; p += 5)          // cache slots of absent pairs must hold finite values
+    if (L.wr) L.sm[SJ_OFF_PC + p] = 0.0;
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     sj_radial(c, L.x[t], L.val[t], L.orb[t]);
@@ -276,8 +278,8 @@ MOLE_D void sj_swap_slots(SjLane& L) {
 // Metropolis::move_state for electron `el` of the spin in slot 0.  d = the pre-generated draws of THIS
 // lane's slot-0 electron (only the owner's are used).  Returns the accept decision (uniform over the group).
 template <int METROP>
-MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, double param, double sd, double inv2tau,
-                    uint32_t compat) {
+MOLE_D bool sj_move_v2(const SjConst& c, SjLane& L, int el, const MoveDraw& d, double param, double sd, double inv2tau,
+                       uint32_t compat) {   // superseded by mole_sj_move.cuh (kept for A/B timing; not instantiated)
   const int spin = L.ph;
   const int n = sj_spin_n(c, spin);
   const bool isown = (L.gl == el);
@@ -438,6 +440,8 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   sj_sync();
   return acc;
 }
+
+#include "mole_sj_move.cuh"
 
 // Local quantities of the current configuration:
 //   kin = -0.5 sum_i lap_i psi / psi,  pot = V (so that E_L = kin + pot),  O[k] = d ln psi / d p_k

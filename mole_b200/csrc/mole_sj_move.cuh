@@ -1,0 +1,197 @@
+// Metropolis::move_state for one electron of the Slater-Jastrow kind (included from mole_sj.cuh).
+//
+// v3: the three independent transcendental chains of a move (orbital radial part and the two Jastrow
+// pairs of each lane) go through the batched, stage-major math of mole_math.cuh, the exp(df) /
+// 1/ratio and t_high / t_low chains are paired the same way, and every lane sums the mailbox rows
+// itself (four warp syncs per move instead of six).  Semantics: src/metropolis/src/metrop.rs:60-96
+// (box) and :150-212 (diffusion), Frobenius norms over ALL electrons' drift.
+#pragma once
+
+template <int METROP>
+MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, double param, double sd, double inv2tau,
+                    uint32_t compat) {
+  const int spin = L.ph;
+  const int n = sj_spin_n(c, spin);
+  const bool isown = (L.gl == el);
+  const int sid_e = spin * 5 + el;
+  double* const mb = L.sm + SJ_OFF_MB;
+  const double* const minv = L.sm + SJ_OFF_MINV + spin * 25;
+  // this lane's column (cg) and the moved electron's column (ce) of the inverse
+  double cg[5], ce[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { cg[k] = minv[k * 5 + L.gl]; ce[k] = minv[k * 5 + el]; }
+  // drift of this lane's slot-0 electron at the current configuration
+  double Gown[3];
+  sj_gradlnD(c, L.x[0], L.orb[0], cg, Gown);
+  // ---- A: the owner proposes, everybody reads the trial point
+  if (isown && L.wr) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double xi = q == 0 ? d.a : (q == 1 ? d.b : d.c);
+      if (METROP == MOLE_METROP_BOX) {
+        const double lo = -0.5 * param, scale = 0.5 * param - lo;
+        mb[MB_XN + q] = L.x[0][q] + (lo + scale * xi);                              // metrop.rs:63-68
+      } else {
+        mb[MB_XN + q] = (L.x[0][q] + (Gown[q] + L.gf[0][q]) * param) + sd * xi;     // metrop.rs:155-160
+      }
+      mb[MB_XN + 4 + q] = L.x[0][q];
+    }
+    mb[MB_XN + 3] = d.u;
+  }
+  sj_sync();
+  double xn[3], xo[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { xn[q] = mb[MB_XN + q]; xo[q] = mb[MB_XN + 4 + q]; }
+  const double u_acc = mb[MB_XN + 3];
+
+  // ---- B: three independent chains, batched: |x'| and the two pair distances -> rsqrt -> exp
+  bool pv[2];
+  int pid[2];
+  double dn[2][3], r2v[3], rv[3], iv[3], ea[3], ev[3];
+  r2v[0] = fma(xn[2], xn[2], fma(xn[1], xn[1], xn[0] * xn[0]));
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int b = (t ^ L.ph) * 5 + L.gl;
+    pv[t] = L.val[t] && !(t == 0 && isown);
+    pid[t] = max(sj_pidx(sid_e, b), 0);   // branch-free; masked entries read finite (zero-initialised) cache slots
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dn[t][q] = xn[q] - L.x[t][q];
+    r2v[1 + t] = pv[t] ? fma(dn[t][2], dn[t][2], fma(dn[t][1], dn[t][1], dn[t][0] * dn[t][0])) : 1.0;
+  }
+  m_sqrt_rsqrt_n<3>(r2v, rv, iv);
+  ea[0] = -(L.gl == 0 ? c.z1 : (L.gl == 1 ? c.z2 : c.z3)) * rv[0];
+  ea[1] = -c.kappa * rv[1];
+  ea[2] = -c.kappa * rv[2];
+  m_exp_n<3, true>(ea, ev);
+  if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = ev[0];                 // one orbital exponential per lane, shared below
+  // pair functions (theory/jastrow.tex:23-31,45-48,68-71,82-97), the two pairs stage by stage
+  double Rs[2], den[2], iden[2], pu[2], pgr[2], plt[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) { Rs[t] = (1.0 - ev[1 + t]) * c.ikappa; den[t] = fma(c.b2, Rs[t], 1.0); }
+  m_rcp_n<2>(den, iden);
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const double R2 = Rs[t] * Rs[t], id2 = iden[t] * iden[t], E = ev[1 + t];
+    pu[t] = fma(c.b1 * Rs[t], iden[t], fma(c.b4 * R2, Rs[t], c.b3 * R2));
+    const double du = fma(c.b1, id2, fma(3.0 * c.b4, R2, 2.0 * c.b3 * Rs[t]));
+    const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden[t], fma(6.0 * c.b4, Rs[t], 2.0 * c.b3));
+    const double g = E * du;
+    pgr[t] = g * iv[1 + t];
+    plt[t] = fma(2.0, pgr[t], fma(E * E, d2u, -c.kappa * g));   // div(rhat g) = 2 g/r + dg/dr
+  }
+  double dfl = 0.0, ge[3] = {0.0, 0.0, 0.0}, gft[2][3];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const double u_old = L.sm[SJ_OFF_PC + pid[t]], gr_old = L.sm[SJ_OFF_PC + SJ_NPAIR + pid[t]];
+    const double m = pv[t] ? 1.0 : 0.0;
+    dfl = fma(m, pu[t] - u_old, dfl);
+    const double gn_ = m * pgr[t], go_ = m * gr_old;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      // grad_b f changes by the (b,e) term: -(x_e - x_b) g/r
+      gft[t][q] = L.gf[t][q] + go_ * (xo[q] - L.x[t][q]) - gn_ * dn[t][q];
+      ge[q] = fma(gn_, dn[t][q], ge[q]);
+    }
+  }
+  if (L.wr) {                                                    // reduction inputs: df and grad_e f (from scratch)
+    mb[MB_RIN + L.gl] = dfl;
+    mb[MB_RIN + 5 + L.gl] = ge[0];
+    mb[MB_RIN + 10 + L.gl] = ge[1];
+    mb[MB_RIN + 15 + L.gl] = ge[2];
+  }
+  sj_sync();
+
+  // ---- C: every lane sums the four rows (lane order 0..4), determinant ratio, Sherman-Morrison column
+  double on[5];
+  on[0] = rv[0]; on[1] = iv[0];
+  on[2] = mb[MB_E]; on[3] = mb[MB_E + 1]; on[4] = mb[MB_E + 2];
+  double red[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double* r = mb + MB_RIN + 5 * j;
+    red[j] = (((r[0] + r[1]) + r[2]) + r[3]) + r[4];
+  }
+  const double df = red[0];
+  if (isown) { gft[0][0] = red[1]; gft[0][1] = red[2]; gft[0][2] = red[3]; }
+  double phin[5];
+  sj_phi(xn, on, n, phin);
+  double v = 0.0, ratio = 0.0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { v = fma(phin[k], cg[k], v); ratio = fma(phin[k], ce[k], ratio); }
+  // 1/ratio and exp(df) are independent chains: issue them together
+  double ef, inv_ratio;
+  {
+    const double xa[1] = {ratio}, xe[1] = {df};
+    double ya[1], ye[1];
+    m_rcp_n<1>(xa, ya);
+    m_exp_n<1>(xe, ye);
+    inv_ratio = ya[0];
+    ef = ye[0];
+  }
+  const double vr = v * inv_ratio;
+  double mt[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) mt[k] = isown ? ce[k] * inv_ratio : fma(-ce[k], vr, cg[k]);
+  const double q = ratio * ef;                                     // psi'/psi
+  bool acc;
+  if (METROP == MOLE_METROP_DIFFUSE) {
+    // Frobenius norms over ALL electrons' drift (metrop.rs:182-193)
+    double Gt[3], G1[3], c1[5];
+    sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], mt, Gt);
+    const double* minv1 = L.sm + SJ_OFF_MINV + (spin ^ 1) * 25;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) c1[k] = minv1[k * 5 + L.gl];
+    sj_gradlnD(c, L.x[1], L.orb[1], c1, G1);
+    double sh = 0.0, sl = 0.0;
+    const double m0 = L.val[0] ? 1.0 : 0.0, m1 = L.val[1] ? 1.0 : 0.0;
+#pragma unroll
+    for (int qq = 0; qq < 3; ++qq) {
+      const double dx = isown ? xo[qq] - xn[qq] : 0.0;
+      const double a0 = dx - (Gt[qq] + gft[0][qq]) * param, b0 = -dx - (Gown[qq] + L.gf[0][qq]) * param;
+      const double a1 = (G1[qq] + gft[1][qq]) * param, b1 = (G1[qq] + L.gf[1][qq]) * param;
+      sh = fma(m0 * a0, a0, fma(m1 * a1, a1, sh));
+      sl = fma(m0 * b0, b0, fma(m1 * b1, b1, sl));
+    }
+    if (L.wr) { mb[MB_RIN + 20 + L.gl] = sh; mb[MB_RIN + 25 + L.gl] = sl; }
+    sj_sync();
+    // ---- D: t_high and t_low, two chains together
+    const double* rh = mb + MB_RIN + 20;
+    const double* rl = mb + MB_RIN + 25;
+    const double targ[2] = {-((((rh[0] + rh[1]) + rh[2]) + rh[3]) + rh[4]) * inv2tau,
+                            -((((rl[0] + rl[1]) + rl[2]) + rl[3]) + rl[4]) * inv2tau};
+    double tv[2];
+    m_exp_n<2, true>(targ, tv);
+    const bool node = !(ratio > 0.0);                              // signum(psi') != signum(psi) or NaN, :178-180
+    const double A = sj_clamp_acceptance(tv[0] * (q * q) / tv[1], compat);   // :195
+    acc = !node && (A > u_acc);
+  } else {
+    acc = sj_clamp_acceptance(q * q, compat) > u_acc;              // metrop.rs:80
+  }
+  if (acc) {
+    if (isown) {
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq) L.x[0][qq] = xn[qq];
+#pragma unroll
+      for (int qq = 0; qq < 5; ++qq) L.orb[0][qq] = on[qq];
+      if (L.act)
+#pragma unroll
+        for (int qq = 0; qq < 3; ++qq) L.sm[SJ_OFF_XS + sid_e * 3 + qq] = xn[qq];
+    }
+    if (L.act) {
+      double* mw = L.sm + SJ_OFF_MINV + spin * 25;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) mw[k * 5 + L.gl] = mt[k];
+    }
+#pragma unroll
+    for (int qq = 0; qq < 3; ++qq) { L.gf[0][qq] = gft[0][qq]; L.gf[1][qq] = gft[1][qq]; }
+    L.psi *= q;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (pv[t] && L.act) {
+        double* pc = L.sm + SJ_OFF_PC + pid[t];
+        pc[0] = pu[t]; pc[SJ_NPAIR] = pgr[t]; pc[2 * SJ_NPAIR] = plt[t]; pc[3 * SJ_NPAIR] = iv[1 + t]; pc[4 * SJ_NPAIR] = Rs[t];
+      }
+  }
+  sj_sync();
+  return acc;
+}
