@@ -389,3 +389,46 @@ def test_dmc_hydrogen_energy(mole):
     dmc = mole.DmcRunner.new(wf, 8192, -0.45, op, m, mole.SRBrancher.new(), identical_start=False)
     en, er = dmc.diffuse(0.01, 3000, 100, 10)
     assert abs(en[-1] + 0.5) < max(6 * er[-1], 3e-3)
+
+
+def test_vmc_sr_slater_jastrow_p7_matches_oracle(mole, orc):
+    """SR with P = 7 (untested upstream, SURVEY §4 gaps): Be Slater-Jastrow, 6 workers, 3 iterations;
+    energies, blocking errors and all seven parameters per iteration against the oracle's raw-sample path."""
+    c = cases()["sj_be"]
+    iters, total, bs, nw = 3, 6 * 60, 10, 6
+    cfg0 = orc.init_uniform(SEED0, 0, 4)
+    opts = orc.run_options(orc.METROP_DIFFUSE, 0.05, nan_reject=1)
+    ropt = orc.Optimizer(orc.OPT_SR, 7, 0.02)
+    ref = orc.vmc_run_optimization(c["owf"], c["oham"], opts, ropt, SEED0, cfg0, iters, total, bs, nw)
+    wf, op = c["make"](mole)
+    obs = mole.operators(**{"Energy": op, "Parameter gradient": mole.ParameterGradient, "Wavefunction value": mole.WavefunctionValue})
+    sampler = mole.Sampler.new(wf, mole.MetropolisDiffuse.from_rng(0.05, SEED0), obs)
+    vmc = mole.VmcRunner(sampler, mole.StochasticReconfiguration(0.02, 7))
+    _, en, er = vmc.run_optimization(iters, total, bs, nw)
+    assert np.max(np.abs(en - ref["energies"]) / np.abs(ref["energies"])) < 1e-8
+    assert np.max(np.abs(er - ref["errors"]) / ref["errors"]) < 1e-5
+    assert np.max(np.abs(vmc.param_history - ref["param_history"]) / np.maximum(np.abs(ref["param_history"]), 1e-2)) < 1e-5
+
+
+def test_dmc_step_slater_jastrow_matches_oracle(mole, orc):
+    """One DMC time step (dmc.rs:87-130) of the cooperative Slater-Jastrow kernel, state re-synchronised
+    on the oracle each step."""
+    c = cases()["sj_li"]
+    wf, op = c["make"](mole)
+    W, tau, seed = 200, 0.01, bytes([3] * 32)
+    m = mole.MetropolisDiffuse.from_rng(tau, seed)
+    x = np.array([orc.init_normal(seed, w, 3, 0.8) for w in range(W)])
+    w = np.ones(W)
+    ens = mole.Ensemble(W, 3, seed)
+    e_ref = -7.0
+    for t in range(3):
+        ens.set_configs(x); ens.set_weights(w); ens.step = t
+        # the oracle's dmc_step uses the reference-faithful NaN policy; Li with tau = 0.01 from N(0, 0.8) stays finite
+        e_o, tw_o, w2, x2 = orc.dmc_step(c["owf"], c["oham"], w, x, tau, tau, e_ref, seed, t)
+        swe, sw = ens.dmc_step(wf, m.set_compat(mole.ffi.COMPAT_NAN_ACCEPT), op, tau, e_ref)
+        assert abs(swe / sw - e_o) < 1e-9 * abs(e_o)
+        assert close(ens.get_configs(), x2) and close(ens.get_weights(), w2, 1e-8)
+        ens.branch(mole.ffi.BRANCH_SR)
+        src = ens.branch_sources()
+        w, x = np.full(W, w2.mean()), x2[src]
+        assert close(ens.get_configs(), x)
