@@ -31,12 +31,14 @@ constexpr int SJ_NPAIR = 45;
 constexpr int SJ_PCV = 5;                       // cached values per pair: u, g/r, lap term, 1/r, R
 // shared memory per walker (offsets in doubles)
 constexpr int SJ_OFF_PC = 0;                               // [SJ_PCV][45]
-constexpr int SJ_OFF_XS = SJ_OFF_PC + SJ_PCV * SJ_NPAIR;   // [10][3] positions by slot id (spin*5 + lane)
-constexpr int SJ_OFF_MINV = SJ_OFF_XS + 30;                // [2][5][5] inverse Slater matrices, (spin, k, j)
-constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 48 doubles
+constexpr int SJ_OFF_MINV = SJ_OFF_PC + SJ_PCV * SJ_NPAIR; // [2][5][5] inverse Slater matrices, (spin, k, j)
+constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 50 doubles
 constexpr int SJ_MB = 50;
-constexpr int SJ_STRIDE = 357;                             // >= SJ_OFF_MB + SJ_MB and == 5 (mod 16)
-static_assert(SJ_STRIDE >= SJ_OFF_MB + SJ_MB && SJ_STRIDE % 16 == 5, "per-walker stride");
+constexpr int SJ_OFF_ACC = SJ_OFF_MB + SJ_MB;              // [42] sum O_k, sum O_k E_L, sum O_k O_l of this walker slot
+constexpr int SJ_NMOM = 42;
+constexpr int SJ_STRIDE = 373;                             // >= SJ_OFF_ACC + SJ_NMOM and == 5 (mod 16)
+static_assert(SJ_STRIDE >= SJ_OFF_ACC + SJ_NMOM && SJ_STRIDE % 16 == 5, "per-walker stride");
+constexpr int SJ_REFRESH_EVERY = 4;                        // sweeps between from-scratch rebuilds of the inverses
 constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
 // mailbox slots
 constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] old position of the moved electron
@@ -70,6 +72,7 @@ struct SjLane {
   double x[2][3];      // own electrons
   double orb[2][5];    // r, 1/r, exp(-z1 r), exp(-z2 r), exp(-z3 r) at own electrons
   double gf[2][3];     // grad_i f
+  double G[2][3];      // grad_i ln D
   double psi;          // replicated over the group
   double* sm;          // this walker's shared-memory region
 };
@@ -210,6 +213,7 @@ MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t) {
 #pragma unroll
   for (int k = 0; k < 5; ++k)
     if (L.wr) L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl] = out[k];          // Minv[k][j = gl]
+  sj_gradlnD(c, L.x[t], L.orb[t], out, L.G[t]);
   sj_sync();
   return det;
 }
@@ -229,12 +233,13 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
   L.ph = 0;
   for (int p = L.gl; p < SJ_PCV * SJ_NPAIR; p += 5)          // cache slots of absent pairs must hold finite values
     if (L.wr) L.sm[SJ_OFF_PC + p] = 0.0;
+  double* const xs = L.sm + SJ_OFF_MB;                       // all 10 positions, staged in the mailbox for the pair loop
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     sj_radial(c, L.x[t], L.val[t], L.orb[t]);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-      if (L.wr) L.sm[SJ_OFF_XS + (t * 5 + L.gl) * 3 + q] = L.x[t][q];
+      if (L.wr) xs[(t * 5 + L.gl) * 3 + q] = L.x[t][q];
   }
   sj_sync();
   // Jastrow from scratch: every lane sums over the partners of its own electrons
@@ -244,7 +249,7 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
     double gx = 0.0, gy = 0.0, gz = 0.0;
     for (int b = 0; b < 10; ++b) {
       const bool pv = L.val[t] && b != a && sj_slot_valid(c, b);
-      const double* xb = L.sm + SJ_OFF_XS + b * 3;
+      const double* xb = xs + b * 3;
       const double dx = L.x[t][0] - xb[0], dy = L.x[t][1] - xb[1], dz = L.x[t][2] - xb[2];
       const double r2 = pv ? fma(dz, dz, fma(dy, dy, dx * dx)) : 1.0;
       const SjPair P = sj_pair(c, r2);
@@ -268,6 +273,7 @@ MOLE_D void sj_swap_slots(SjLane& L) {
   for (int q = 0; q < 3; ++q) {
     double t = L.x[0][q]; L.x[0][q] = L.x[1][q]; L.x[1][q] = t;
     t = L.gf[0][q]; L.gf[0][q] = L.gf[1][q]; L.gf[1][q] = t;
+    t = L.G[0][q]; L.G[0][q] = L.G[1][q]; L.G[1][q] = t;
   }
 #pragma unroll
   for (int q = 0; q < 5; ++q) { const double t = L.orb[0][q]; L.orb[0][q] = L.orb[1][q]; L.orb[1][q] = t; }
@@ -277,6 +283,7 @@ MOLE_D void sj_swap_slots(SjLane& L) {
 
 // Metropolis::move_state for electron `el` of the spin in slot 0.  d = the pre-generated draws of THIS
 // lane's slot-0 electron (only the owner's are used).  Returns the accept decision (uniform over the group).
+#if 0   // v2 of the move (six warp syncs, lane-specialised exponentials), superseded by mole_sj_move.cuh
 template <int METROP>
 MOLE_D bool sj_move_v2(const SjConst& c, SjLane& L, int el, const MoveDraw& d, double param, double sd, double inv2tau,
                        uint32_t compat) {   // superseded by mole_sj_move.cuh (kept for A/B timing; not instantiated)
@@ -440,6 +447,7 @@ MOLE_D bool sj_move_v2(const SjConst& c, SjLane& L, int el, const MoveDraw& d, d
   sj_sync();
   return acc;
 }
+#endif
 
 #include "mole_sj_move.cuh"
 
@@ -460,10 +468,10 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     const double* x = L.x[t];
     const double* o = L.orb[t];
     const double r = o[0], ir = o[1];
-    double m[5], G[3];
+    double m[5];
+    const double* G = L.G[t];
 #pragma unroll
     for (int k = 0; k < 5; ++k) m[k] = L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl];
-    sj_gradlnD(c, x, o, m, G);
     if (Gout) { Gout[t][0] = G[0]; Gout[t][1] = G[1]; Gout[t][2] = G[2]; }
     // lap phi_k
     const double cp = o[4] * (c.z3 * c.z3 - 4.0 * c.z3 * ir);
@@ -648,10 +656,16 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
   const bool want_e = (sp.observables & MOLE_OBS_ENERGY) != 0;
   const int64_t W = sp.W;
   const int ne = c.nup + c.ndn;
-  double accv[SJ_ACC_PER_LANE];
-#pragma unroll
-  for (int i = 0; i < SJ_ACC_PER_LANE; ++i) accv[i] = 0.0;
+  // the ten scalar accumulators live in two registers per lane (compact entry i in lanes gl == i%5);
+  // the 42 optimisation moments live in this walker slot's shared memory
+  double accv[2] = {0.0, 0.0};
   SjLane L;
+  if (OPT) {
+    double* am = sj_smem + (size_t)(warp * SJ_WPW + (g < SJ_WPW ? g : 0)) * SJ_STRIDE + SJ_OFF_ACC;
+    if (g < SJ_WPW)
+      for (int j = lane - 5 * g; j < SJ_NMOM; j += 5) am[j] = 0.0;
+    __syncwarp();
+  }
 
   const int64_t n_chunks = (W + SJ_WPW - 1) / SJ_WPW;
   for (int64_t chunk = (int64_t)blockIdx.x * SJ_WARPS + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * SJ_WARPS) {
@@ -665,7 +679,7 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
 #pragma unroll 1
     for (int s = 0; s < sp.n_sweeps; ++s) {
       const uint32_t step = sp.step0 + (uint32_t)s;
-      if (s > 0) sj_refresh(c, L);
+      if (s > 0 && (s % SJ_REFRESH_EVERY) == 0) sj_refresh(c, L);
       uint8_t* tra = sp.tr_accept ? sp.tr_accept + (size_t)s * ne * W + (w < W ? w : 0) : nullptr;
       const int n_acc = sj_sweep_moves<METROP>(c, L, sp.key, wid, step, sp.metrop_param, sd, inv2tau, sp.compat, tra, (size_t)W);
       if (L.act) {
@@ -713,15 +727,13 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
         }
         sj_sync();
         if (L.act) {
-#pragma unroll
-          for (int idx = 2; idx < SJ_ACC_PER_LANE; ++idx) {
-            const int j = L.gl + 5 * idx - 10;                        // 0 .. 2P+NOO-1
-            if (j < SJ_NP) accv[idx] += os[j];
-            else if (j < 2 * SJ_NP) accv[idx] = fma(os[j - SJ_NP], el, accv[idx]);
-            else if (j < 2 * SJ_NP + 28) {
-              const int q = j - 2 * SJ_NP;
-              accv[idx] = fma(os[c_sj_oo_k[q]], os[c_sj_oo_l[q]], accv[idx]);
-            }
+          double* am = L.sm + SJ_OFF_ACC;
+          for (int j = L.gl; j < SJ_NMOM; j += 5) {                   // 0 .. 2P+NOO-1, lane gl owns j == gl (mod 5)
+            double add;
+            if (j < SJ_NP) add = os[j];
+            else if (j < 2 * SJ_NP) add = os[j - SJ_NP] * el;
+            else add = os[c_sj_oo_k[j - 2 * SJ_NP]] * os[c_sj_oo_l[j - 2 * SJ_NP]];
+            am[j] += add;
           }
         }
         sj_sync();
@@ -733,17 +745,17 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
 
   // block-tree reduction of the lane-distributed accumulators (compact entry i lives in lanes gl == i%5)
   __syncthreads();
-  double* red = sj_smem;                                               // [SJ_WARPS][SJ_NACC]
+  double* red = sj_smem;                                               // [SJ_WARPS][16] scalars (pair-cache area of slot 0)
   __shared__ bool is_last;
   const int gl = lane % 5;
   const bool counted = lane < 5 * SJ_WPW;
   constexpr int LEN = OPT ? SJ_NACC : 10;
 #pragma unroll
-  for (int i = 0; i < LEN; ++i) {
+  for (int i = 0; i < 10; ++i) {
     double v = (counted && (i % 5) == gl) ? accv[i / 5] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SJ_FULL, v, o);
-    if (lane == 0) red[warp * SJ_NACC + i] = v;
+    if (lane == 0) red[warp * 16 + i] = v;
   }
   __syncthreads();
   auto slot = [](int i) {
@@ -754,7 +766,11 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
   };
   if (threadIdx.x < LEN) {
     double s = 0.0;
-    for (int q = 0; q < SJ_WARPS; ++q) s += red[q * SJ_NACC + threadIdx.x];
+    if (threadIdx.x < 10) {
+      for (int q = 0; q < SJ_WARPS; ++q) s += red[q * 16 + threadIdx.x];
+    } else {
+      for (int q = 0; q < SJ_WPB; ++q) s += sj_smem[(size_t)q * SJ_STRIDE + SJ_OFF_ACC + (threadIdx.x - 10)];
+    }
     sp.partials[(size_t)blockIdx.x * ACC_LEN + slot(threadIdx.x)] = s;
   }
   __threadfence();

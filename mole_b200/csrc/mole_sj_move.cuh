@@ -20,9 +20,8 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   double cg[5], ce[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) { cg[k] = minv[k * 5 + L.gl]; ce[k] = minv[k * 5 + el]; }
-  // drift of this lane's slot-0 electron at the current configuration
-  double Gown[3];
-  sj_gradlnD(c, L.x[0], L.orb[0], cg, Gown);
+  // grad ln D of the own electrons is carried in L.G (rebuilt by sj_refresh, updated on accepted moves)
+  const double* const Gown = L.G[0];
   // ---- A: the owner proposes, everybody reads the trial point
   if (isown && L.wr) {
 #pragma unroll
@@ -118,30 +117,17 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   double v = 0.0, ratio = 0.0;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { v = fma(phin[k], cg[k], v); ratio = fma(phin[k], ce[k], ratio); }
-  // 1/ratio and exp(df) are independent chains: issue them together
-  double ef, inv_ratio;
-  {
-    const double xa[1] = {ratio}, xe[1] = {df};
-    double ya[1], ye[1];
-    m_rcp_n<1>(xa, ya);
-    m_exp_n<1>(xe, ye);
-    inv_ratio = ya[0];
-    ef = ye[0];
-  }
+  const double inv_ratio = m_rcp(ratio);
   const double vr = v * inv_ratio;
   double mt[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) mt[k] = isown ? ce[k] * inv_ratio : fma(-ce[k], vr, cg[k]);
-  const double q = ratio * ef;                                     // psi'/psi
+  double q, Gt[3];
   bool acc;
   if (METROP == MOLE_METROP_DIFFUSE) {
     // Frobenius norms over ALL electrons' drift (metrop.rs:182-193)
-    double Gt[3], G1[3], c1[5];
     sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], mt, Gt);
-    const double* minv1 = L.sm + SJ_OFF_MINV + (spin ^ 1) * 25;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) c1[k] = minv1[k * 5 + L.gl];
-    sj_gradlnD(c, L.x[1], L.orb[1], c1, G1);
+    const double* const G1 = L.G[1];
     double sh = 0.0, sl = 0.0;
     const double m0 = L.val[0] ? 1.0 : 0.0, m1 = L.val[1] ? 1.0 : 0.0;
 #pragma unroll
@@ -154,17 +140,19 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     }
     if (L.wr) { mb[MB_RIN + 20 + L.gl] = sh; mb[MB_RIN + 25 + L.gl] = sl; }
     sj_sync();
-    // ---- D: t_high and t_low, two chains together
+    // ---- D: exp(df), t_high and t_low: three chains together
     const double* rh = mb + MB_RIN + 20;
     const double* rl = mb + MB_RIN + 25;
-    const double targ[2] = {-((((rh[0] + rh[1]) + rh[2]) + rh[3]) + rh[4]) * inv2tau,
+    const double targ[3] = {df, -((((rh[0] + rh[1]) + rh[2]) + rh[3]) + rh[4]) * inv2tau,
                             -((((rl[0] + rl[1]) + rl[2]) + rl[3]) + rl[4]) * inv2tau};
-    double tv[2];
-    m_exp_n<2, true>(targ, tv);
+    double tv[3];
+    m_exp_n<3>(targ, tv);
+    q = ratio * tv[0];                                             // psi'/psi
     const bool node = !(ratio > 0.0);                              // signum(psi') != signum(psi) or NaN, :178-180
-    const double A = sj_clamp_acceptance(tv[0] * (q * q) / tv[1], compat);   // :195
+    const double A = sj_clamp_acceptance(tv[1] * (q * q) / tv[2], compat);   // :195
     acc = !node && (A > u_acc);
   } else {
+    q = ratio * m_exp(df);
     acc = sj_clamp_acceptance(q * q, compat) > u_acc;              // metrop.rs:80
   }
   if (acc) {
@@ -173,9 +161,12 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
       for (int qq = 0; qq < 3; ++qq) L.x[0][qq] = xn[qq];
 #pragma unroll
       for (int qq = 0; qq < 5; ++qq) L.orb[0][qq] = on[qq];
-      if (L.act)
+    }
+    if (METROP == MOLE_METROP_DIFFUSE) {
 #pragma unroll
-        for (int qq = 0; qq < 3; ++qq) L.sm[SJ_OFF_XS + sid_e * 3 + qq] = xn[qq];
+      for (int qq = 0; qq < 3; ++qq) L.G[0][qq] = Gt[qq];
+    } else {
+      sj_gradlnD(c, L.x[0], L.orb[0], mt, L.G[0]);
     }
     if (L.act) {
       double* mw = L.sm + SJ_OFF_MINV + spin * 25;

@@ -394,9 +394,20 @@ def test_dmc_hydrogen_energy(mole):
 def test_vmc_sr_slater_jastrow_p7_matches_oracle(mole, orc):
     """SR with P = 7 (untested upstream, SURVEY §4 gaps): Be Slater-Jastrow, 6 workers, 3 iterations;
     energies, blocking errors and all seven parameters per iteration against the oracle's raw-sample path."""
-    c = cases()["sj_be"]
+    # Be uses only the 1s/2s orbitals: d psi/d zeta3 == 0, S is singular -> Error::LinalgError on both sides
+    cb = cases()["sj_be"]
+    with pytest.raises(RuntimeError):
+        orc.vmc_run_optimization(cb["owf"], cb["oham"], orc.run_options(orc.METROP_DIFFUSE, 0.05, nan_reject=1),
+                                 orc.Optimizer(orc.OPT_SR, 7, 0.02), SEED0, orc.init_uniform(SEED0, 0, 4), 1, 360, 10, 6)
+    wfb, opb = cb["make"](mole)
+    obsb = mole.operators(**{"Energy": opb, "Parameter gradient": mole.ParameterGradient, "Wavefunction value": mole.WavefunctionValue})
+    with pytest.raises(mole.MoleError) as ei:
+        mole.VmcRunner(mole.Sampler.new(wfb, mole.MetropolisDiffuse.from_rng(0.05, SEED0), obsb),
+                       mole.StochasticReconfiguration(0.02, 7)).run_optimization(1, 360, 10, 6)
+    assert ei.value.code == mole.ffi.ERR_LINALG
+    c = cases()["sj_ne"]
     iters, total, bs, nw = 3, 6 * 60, 10, 6
-    cfg0 = orc.init_uniform(SEED0, 0, 4)
+    cfg0 = orc.init_uniform(SEED0, 0, 10)
     opts = orc.run_options(orc.METROP_DIFFUSE, 0.05, nan_reject=1)
     ropt = orc.Optimizer(orc.OPT_SR, 7, 0.02)
     ref = orc.vmc_run_optimization(c["owf"], c["oham"], opts, ropt, SEED0, cfg0, iters, total, bs, nw)
