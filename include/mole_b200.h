@@ -304,7 +304,8 @@ int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_
 /* sustained DFMA throughput of the device (TFLOP/s) measured with a register-resident FMA chain */
 int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops);
 /* evaluates the kernels' branch-free fp64 elementary functions on the device (accuracy tests):
- * which = 0 exp, 1 reciprocal, 2 reciprocal square root, 3 square root */
+ * which = 0 exp, 1 reciprocal, 2 reciprocal square root, 3 square root, 4 natural log,
+ * 5 / 6 sine / cosine of a fraction of a full turn */
 int32_t mole_math_probe(mole_ctx_t ctx, int32_t which, const double* in, int64_t n, double* out);
 /* number of kernels this library has launched on ctx since creation */
 int32_t mole_ctx_launch_count(mole_ctx_t ctx, int64_t* n);

@@ -634,7 +634,7 @@ int32_t mole_branch_sources(mole_ens_t e, int32_t* src) {
 
 // ------------------------------------------------------------------ math probe (accuracy tests)
 int32_t mole_math_probe(mole_ctx_t ctx, int32_t which, const double* in, int64_t n, double* out) {
-  if (!ctx || !in || !out || n < 1 || which < 0 || which > 3) return MOLE_ERR_INVALID_ARG;
+  if (!ctx || !in || !out || n < 1 || which < 0 || which > 6) return MOLE_ERR_INVALID_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
   double *d_in = nullptr, *d_out = nullptr;
   CU(ctx, cudaMalloc(&d_in, n * sizeof(double)));

@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 #include "mole_internal.h"
+#define MOLE_HOST_ONLY   // only the host-callable Philox helpers of mole_rng.cuh are needed here
 #include "mole_rng.cuh"
 
 RngKey mole_key_from_seed(const uint8_t seed[32]) {

@@ -406,7 +406,15 @@ __global__ void math_probe_kernel(int which, const double* __restrict__ in, int6
     case 0: y = m_exp(x); break;
     case 1: y = m_rcp(x); break;
     case 2: y = m_rsqrt(x); break;
-    default: y = m_sqrt_rsqrt(x, r); break;
+    case 3: y = m_sqrt_rsqrt(x, r); break;
+    case 4: { const double a[1] = {x}; double o[1]; m_log_n<1>(a, o); y = o[0]; break; }
+    default: {
+      const double a[1] = {x};
+      double s[1], c[1];
+      m_sincos_turn_n<1>(a, s, c);
+      y = which == 5 ? s[0] : c[0];
+      break;
+    }
   }
   out[i] = y;
 }

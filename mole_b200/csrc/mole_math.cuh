@@ -148,4 +148,84 @@ MOLE_D double m_exp(double x) {
   return y[0];
 }
 
+// ln(x) for finite normal x > 0.  x = m 2^e, m in [sqrt(1/2), sqrt 2); ln m = 2 atanh(s), s = (m-1)/(m+1),
+// atanh(s)/s = 1 + z P(z), z = s^2 <= 0.0295, P degree 8 (max relative error 5e-19 before rounding).
+//   [0] ln2 hi  [1] ln2 lo  [2..10] P coefficients
+__constant__ double c_mlog[11] = {6.93147180369123816490e-01, 1.90821492927058770002e-10,
+                                  0.3333333333333333, 0.19999999999999996, 0.14285714285717704, 0.11111111109922116,
+                                  0.09090909297884532, 0.07692287483230453, 0.06667822920974689, 0.05843981498771078,
+                                  0.0594172619705393};
+template <int N>
+MOLE_D void m_log_n(const double (&x)[N], double (&y)[N]) {
+  double m[N], ef[N], den[N], rden[N], s[N], z[N], p[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int hi = __double2hiint(x[i]), lo = __double2loint(x[i]);
+    int e = (hi >> 20) - 1023;
+    m[i] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const bool big = m[i] > 1.4142135623730951;
+    m[i] = big ? 0.5 * m[i] : m[i];
+    e += big ? 1 : 0;
+    ef[i] = (double)e;
+    den[i] = m[i] + 1.0;
+  }
+  m_rcp_n<N>(den, rden);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = (m[i] - 1.0) * rden[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = fma(fma(-s[i], den[i], m[i] - 1.0), rden[i], s[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { z[i] = s[i] * s[i]; p[i] = c_mlog[10]; }
+#pragma unroll
+  for (int k = 9; k >= 2; --k)
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], z[i], c_mlog[k]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double s2 = s[i] + s[i];
+    const double lm = fma(s2 * z[i], p[i], s2);
+    y[i] = fma(ef[i], c_mlog[0], fma(ef[i], c_mlog[1], lm));
+  }
+}
+
+// sin and cos of a fraction of a full turn, a in [0, 1]: quarter-turn index k = rint(4a), g = 4a - k in
+// [-1/2, 1/2], sin((pi/2) g) = g S(g^2), cos((pi/2) g) = C(g^2) (max relative errors 5e-17 / 3e-17), then
+// the quadrant rotation with integer sign flips - no branches, exact argument reduction.
+__constant__ double c_msin[8] = {1.5707963267948966, -0.6459640975062463, 0.07969262624616692, -0.004681754135314819,
+                                 0.0001604411847265753, -3.5988427165242496e-06, 5.691927654951105e-08,
+                                 -6.62760087835982e-10};
+__constant__ double c_mcos[9] = {1.0, -1.2337005501361697, 0.25366950790104803, -0.020863480763352916,
+                                 0.0009192602748385314, -2.52020423627168e-05, 4.710874076696347e-07,
+                                 -6.386325241874813e-09, 6.506630612891103e-11};
+template <int N>
+MOLE_D void m_sincos_turn_n(const double (&a)[N], double (&sn)[N], double (&cs)[N]) {
+  double g[N], w[N], ps[N], pc[N];
+  int k[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double t = fma(a[i], 4.0, 6755399441055744.0);
+    k[i] = __double2loint(t);
+    g[i] = fma(a[i], 4.0, -(t - 6755399441055744.0));
+    w[i] = g[i] * g[i];
+    ps[i] = c_msin[7];
+    pc[i] = c_mcos[8];
+  }
+#pragma unroll
+  for (int q = 6; q >= 0; --q)
+#pragma unroll
+    for (int i = 0; i < N; ++i) ps[i] = fma(ps[i], w[i], c_msin[q]);
+#pragma unroll
+  for (int q = 7; q >= 0; --q)
+#pragma unroll
+    for (int i = 0; i < N; ++i) pc[i] = fma(pc[i], w[i], c_mcos[q]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    ps[i] *= g[i];
+    const bool odd = (k[i] & 1) != 0;
+    const double s0 = odd ? pc[i] : ps[i], c0 = odd ? ps[i] : pc[i];
+    sn[i] = __hiloint2double(__double2hiint(s0) ^ ((k[i] & 2) << 30), __double2loint(s0));
+    cs[i] = __hiloint2double(__double2hiint(c0) ^ (((k[i] + 1) & 2) << 30), __double2loint(c0));
+  }
+}
+
 #endif  // __CUDACC__

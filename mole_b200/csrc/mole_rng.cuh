@@ -58,17 +58,24 @@ MOLE_HD MoveDraw mole_draw_uniform4(RngKey k, uint64_t walker, uint32_t step, ui
   return MoveDraw{mole_u53(p.a, p.b), mole_u53(p.c, p.d), mole_u53(q.a, q.b), mole_u53(q.c, q.d)};
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && !defined(MOLE_HOST_ONLY)
+#include "mole_math.cuh"
 // three standard normals (Box-Muller) + one uniform: MetropolisDiffuse (metrop.rs:160,197), DmcRunner::new (dmc.rs:52-56)
+// r = sqrt(-2 ln u), angle = 2 pi (w / 2^32); the two logs, two square roots and two sin/cos go through
+// the branch-free batched math (exact argument reduction for the angles).
 __device__ __forceinline__ MoveDraw mole_draw_normal3_uniform1(RngKey k, uint64_t walker, uint32_t step, uint32_t dom,
                                                                uint32_t elec) {
   const Philox4 p = mole_draw(k, walker, step, dom, elec, 0);
   const Philox4 q = mole_draw(k, walker, step, dom, elec, 1);
-  const double r1 = sqrt(-2.0 * log(mole_u53_open(p.a, p.b)));
-  const double r2 = sqrt(-2.0 * log(mole_u53_open(q.a, q.b)));
-  double s1, c1;
-  sincospi(2.0 * ((double)p.c * 0x1.0p-32), &s1, &c1);   // angle = 2*pi*(w/2^32); sincospi reduces exactly
-  const double c2 = cospi(2.0 * ((double)p.d * 0x1.0p-32));
-  return MoveDraw{r1 * c1, r1 * s1, r2 * c2, mole_u53(q.c, q.d)};
+  const double u[2] = {mole_u53_open(p.a, p.b), mole_u53_open(q.a, q.b)};
+  double lg[2], arg[2], r[2], ri[2];
+  m_log_n<2>(u, lg);
+  arg[0] = fmax(-2.0 * lg[0], 1e-300);                   // u = 1 gives ln u = 0: keep the rsqrt seed finite (r ~ 1e-150)
+  arg[1] = fmax(-2.0 * lg[1], 1e-300);
+  m_sqrt_rsqrt_n<2>(arg, r, ri);
+  const double a[2] = {(double)p.c * 0x1.0p-32, (double)p.d * 0x1.0p-32};
+  double sn[2], cs[2];
+  m_sincos_turn_n<2>(a, sn, cs);
+  return MoveDraw{r[0] * cs[0], r[0] * sn[0], r[1] * cs[1], mole_u53(q.c, q.d)};
 }
 #endif

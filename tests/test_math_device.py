@@ -36,3 +36,25 @@ def test_rcp_rsqrt_sqrt(ctx):
     assert ulp_err(ctx.math_probe(1, -x), -1.0 / x).max() <= 2.0
     assert ulp_err(ctx.math_probe(2, x), 1.0 / np.sqrt(x)).max() <= 2.0
     assert ulp_err(ctx.math_probe(3, x), np.sqrt(x)).max() <= 1.0
+
+
+def test_log_sincos_turn(ctx):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(0.0, 1.0, 300000) + 2.0 ** -53, 2.0 ** -rng.uniform(0, 53, 100000), 10.0 ** rng.uniform(-300, 300, 100000)])
+    got = ctx.math_probe(4, x)
+    ref = np.log(x)
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) < 4.5e-16
+    assert ctx.math_probe(4, np.array([1.0]))[0] == 0.0
+    a = np.concatenate([rng.uniform(0.0, 1.0, 400000), np.arange(0, 2 ** 12) / 2.0 ** 12, [0.0, 0.25, 0.5, 0.75, 1.0 - 2.0 ** -32]])
+    s, c = ctx.math_probe(5, a), ctx.math_probe(6, a)
+    # numpy's sin(2*pi*a) carries the rounding of 2*pi*a (~9e-16 in the angle); mpmath on a subset is the tight check
+    assert np.max(np.abs(s - np.sin(2 * np.pi * a))) < 2e-15 and np.max(np.abs(c - np.cos(2 * np.pi * a))) < 2e-15
+    assert np.max(np.abs(s * s + c * c - 1.0)) < 6e-16
+    import mpmath as mp
+    mp.mp.dps = 30
+    for i in range(0, 3000, 3):
+        t = 2 * mp.pi * mp.mpf(float(a[i]))
+        assert abs(mp.mpf(float(s[i])) - mp.sin(t)) < 3e-16 and abs(mp.mpf(float(c[i])) - mp.cos(t)) < 3e-16
+    # exact quadrant values (numpy's sin(2 pi a) is not exact there)
+    assert list(ctx.math_probe(5, np.array([0.0, 0.25, 0.5, 0.75]))) == [0.0, 1.0, 0.0, -1.0]
+    assert list(ctx.math_probe(6, np.array([0.0, 0.25, 0.5, 0.75]))) == [1.0, 0.0, -1.0, 0.0]
