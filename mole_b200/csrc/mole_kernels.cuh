@@ -114,7 +114,7 @@ MOLE_D bool mole_move_state(const WfParams& p, Walker<WF>& wk, int e, double par
     return false;
   } else {
     const MoveDraw d = mole_draw_normal3_uniform1(key, wid, step, DOM_MOVE, (uint32_t)e);
-    const double inv_o = 1.0 / wk.psi;
+    const double inv_o = m_rcp(wk.psi);
     xn[0] = (wk.st.x[3 * e] + wk.g[3 * e] * inv_o * param) + sd * d.a;           // metrop.rs:155-160
     xn[1] = (wk.st.x[3 * e + 1] + wk.g[3 * e + 1] * inv_o * param) + sd * d.b;
     xn[2] = (wk.st.x[3 * e + 2] + wk.g[3 * e + 2] * inv_o * param) + sd * d.c;
@@ -125,7 +125,7 @@ MOLE_D bool mole_move_state(const WfParams& p, Walker<WF>& wk, int e, double par
     WF::grad(p, tr, gn);
     // node test, metrop.rs:178-180 (signum of NaN is NaN and NaN != NaN rejects)
     if (isnan(pn) || isnan(wk.psi) || (signbit(pn) != signbit(wk.psi))) return false;
-    const double inv_n = 1.0 / pn;
+    const double inv_n = m_rcp(pn);
     double sh = 0.0, sl = 0.0;                                   // Frobenius norms over ALL electrons, :182-193
 #pragma unroll
     for (int i = 0; i < 3 * NE; ++i) {
@@ -135,7 +135,11 @@ MOLE_D bool mole_move_state(const WfParams& p, Walker<WF>& wk, int e, double par
       sh = fma(a, a, sh);
       sl = fma(b, b, sl);
     }
-    const double th = exp(-sh / (2.0 * param)), tl = exp(-sl / (2.0 * param));
+    const double i2t = 0.5 / param;
+    const double targ[2] = {-sh * i2t, -sl * i2t};
+    double tv[2];
+    m_exp_n<2, true>(targ, tv);                                  // t_high, t_low as two interleaved chains
+    const double th = tv[0], tl = tv[1];
     const double A = mole_clamp_acceptance(th * (pn * pn) / (tl * (wk.psi * wk.psi)), compat);     // :195
     if (A > d.u) {
       wk.st = tr;
@@ -160,7 +164,7 @@ MOLE_D double mole_local_energy(const WfParams& p, const HamParams& h, const typ
   }
   if (h.kind != MOLE_OP_KINETIC) hpsi = fma(mole_potential<WF::NE>(h, st.x), psi, hpsi);
   hpsi_out = hpsi;
-  return hpsi / psi;
+  return hpsi * m_rcp(psi);
 }
 
 // ------------------------------------------------------------------ init
@@ -277,12 +281,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepParams 
       const int64_t si = s - sp.n_discard;
       // Sampler::sample, samplers.rs:81-104
       double el = 0.0, hpsi, kin_psi = 0.0;
+      const double inv = m_rcp(wk.psi);
       if (want_e) {
         el = mole_local_energy<WF>(p, sp.ham, wk.st, wk.psi, hpsi, kin_psi);
         acc.v[ACC_N] += 1.0;
         acc.v[ACC_E] += el;
         acc.v[ACC_E2] = fma(el, el, acc.v[ACC_E2]);
-        acc.v[ACC_T] += kin_psi / wk.psi;
+        acc.v[ACC_T] += kin_psi * inv;
         blk += el;
         if (++fill == sp.block_size) {                          // block means, vmc.rs:158-164
           const double bm = blk / (double)sp.block_size;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepParams 
         if (sp.tr_energy) sp.tr_energy[(size_t)si * W + w] = el;
       }
       if (sp.observables & MOLE_OBS_KINETIC) {
-        const double k = want_e ? kin_psi / wk.psi : -0.5 * WF::lap(p, wk.st) / wk.psi;
+        const double k = want_e ? kin_psi * inv : -0.5 * WF::lap(p, wk.st) * inv;
         if (sp.tr_kinetic) sp.tr_kinetic[(size_t)si * W + w] = k;
       }
       acc.v[ACC_PSI] += wk.psi;
@@ -303,7 +308,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepParams 
       if (OPT && NP > 0) {
         double pg[NP > 0 ? NP : 1], o[NP > 0 ? NP : 1];
         WF::pgrad(p, wk.st, pg);
-        const double inv = 1.0 / wk.psi;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           // intended O_k = d_k psi / psi; MOLE_COMPAT_VECTOR_DIV: stored sample 1/d_k psi, O_k = 1/(psi d_k psi)

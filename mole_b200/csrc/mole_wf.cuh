@@ -4,25 +4,28 @@
 // Each kind mirrors one user impl of Function / Differentiate / Optimize in the reference's
 // examples/ and tests/ (file:line next to each struct).  Unlike the reference, which recomputes
 // every norm and exponential on every call, a kind keeps the per-electron
-// radial quantities in a State so that a single-electron move re-evaluates only what changed.
+// radial quantities (r, 1/r, exp(-alpha r)) in a State so that a single-electron move re-evaluates
+// only what changed and no formula needs a division.  Square roots, reciprocals and exponentials go
+// through the branch-free batched math of mole_math.cuh (<= 2 ulp, far inside the 1e-10 parity bar).
 // value/gradient/laplacian keep the reference's meaning: UN-normalised psi, grad psi, sum_i lap_i psi.
 #pragma once
 #include "mole_internal.h"
+#include "mole_math.cuh"
 
 enum { K_STO_1S = 0, K_GAUSSIAN = 1, K_STO_PRODUCT = 2, K_H2_HL_STO = 3, K_H2P_PRODUCT = 4, K_SLATER_JASTROW = 5,
        K_CONSTANT = 6 };
 
 template <int KIND> struct WfDev;
 
-MOLE_D double mole_norm3(double a, double b, double c) { return sqrt(fma(c, c, fma(b, b, a * a))); }
+MOLE_D double mole_norm2_3(double a, double b, double c) { return fma(c, c, fma(b, b, a * a)); }
 
 // ---- 1-electron STO, psi = exp(-alpha |x|)                 examples/dmc.rs:106-143
 template <> struct WfDev<K_STO_1S> {
   static constexpr int NE = 1, NP = 1;
-  struct State { double x[3]; double r, e; };
+  struct State { double x[3]; double r, ir, e; };
   MOLE_D static void init(const WfParams& p, State& s) {
-    s.r = mole_norm3(s.x[0], s.x[1], s.x[2]);
-    s.e = exp(-p.p[0] * s.r);
+    s.r = m_sqrt_rsqrt(mole_norm2_3(s.x[0], s.x[1], s.x[2]), s.ir);
+    s.e = m_exp(-p.p[0] * s.r);
   }
   MOLE_D static void move(const WfParams& p, State& s, int, const double xn[3]) {
     s.x[0] = xn[0]; s.x[1] = xn[1]; s.x[2] = xn[2];
@@ -30,11 +33,11 @@ template <> struct WfDev<K_STO_1S> {
   }
   MOLE_D static double psi(const WfParams&, const State& s) { return s.e; }
   MOLE_D static void grad(const WfParams& p, const State& s, double* g) {
-    const double c = -p.p[0] * s.e / s.r;                     // dmc.rs:116-119
+    const double c = -p.p[0] * s.e * s.ir;                    // dmc.rs:116-119
     g[0] = c * s.x[0]; g[1] = c * s.x[1]; g[2] = c * s.x[2];
   }
   MOLE_D static double lap(const WfParams& p, const State& s) {
-    return p.p[0] * s.e / s.r * (p.p[0] * s.r - 2.0);        // dmc.rs:121-124
+    return p.p[0] * s.e * s.ir * (p.p[0] * s.r - 2.0);        // dmc.rs:121-124
   }
   MOLE_D static void pgrad(const WfParams&, const State& s, double* o) { o[0] = -s.r * s.e; }  // dmc.rs:128-130
 };
@@ -44,8 +47,8 @@ template <> struct WfDev<K_GAUSSIAN> {
   static constexpr int NE = 1, NP = 1;
   struct State { double x[3]; double n2, e; };
   MOLE_D static void init(const WfParams& p, State& s) {
-    s.n2 = fma(s.x[2], s.x[2], fma(s.x[1], s.x[1], s.x[0] * s.x[0]));
-    s.e = exp(-s.n2 / (p.p[0] * p.p[0]));
+    s.n2 = mole_norm2_3(s.x[0], s.x[1], s.x[2]);
+    s.e = m_exp(-s.n2 * m_rcp(p.p[0] * p.p[0]));
   }
   MOLE_D static void move(const WfParams& p, State& s, int, const double xn[3]) {
     s.x[0] = xn[0]; s.x[1] = xn[1]; s.x[2] = xn[2];
@@ -53,43 +56,43 @@ template <> struct WfDev<K_GAUSSIAN> {
   }
   MOLE_D static double psi(const WfParams&, const State& s) { return s.e; }
   MOLE_D static void grad(const WfParams& p, const State& s, double* g) {
-    const double c = -2.0 * s.e / (p.p[0] * p.p[0]);          // dmc.rs:56-59
+    const double c = -2.0 * s.e * m_rcp(p.p[0] * p.p[0]);     // dmc.rs:56-59
     g[0] = c * s.x[0]; g[1] = c * s.x[1]; g[2] = c * s.x[2];
   }
   MOLE_D static double lap(const WfParams& p, const State& s) {
     const double a2 = p.p[0] * p.p[0];
-    return s.e * (4.0 * s.n2 - 6.0 * a2) / (a2 * a2);         // dmc.rs:61-64
+    return s.e * (4.0 * s.n2 - 6.0 * a2) * m_rcp(a2 * a2);    // dmc.rs:61-64
   }
   MOLE_D static void pgrad(const WfParams& p, const State& s, double* o) {
-    o[0] = s.e * 2.0 * s.n2 / (p.p[0] * p.p[0] * p.p[0]);     // dmc.rs:74-79
+    o[0] = s.e * 2.0 * s.n2 * m_rcp(p.p[0] * p.p[0] * p.p[0]);   // dmc.rs:74-79
   }
 };
 
 // ---- He singlet, psi = exp(-alpha (r1 + r2))               examples/helium_atom_singlet.rs:60-118
 template <> struct WfDev<K_STO_PRODUCT> {
   static constexpr int NE = 2, NP = 1;
-  struct State { double x[6]; double r[2], e; };
+  struct State { double x[6]; double r[2], ir[2], e; };
   MOLE_D static void init(const WfParams& p, State& s) {
-    s.r[0] = mole_norm3(s.x[0], s.x[1], s.x[2]);
-    s.r[1] = mole_norm3(s.x[3], s.x[4], s.x[5]);
-    s.e = exp(-p.p[0] * (s.r[0] + s.r[1]));
+    const double n2[2] = {mole_norm2_3(s.x[0], s.x[1], s.x[2]), mole_norm2_3(s.x[3], s.x[4], s.x[5])};
+    m_sqrt_rsqrt_n<2>(n2, s.r, s.ir);
+    s.e = m_exp(-p.p[0] * (s.r[0] + s.r[1]));
   }
   MOLE_D static void move(const WfParams& p, State& s, int e, const double xn[3]) {
     s.x[3 * e] = xn[0]; s.x[3 * e + 1] = xn[1]; s.x[3 * e + 2] = xn[2];
-    s.r[e] = mole_norm3(xn[0], xn[1], xn[2]);
-    s.e = exp(-p.p[0] * (s.r[0] + s.r[1]));
+    s.r[e] = m_sqrt_rsqrt(mole_norm2_3(xn[0], xn[1], xn[2]), s.ir[e]);
+    s.e = m_exp(-p.p[0] * (s.r[0] + s.r[1]));
   }
   MOLE_D static double psi(const WfParams&, const State& s) { return s.e; }
   MOLE_D static void grad(const WfParams& p, const State& s, double* g) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const double c = -p.p[0] / s.r[e] * s.e;                // helium_atom_singlet.rs:80-81
+      const double c = -p.p[0] * s.ir[e] * s.e;               // helium_atom_singlet.rs:80-81
       g[3 * e] = c * s.x[3 * e]; g[3 * e + 1] = c * s.x[3 * e + 1]; g[3 * e + 2] = c * s.x[3 * e + 2];
     }
   }
   MOLE_D static double lap(const WfParams& p, const State& s) {
     const double al = p.p[0];                                 // helium_atom_singlet.rs:96-97
-    return al / s.r[0] * s.e * (al * s.r[0] - 2.0) + al / s.r[1] * s.e * (al * s.r[1] - 2.0);
+    return al * s.ir[0] * s.e * (al * s.r[0] - 2.0) + al * s.ir[1] * s.e * (al * s.r[1] - 2.0);
   }
   MOLE_D static void pgrad(const WfParams&, const State& s, double* o) { o[0] = -s.e * (s.r[0] + s.r[1]); }  // :102-105
 };
@@ -97,16 +100,16 @@ template <> struct WfDev<K_STO_PRODUCT> {
 // ---- H2 Heitler-London, psi = phi(x1-R/2)phi(x2+R/2) + phi(x1+R/2)phi(x2-R/2)   examples/hydrogen_molecule.rs:88-168
 template <> struct WfDev<K_H2_HL_STO> {
   static constexpr int NE = 2, NP = 1;
-  // ra[e] = |x_e - R/2|, rb[e] = |x_e + R/2| and the matching STO values
-  struct State { double x[6]; double ra[2], rb[2], ea[2], eb[2]; };
+  // per electron e: r[e][0] = |x_e - R/2|, r[e][1] = |x_e + R/2|, their reciprocals and the STO values
+  struct State { double x[6]; double r[2][2], ir[2][2], ex[2][2]; };
   MOLE_D static void one(const WfParams& p, State& s, int e) {
     const double h = 0.5 * p.geom[0];
     const double yz = fma(s.x[3 * e + 2], s.x[3 * e + 2], s.x[3 * e + 1] * s.x[3 * e + 1]);
     const double xa = s.x[3 * e] - h, xb = s.x[3 * e] + h;
-    s.ra[e] = sqrt(fma(xa, xa, yz));
-    s.rb[e] = sqrt(fma(xb, xb, yz));
-    s.ea[e] = exp(-p.p[0] * s.ra[e]);
-    s.eb[e] = exp(-p.p[0] * s.rb[e]);
+    const double n2[2] = {fma(xa, xa, yz), fma(xb, xb, yz)};
+    m_sqrt_rsqrt_n<2>(n2, s.r[e], s.ir[e]);
+    const double a[2] = {-p.p[0] * s.r[e][0], -p.p[0] * s.r[e][1]};
+    m_exp_n<2, true>(a, s.ex[e]);
   }
   MOLE_D static void init(const WfParams& p, State& s) { one(p, s, 0); one(p, s, 1); }
   MOLE_D static void move(const WfParams& p, State& s, int e, const double xn[3]) {
@@ -114,7 +117,7 @@ template <> struct WfDev<K_H2_HL_STO> {
     one(p, s, e);
   }
   MOLE_D static double psi(const WfParams&, const State& s) {
-    return fma(s.ea[0], s.eb[1], s.eb[0] * s.ea[1]);         // hydrogen_molecule.rs:96-99
+    return fma(s.ex[0][0], s.ex[1][1], s.ex[0][1] * s.ex[1][0]);   // hydrogen_molecule.rs:96-99
   }
   MOLE_D static void grad(const WfParams& p, const State& s, double* g) {
     const double h = 0.5 * p.geom[0];
@@ -122,59 +125,59 @@ template <> struct WfDev<K_H2_HL_STO> {
     for (int e = 0; e < 2; ++e) {
       const int o = 1 - e;
       // grad_e psi = phi(x_o + R/2) grad phi(x_e - R/2) + phi(x_o - R/2) grad phi(x_e + R/2)   (:114-119)
-      const double ca = -p.p[0] * s.ea[e] / s.ra[e] * s.eb[o];
-      const double cb = -p.p[0] * s.eb[e] / s.rb[e] * s.ea[o];
+      const double ca = -p.p[0] * s.ex[e][0] * s.ir[e][0] * s.ex[o][1];
+      const double cb = -p.p[0] * s.ex[e][1] * s.ir[e][1] * s.ex[o][0];
       g[3 * e] = fma(ca, s.x[3 * e] - h, cb * (s.x[3 * e] + h));
       g[3 * e + 1] = (ca + cb) * s.x[3 * e + 1];
       g[3 * e + 2] = (ca + cb) * s.x[3 * e + 2];
     }
   }
-  MOLE_D static double sto_lap(double al, double r, double e) { return al * e / r * (al * r - 2.0); }  // :51-53
+  MOLE_D static double sto_lap(double al, double r, double ir, double e) { return al * e * ir * (al * r - 2.0); }  // :51-53
   MOLE_D static double lap(const WfParams& p, const State& s) {
     const double al = p.p[0];                                  // :129-133
-    return (s.eb[1] * sto_lap(al, s.ra[0], s.ea[0]) + s.ea[1] * sto_lap(al, s.rb[0], s.eb[0])) +
-           (s.eb[0] * sto_lap(al, s.ra[1], s.ea[1]) + s.ea[0] * sto_lap(al, s.rb[1], s.eb[1]));
+    return (s.ex[1][1] * sto_lap(al, s.r[0][0], s.ir[0][0], s.ex[0][0]) + s.ex[1][0] * sto_lap(al, s.r[0][1], s.ir[0][1], s.ex[0][1])) +
+           (s.ex[0][1] * sto_lap(al, s.r[1][0], s.ir[1][0], s.ex[1][0]) + s.ex[0][0] * sto_lap(al, s.r[1][1], s.ir[1][1], s.ex[1][1]));
   }
   MOLE_D static void pgrad(const WfParams&, const State& s, double* o) {
     // d/dalpha of each STO is -r e (:55-57); product rule over the two terms (:144-153)
-    o[0] = s.ea[0] * (-s.rb[1] * s.eb[1]) + (-s.ra[0] * s.ea[0]) * s.eb[1] +
-           s.eb[0] * (-s.ra[1] * s.ea[1]) + (-s.rb[0] * s.eb[0]) * s.ea[1];
+    o[0] = s.ex[0][0] * (-s.r[1][1] * s.ex[1][1]) + (-s.r[0][0] * s.ex[0][0]) * s.ex[1][1] +
+           s.ex[0][1] * (-s.r[1][0] * s.ex[1][0]) + (-s.r[0][1] * s.ex[0][1]) * s.ex[1][0];
   }
 };
 
 // ---- H2+ product ansatz, psi = phi(x - R/2) phi(x + R/2)   tests/hydrogen_molecular_ion_lcao.rs:66-92
 template <> struct WfDev<K_H2P_PRODUCT> {
   static constexpr int NE = 1, NP = 0;
-  struct State { double x[3]; double r1, r2, e1, e2; };
+  struct State { double x[3]; double r[2], ir[2], ex[2]; };
   MOLE_D static void init(const WfParams& p, State& s) {
     const double h = 0.5 * p.geom[0];
     const double yz = fma(s.x[2], s.x[2], s.x[1] * s.x[1]);
     const double xa = s.x[0] - h, xb = s.x[0] + h;
-    s.r1 = sqrt(fma(xa, xa, yz));
-    s.r2 = sqrt(fma(xb, xb, yz));
-    s.e1 = exp(-p.p[0] * s.r1);
-    s.e2 = exp(-p.p[0] * s.r2);
+    const double n2[2] = {fma(xa, xa, yz), fma(xb, xb, yz)};
+    m_sqrt_rsqrt_n<2>(n2, s.r, s.ir);
+    const double a[2] = {-p.p[0] * s.r[0], -p.p[0] * s.r[1]};
+    m_exp_n<2, true>(a, s.ex);
   }
   MOLE_D static void move(const WfParams& p, State& s, int, const double xn[3]) {
     s.x[0] = xn[0]; s.x[1] = xn[1]; s.x[2] = xn[2];
     init(p, s);
   }
-  MOLE_D static double psi(const WfParams&, const State& s) { return s.e1 * s.e2; }
+  MOLE_D static double psi(const WfParams&, const State& s) { return s.ex[0] * s.ex[1]; }
   MOLE_D static void grad(const WfParams& p, const State& s, double* g) {
     const double h = 0.5 * p.geom[0];
-    const double c1 = -p.p[0] * s.e1 / s.r1 * s.e2;           // phi(r2) grad phi(r1)
-    const double c2 = -p.p[0] * s.e2 / s.r2 * s.e1;           // phi(r1) grad phi(r2)   (:82)
+    const double c1 = -p.p[0] * s.ex[0] * s.ir[0] * s.ex[1];   // phi(r2) grad phi(r1)
+    const double c2 = -p.p[0] * s.ex[1] * s.ir[1] * s.ex[0];   // phi(r1) grad phi(r2)   (:82)
     g[0] = fma(c1, s.x[0] - h, c2 * (s.x[0] + h));
     g[1] = (c1 + c2) * s.x[1];
     g[2] = (c1 + c2) * s.x[2];
   }
   MOLE_D static double lap(const WfParams& p, const State& s) {
     const double al = p.p[0], h = 0.5 * p.geom[0];
-    const double l1 = al * s.e1 / s.r1 * (al * s.r1 - 2.0), l2 = al * s.e2 / s.r2 * (al * s.r2 - 2.0);
-    const double g1 = -al * s.e1 / s.r1, g2 = -al * s.e2 / s.r2;
+    const double g1 = -al * s.ex[0] * s.ir[0], g2 = -al * s.ex[1] * s.ir[1];
+    const double l1 = -g1 * (al * s.r[0] - 2.0), l2 = -g2 * (al * s.r[1] - 2.0);
     const double xa = s.x[0] - h, xb = s.x[0] + h;
     const double dot = (g1 * xa) * (g2 * xb) + (g1 * s.x[1]) * (g2 * s.x[1]) + (g1 * s.x[2]) * (g2 * s.x[2]);
-    return s.e1 * l2 + s.e2 * l1 + 2.0 * dot;                 // :88-90
+    return s.ex[0] * l2 + s.ex[1] * l1 + 2.0 * dot;           // :88-90
   }
   MOLE_D static void pgrad(const WfParams&, const State&, double*) {}
 };
@@ -198,11 +201,15 @@ MOLE_D double mole_potential(const HamParams& h, const double* x) {
   double v = 0.0;
   if (h.kind == MOLE_OP_IONIC_POT || h.kind == MOLE_OP_IONIC || h.kind == MOLE_OP_ELECTRONIC) {
     double pot = 0.0;                                         // IonicPotential::value, operator.rs:25-36
-    for (int i = 0; i < h.n_ions; ++i)
+    for (int i = 0; i < h.n_ions; ++i) {
+      double d2[NE], ri[NE];
 #pragma unroll
       for (int j = 0; j < NE; ++j)
-        pot -= h.ion_z[i] / mole_norm3(x[3 * j] - h.ion_pos[3 * i], x[3 * j + 1] - h.ion_pos[3 * i + 1],
-                                       x[3 * j + 2] - h.ion_pos[3 * i + 2]);
+        d2[j] = mole_norm2_3(x[3 * j] - h.ion_pos[3 * i], x[3 * j + 1] - h.ion_pos[3 * i + 1], x[3 * j + 2] - h.ion_pos[3 * i + 2]);
+      m_rsqrt_n<NE>(d2, ri);
+#pragma unroll
+      for (int j = 0; j < NE; ++j) pot = fma(-h.ion_z[i], ri[j], pot);
+    }
     v = pot + h.ionic_repulsion;
   }
   if (h.kind == MOLE_OP_ELEC_POT || h.kind == MOLE_OP_ELECTRONIC) {
@@ -211,7 +218,7 @@ MOLE_D double mole_potential(const HamParams& h, const double* x) {
     for (int i = 0; i < NE; ++i)
 #pragma unroll
       for (int j = i + 1; j < NE; ++j)
-        pot += 1.0 / mole_norm3(x[3 * i] - x[3 * j], x[3 * i + 1] - x[3 * j + 1], x[3 * i + 2] - x[3 * j + 2]);
+        pot += m_rsqrt(mole_norm2_3(x[3 * i] - x[3 * j], x[3 * i + 1] - x[3 * j + 1], x[3 * i + 2] - x[3 * j + 2]));
     v += pot;
   }
   if (h.kind == MOLE_OP_HARMONIC) {                           // custom_operator.rs:56-58
