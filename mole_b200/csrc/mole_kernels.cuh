@@ -427,6 +427,7 @@ __global__ void math_probe_kernel(int which, const double* __restrict__ in, int6
 __global__ void dfma_peak_kernel(double* out, int iters, double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, c = 1e-9;
+#pragma unroll 8
   for (int i = 0; i < iters; ++i) {
     a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);

@@ -23,10 +23,16 @@
 #include "mole_math.cuh"
 
 constexpr int SJ_WPW = 6;                      // walkers per warp
-constexpr int SJ_WARPS = 4;
+#ifndef MOLE_SJ_WARPS
+#define MOLE_SJ_WARPS 4
+#endif
+#ifndef MOLE_SJ_MIN_CTAS
+#define MOLE_SJ_MIN_CTAS 2
+#endif
+constexpr int SJ_WARPS = MOLE_SJ_WARPS;
 constexpr int SJ_THREADS = 32 * SJ_WARPS;
 constexpr int SJ_WPB = SJ_WPW * SJ_WARPS;       // walkers per CTA
-constexpr int SJ_MIN_CTAS = 2;                  // CTAs per SM the register budget is tuned for
+constexpr int SJ_MIN_CTAS = MOLE_SJ_MIN_CTAS;   // CTAs per SM the register budget is tuned for
 constexpr int SJ_NPAIR = 45;
 constexpr int SJ_PCV = 5;                       // cached values per pair: u, g/r, lap term, 1/r, R
 // shared memory per walker (offsets in doubles)
