@@ -197,7 +197,7 @@ typedef struct {
   int32_t block_size;     /* blocking-analysis block, vmc.rs:150-170 (>=1)                          */
   uint32_t observables;   /* MOLE_OBS_* mask; accumulators are updated for the enabled ones         */
   uint32_t compat;        /* MOLE_COMPAT_*                                                          */
-  int32_t reserved;
+  uint32_t flags;         /* MOLE_SWEEP_*: keep / append the E_L series on the device (see "series") */
   /* optional per-sample traces, HOST pointers, sample-major: trace[s*W + w], s over sampled sweeps */
   double* energy_trace;   /* E_L                                   (W*n_samples) */
   double* wfvalue_trace;  /* psi  (the stored "Wavefunction value") (W*n_samples) */
@@ -299,6 +299,67 @@ int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_
                          double time_step, double* reference_energy /* in/out */, int32_t num_iterations,
                          int32_t block_size, int32_t num_eq_blocks, double* energies, double* errors,
                          int32_t* n_out, double* step_energies /* nullable, num_iterations */);
+
+/* ---- series statistics on the device ---------------------------------------------
+ * Port of the reference's offline analysis tool scripts/statfor.rs (mean :17-19, variance :23-26,
+ * correlation :31-54, blocking :58-81; scripts/statfor.py:21-40 is the same correlation()) applied to
+ * every walker's local-energy series without the series leaving the GPU.  A sweep called with
+ * MOLE_SWEEP_KEEP_SERIES stores its E_L samples in a device buffer owned by the ensemble
+ * (MOLE_SWEEP_APPEND_SERIES appends to it); mole_series_analyze then runs statfor per walker and
+ * returns walker-averaged results (and, optionally, the per-walker ones). */
+enum { MOLE_SWEEP_KEEP_SERIES = 1, MOLE_SWEEP_APPEND_SERIES = 2 };
+#define MOLE_SERIES_MAX_LAG 200 /* MAX_STEPS, statfor.rs:32 */
+typedef struct {
+  double average;  /* statfor.rs:17-19              */
+  double variance; /* ddof = 1, statfor.rs:23-26,87 */
+  double tcorr;    /* statfor.rs:35-52              */
+  double n_eff;    /* nsteps / tcorr, :53           */
+  double sigma;    /* sqrt(variance*tcorr/nsteps)   */
+} mole_series_stats;
+/* number of samples per walker currently held */
+int32_t mole_series_length(mole_ens_t ens, int64_t* n);
+int32_t mole_series_clear(mole_ens_t ens);
+/* block-size schedule of statfor.rs:59-66 for a series of n samples: 1, 1+step, ... <= n/20.
+ * sizes may be NULL to query the count. */
+int32_t mole_series_block_sizes(int64_t n, int32_t* sizes, int32_t* n_sizes);
+/* statfor per walker.  drop_last != 0 analyses data[..len-1] like statfor.rs:85.
+ * mean_stats: the five quantities averaged over walkers; corr[lags]: walker-mean autocorrelation,
+ * lags = min(MOLE_SERIES_MAX_LAG, n-1) (nullable); block_errors[n_sizes]: walker-mean blocking error
+ * for the given block sizes (nullable); per_walker[W], per_walker_corr[lags*W] (lag-major) and
+ * per_walker_block_errors[n_sizes*W]: host buffers for the unreduced results (nullable; parity tests). */
+int32_t mole_series_analyze(mole_ens_t ens, int32_t drop_last, mole_series_stats* mean_stats, double* corr,
+                            int32_t n_sizes, const int32_t* block_sizes, double* block_errors,
+                            mole_series_stats* per_walker, double* per_walker_corr, double* per_walker_block_errors);
+/* one walker's series to the host, or as the text format scripts/statfor.py:17-19 and statfor.rs:7-13
+ * read (one float per line, 17 significant digits) */
+int32_t mole_series_get(mole_ens_t ens, int64_t walker, double* out);
+int32_t mole_series_write_text(mole_ens_t ens, int64_t walker, const char* path);
+
+/* ---- Log (montecarlo/src/traits.rs:44-47) ----------------------------------------------------------
+ * Runner::run calls logger.log(data) after every sample and prints its output once per block
+ * (montecarlo.rs:31-43).  The ensemble equivalent is a callback per block fed with block-level
+ * reductions over all walkers of this rank; one launch per block. */
+typedef struct {
+  int32_t block_nr;       /* 1.. (block 0 is the discarded equilibration block) */
+  int32_t block_size;
+  double n_samples;       /* samples in this block, all walkers                 */
+  double block_energy;    /* mean E_L over this block                           */
+  double running_energy;  /* mean E_L over all sampled blocks so far            */
+  double block_kinetic;   /* mean -0.5 lap/psi (MOLE_OBS_KINETIC)               */
+  double block_wfvalue;   /* mean psi (MOLE_OBS_WFVALUE)                        */
+  double acceptance;      /* accepted / proposed single-electron moves, block   */
+} mole_block_log;
+typedef void (*mole_log_fn)(void* user, const mole_block_log* data);
+int32_t mole_runner_run_logged(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, uint32_t observables,
+                               uint32_t compat, int32_t steps, int32_t block_size, uint32_t sweep_flags,
+                               mole_log_fn log, void* user);
+
+/* ---- checkpoint / restart ----------------------------------------------------------
+ * Binary dump of the ensemble: configurations, weights, block partial sums, accumulators, cached E_L,
+ * step counter and Philox key.  The random streams are counter-based, so a restored ensemble continues
+ * bit-identically. */
+int32_t mole_ensemble_save(mole_ens_t ens, const char* path);
+int32_t mole_ensemble_load(mole_ens_t ens, const char* path); /* W and N_e must match */
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 /* sustained DFMA throughput of the device (TFLOP/s) measured with a register-resident FMA chain */

@@ -10,7 +10,7 @@ from .api import (Context, default_context, comm_unique_id, derive_seed, WaveFun
                   HeliumAtomWaveFunction, HydrogenMoleculeWaveFunction, H2WF, SlaterJastrow, WaveFunctionMock,
                   LocalOperator, KineticEnergy, IonicPotential, ElectronicPotential, IonicHamiltonian,
                   ElectronicHamiltonian, HarmonicHamiltonian, ParameterGradient, WavefunctionValue, operators,
-                  MetropolisBox, MetropolisDiffuse, Ensemble, acc_finalize, Optimizer, SteepestDescent, MomentumDescent,
+                  MetropolisBox, MetropolisDiffuse, Ensemble, acc_finalize, series_block_sizes, Optimizer, SteepestDescent, MomentumDescent,
                   NesterovMomentum, OnlineLbfgs, StochasticReconfiguration, MonteCarloResult, Sampler, Runner,
                   VmcRunner, SRBrancher, SimpleBranching, DmcRunner)
 

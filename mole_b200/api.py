@@ -494,13 +494,15 @@ class Ensemble:
         return out
 
     def sweep(self, wf, metrop, op, n_sweeps, n_discard=0, block_size=1, observables=ffi.OBS_ENERGY, compat=0,
-              traces=()):
+              traces=(), keep_series=False, append_series=False):
         """mole_sweep.  traces: subset of ("energy","wfvalue","kinetic","pgrad","accept").
-        Returned traces are indexed [walker, sample(, k)] / accept [walker, sweep, electron]."""
+        Returned traces are indexed [walker, sample(, k)] / accept [walker, sweep, electron].
+        keep_series / append_series: keep the E_L samples on the device for series_analyze()."""
         W, ne, P = self.n_walkers, self.n_elec, wf.num_parameters()
         ns = n_sweeps - n_discard
         a = ffi.SweepArgs()
         a.n_sweeps, a.n_discard, a.block_size, a.observables, a.compat = n_sweeps, n_discard, block_size, observables, compat
+        a.flags = (ffi.SWEEP_KEEP_SERIES if keep_series else 0) | (ffi.SWEEP_APPEND_SERIES if append_series else 0)
         bufs = {}
         if "energy" in traces and ns > 0:
             bufs["energy"] = np.empty((ns, W)); a.energy_trace = bufs["energy"].ctypes.data
@@ -517,6 +519,68 @@ class Ensemble:
         for k, v in bufs.items():
             out[k] = np.ascontiguousarray(np.moveaxis(v, -1, 0))   # walker-major
         return out
+
+    # ---- series statistics on the device (scripts/statfor.rs) ----
+    def series_length(self):
+        n = C.c_int64()
+        self._c(lib().mole_series_length(self.handle, C.byref(n)))
+        return n.value
+
+    def series_clear(self):
+        self._c(lib().mole_series_clear(self.handle))
+
+    def series_analyze(self, block_sizes=None, drop_last=False, per_walker=False):
+        """statfor per walker on the kept E_L series; returns walker means (and per-walker arrays).
+        block_sizes=None uses the reference's schedule (statfor.rs:59-66)."""
+        n = self.series_length() - (1 if drop_last else 0)
+        if block_sizes is None:
+            block_sizes = series_block_sizes(n)
+        bs = np.ascontiguousarray(block_sizes, dtype=np.int32)
+        lags = max(min(ffi.SERIES_MAX_LAG, n - 1), 0)
+        W = self.n_walkers
+        ms = ffi.SeriesStats()
+        corr, berr = np.empty(lags), np.empty(bs.size)
+        pw = np.empty((W, 5)) if per_walker else None
+        pwc = np.empty((lags, W)) if per_walker else None
+        pwb = np.empty((bs.size, W)) if per_walker else None
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+        self._c(lib().mole_series_analyze(self.handle, C.c_int32(1 if drop_last else 0), C.byref(ms), ptr(corr),
+                                          C.c_int32(bs.size), ptr(bs), ptr(berr), ptr(pw), ptr(pwc), ptr(pwb)))
+        out = dict(average=ms.average, variance=ms.variance, tcorr=ms.tcorr, n_eff=ms.n_eff, sigma=ms.sigma,
+                   corr=corr, block_sizes=bs, block_errors=berr)
+        if per_walker:
+            out.update(per_walker=pw, per_walker_corr=pwc.T.copy(), per_walker_block_errors=pwb.T.copy())
+        return out
+
+    def series_get(self, walker):
+        out = np.empty(self.series_length())
+        self._c(lib().mole_series_get(self.handle, C.c_int64(walker), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def series_write_text(self, walker, path):
+        """One float per line: the input format of scripts/statfor.py:17-19 / statfor.rs:7-13."""
+        self._c(lib().mole_series_write_text(self.handle, C.c_int64(walker), str(path).encode()))
+
+    # ---- checkpoint / restart ----
+    def save(self, path):
+        self._c(lib().mole_ensemble_save(self.handle, str(path).encode()))
+
+    def load(self, path):
+        self._c(lib().mole_ensemble_load(self.handle, str(path).encode()))
+
+    def run_logged(self, wf, metrop, op, steps, block_size, log=None, observables=ffi.OBS_ENERGY, compat=0,
+                   keep_series=False):
+        """Runner::run with a Log (montecarlo.rs:24-46): `log(dict) -> str` is called once per sampled
+        block with block-level reductions; non-empty output is printed like the reference does."""
+        def _cb(_user, d):
+            d = d.contents
+            s = log({f: getattr(d, f) for f, _ in ffi.BlockLog._fields_})
+            if s:
+                print(s)
+        cb = ffi.LOG_FN(_cb) if log is not None else C.cast(None, ffi.LOG_FN)
+        self._c(lib().mole_runner_run_logged(self.handle, wf.handle, metrop.handle, _h(op), C.c_uint32(observables),
+                                             C.c_uint32(compat), C.c_int32(steps), C.c_int32(block_size),
+                                             C.c_uint32(ffi.SWEEP_KEEP_SERIES if keep_series else 0), cb, None))
 
     def acc_reset(self):
         self._c(lib().mole_acc_reset(self.handle))
@@ -552,6 +616,16 @@ class Ensemble:
         if getattr(self, "handle", None):
             lib().mole_ensemble_destroy(self.handle)
             self.handle = None
+
+
+def series_block_sizes(n):
+    """Block-size schedule of the reference's blocking analysis (scripts/statfor.rs:59-66)."""
+    k = C.c_int32()
+    ffi.check(lib().mole_series_block_sizes(C.c_int64(n), None, C.byref(k)))
+    out = np.empty(k.value, dtype=np.int32)
+    if k.value:
+        ffi.check(lib().mole_series_block_sizes(C.c_int64(n), out.ctypes.data_as(C.c_void_p), C.byref(k)))
+    return out
 
 
 def acc_finalize(acc):
@@ -723,6 +797,14 @@ class Runner:
             if s.mask & ffi.OBS_PGRAD:
                 bufs["Parameter gradient"] = np.empty((ns, P, W))
         ens.acc_reset()
+        if self.logger is not None and not traces:
+            # Log (montecarlo/src/traits.rs:44-47): one launch per block, logger.log(block reductions) per block
+            ens.run_logged(wf, s.metropolis, s.ham, steps, block_size, log=self.logger.log, observables=s.mask,
+                           compat=s.compat)
+            acc = ens.acc_get()
+            s.acceptance_ = acc.n_accept / ne
+            self.acc = acc
+            return MonteCarloResult(wf, s.acceptance_, {})
         check(lib().mole_runner_run(ens.handle, wf.handle, s.metropolis.handle, _h(s.ham), C.c_uint32(s.mask),
                                     C.c_uint32(s.compat), C.c_int32(steps), C.c_int32(block_size),
                                     _dp(bufs.get("Energy")), _dp(bufs.get("Wavefunction value")),

@@ -5,10 +5,13 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <string>
+#include <vector>
 #include "mole_internal.h"
 #include "mole_kernels.cuh"
 #include "mole_branch.cuh"
 #include "mole_sj.cuh"
+#include "mole_stats.cuh"
 
 static std::string g_last_error;
 
@@ -221,7 +224,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->x0);
   cudaFree(e->x); cudaFree(e->x2); cudaFree(e->w); cudaFree(e->w2); cudaFree(e->el); cudaFree(e->el2);
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
-  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src);
+  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series);
   delete e;
   return MOLE_OK;
 }
@@ -448,8 +451,28 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
   sp.wf = wf->p;
   if (op) sp.ham = op->p;
 
+  // E_L series kept on the device for mole_series_analyze: the kernel writes straight into it
+  const bool keep_series = (a->flags & (MOLE_SWEEP_KEEP_SERIES | MOLE_SWEEP_APPEND_SERIES)) && nsamp > 0 &&
+                           (a->observables & MOLE_OBS_ENERGY);
+  if (keep_series) {
+    if (!(a->flags & MOLE_SWEEP_APPEND_SERIES)) e->series_n = 0;
+    const int64_t need = e->series_n + nsamp;
+    if (need > e->series_cap) {
+      const int64_t cap = std::max(need, 2 * e->series_cap);
+      double* grown = nullptr;
+      CU(ctx, cudaMalloc(&grown, (size_t)cap * W * sizeof(double)));
+      if (e->series_n > 0)
+        CU(ctx, cudaMemcpyAsync(grown, e->series, (size_t)e->series_n * W * sizeof(double), cudaMemcpyDeviceToDevice, STREAM(ctx)));
+      CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+      cudaFree(e->series);
+      e->series = grown;
+      e->series_cap = cap;
+    }
+    sp.tr_energy = e->series + (size_t)e->series_n * W;
+    e->series_n = need;
+  }
   // device staging for the optional traces
-  if (a->energy_trace && nsamp > 0) CU(ctx, cudaMalloc(&sp.tr_energy, (size_t)W * nsamp * sizeof(double)));
+  if (a->energy_trace && nsamp > 0 && !keep_series) CU(ctx, cudaMalloc(&sp.tr_energy, (size_t)W * nsamp * sizeof(double)));
   if (a->wfvalue_trace && nsamp > 0) CU(ctx, cudaMalloc(&sp.tr_wfvalue, (size_t)W * nsamp * sizeof(double)));
   if (a->kinetic_trace && nsamp > 0) CU(ctx, cudaMalloc(&sp.tr_kinetic, (size_t)W * nsamp * sizeof(double)));
   if (a->pgrad_trace && nsamp > 0 && opt) CU(ctx, cudaMalloc(&sp.tr_pgrad, (size_t)W * nsamp * np * sizeof(double)));
@@ -473,15 +496,16 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
   if (opt) e->np_last = np;
   e->el_cached = 0;
 
-  const bool any_trace = sp.tr_energy || sp.tr_wfvalue || sp.tr_kinetic || sp.tr_pgrad || sp.tr_accept;
+  const bool any_trace = (sp.tr_energy && a->energy_trace) || sp.tr_wfvalue || sp.tr_kinetic || sp.tr_pgrad || sp.tr_accept;
   if (any_trace) {
-    if (sp.tr_energy) CU(ctx, cudaMemcpyAsync(a->energy_trace, sp.tr_energy, (size_t)W * nsamp * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
+    if (sp.tr_energy && a->energy_trace) CU(ctx, cudaMemcpyAsync(a->energy_trace, sp.tr_energy, (size_t)W * nsamp * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
     if (sp.tr_wfvalue) CU(ctx, cudaMemcpyAsync(a->wfvalue_trace, sp.tr_wfvalue, (size_t)W * nsamp * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
     if (sp.tr_kinetic) CU(ctx, cudaMemcpyAsync(a->kinetic_trace, sp.tr_kinetic, (size_t)W * nsamp * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
     if (sp.tr_pgrad) CU(ctx, cudaMemcpyAsync(a->pgrad_trace, sp.tr_pgrad, (size_t)W * nsamp * np * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
     if (sp.tr_accept) CU(ctx, cudaMemcpyAsync(a->accept_trace, sp.tr_accept, (size_t)W * a->n_sweeps * ne, cudaMemcpyDeviceToHost, STREAM(ctx)));
     CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
-    cudaFree(sp.tr_energy); cudaFree(sp.tr_wfvalue); cudaFree(sp.tr_kinetic); cudaFree(sp.tr_pgrad); cudaFree(sp.tr_accept);
+    if (!keep_series) cudaFree(sp.tr_energy);
+    cudaFree(sp.tr_wfvalue); cudaFree(sp.tr_kinetic); cudaFree(sp.tr_pgrad); cudaFree(sp.tr_accept);
   }
   return MOLE_OK;
 }
@@ -676,5 +700,7 @@ int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops) {
   *tflops = best;
   return MOLE_OK;
 }
+
+#include "mole_api_series.inc"
 
 }  // extern "C"

@@ -242,6 +242,65 @@ int32_t mole_runner_run(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t
   return mole_sweep(ens, wf, m, op, &a);
 }
 
+// Runner::run with a logger (montecarlo.rs:31-43, Log: montecarlo/src/traits.rs:44-47): one launch per
+// block, the callback sees the block-level reductions (differences of the device accumulators).
+int32_t mole_runner_run_logged(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, uint32_t observables,
+                               uint32_t compat, int32_t steps, int32_t block_size, uint32_t sweep_flags, mole_log_fn log,
+                               void* user) {
+  if (!ens) return MOLE_ERR_INVALID_ARG;
+  if (block_size < 1 || !(steps >= 2 * block_size))
+    return mole_set_error(ens->ctx, MOLE_ERR_ASSERT, "assertion failed: steps >= 2 * block_size (montecarlo.rs:29)");
+  const int blocks = steps / block_size;
+  mole_acc_host prev, cur, first;
+  int32_t rc;
+  if ((rc = mole_acc_get(ens, &prev)) != MOLE_OK) return rc;
+  first = prev;
+  for (int b = 0; b < blocks; ++b) {
+    mole_sweep_args a;
+    memset(&a, 0, sizeof(a));
+    a.n_sweeps = block_size;
+    a.n_discard = b == 0 ? block_size : 0;   // block 0 is equilibration (:36)
+    a.block_size = block_size;
+    a.observables = observables;
+    a.compat = compat;
+    a.flags = sweep_flags;
+    if (b > 1 && (sweep_flags & MOLE_SWEEP_KEEP_SERIES)) a.flags = (sweep_flags & ~MOLE_SWEEP_KEEP_SERIES) | MOLE_SWEEP_APPEND_SERIES;
+    if ((rc = mole_sweep(ens, wf, m, op, &a)) != MOLE_OK) return rc;
+    if (!log) continue;
+    if ((rc = mole_acc_get(ens, &cur)) != MOLE_OK) return rc;
+    if (b == 0) { prev = cur; continue; }
+    mole_block_log d;
+    memset(&d, 0, sizeof(d));
+    d.block_nr = b;
+    d.block_size = block_size;
+    d.n_samples = cur.n_samples - prev.n_samples;
+    const double ns = d.n_samples > 0 ? d.n_samples : 1.0, nt = cur.n_samples - first.n_samples;
+    d.block_energy = (cur.sum_e - prev.sum_e) / ns;
+    d.running_energy = (cur.sum_e - first.sum_e) / (nt > 0 ? nt : 1.0);
+    d.block_kinetic = (cur.sum_t - prev.sum_t) / ns;
+    d.block_wfvalue = (cur.sum_psi - prev.sum_psi) / ns;
+    const double mv = cur.n_moves - prev.n_moves;
+    d.acceptance = mv > 0 ? (cur.n_accept - prev.n_accept) / mv : 0.0;
+    log(user, &d);
+    prev = cur;
+  }
+  return MOLE_OK;
+}
+
+// block-size schedule of the reference's blocking analysis (scripts/statfor.rs:59-66):
+// MIN_LEFT = 20, NSIZES = 100, sizes 1, 1+step, ... <= n/20 with step = max(n/20/100, 1)
+int32_t mole_series_block_sizes(int64_t n, int32_t* sizes, int32_t* n_sizes) {
+  if (!n_sizes || n < 0) return MOLE_ERR_INVALID_ARG;
+  const int64_t large = n / 20, step = std::max<int64_t>(large / 100, 1);
+  int32_t k = 0;
+  for (int64_t s = 1; s <= large; s += step) {
+    if (sizes) sizes[k] = (int32_t)s;
+    ++k;
+  }
+  *n_sizes = k;
+  return MOLE_OK;
+}
+
 // ------------------------------------------------------------------ VmcRunner::run_optimization (vmc.rs:43-106)
 int32_t mole_vmc_run_optimization(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, mole_opt_t opt,
                                   const uint8_t master_seed[32], int32_t iters, int64_t total_samples, int32_t block_size,

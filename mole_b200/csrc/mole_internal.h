@@ -109,6 +109,8 @@ struct mole_ens_s {
   unsigned long long* blocksums = nullptr; int n_scan_blocks = 0;
   int32_t* src = nullptr;   // [W] branching source indices
   int32_t np_last = 0;      // P of the last sweep that touched acc
+  double* series = nullptr; // [series_n][W] E_L samples kept on the device (MOLE_SWEEP_KEEP_SERIES)
+  int64_t series_n = 0, series_cap = 0;
 };
 
 // ---- host-only helpers (mole_host.cpp) ---------------------------------------------------------

@@ -51,9 +51,25 @@ class OpDesc(C.Structure):
 
 class SweepArgs(C.Structure):
     _fields_ = [("n_sweeps", C.c_int32), ("n_discard", C.c_int32), ("block_size", C.c_int32),
-                ("observables", C.c_uint32), ("compat", C.c_uint32), ("reserved", C.c_int32),
+                ("observables", C.c_uint32), ("compat", C.c_uint32), ("flags", C.c_uint32),
                 ("energy_trace", C.c_void_p), ("wfvalue_trace", C.c_void_p), ("kinetic_trace", C.c_void_p),
                 ("pgrad_trace", C.c_void_p), ("accept_trace", C.c_void_p)]
+
+
+class SeriesStats(C.Structure):
+    _fields_ = [("average", C.c_double), ("variance", C.c_double), ("tcorr", C.c_double), ("n_eff", C.c_double),
+                ("sigma", C.c_double)]
+
+
+class BlockLog(C.Structure):
+    _fields_ = [("block_nr", C.c_int32), ("block_size", C.c_int32), ("n_samples", C.c_double),
+                ("block_energy", C.c_double), ("running_energy", C.c_double), ("block_kinetic", C.c_double),
+                ("block_wfvalue", C.c_double), ("acceptance", C.c_double)]
+
+
+LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(BlockLog))
+SWEEP_KEEP_SERIES, SWEEP_APPEND_SERIES = 1, 2
+SERIES_MAX_LAG = 200
 
 
 class AccHost(C.Structure):
@@ -86,6 +102,8 @@ SYMBOLS = [
     "mole_comm_destroy", "mole_opt_create", "mole_opt_destroy", "mole_opt_step", "mole_opt_sr_matrix",
     "mole_runner_run", "mole_vmc_run_optimization", "mole_dmc_step", "mole_branch", "mole_branch_sources",
     "mole_dmc_diffuse", "mole_bench_fp64_peak", "mole_ctx_launch_count", "mole_math_probe",
+    "mole_series_length", "mole_series_clear", "mole_series_block_sizes", "mole_series_analyze", "mole_series_get",
+    "mole_series_write_text", "mole_runner_run_logged", "mole_ensemble_save", "mole_ensemble_load",
 ]
 
 _lib = None

@@ -366,3 +366,24 @@ def bench_vmc(d, h, opts, cfgs, steps, block_size, seed):
     secs = lib().orc_bench_vmc(C.byref(d), C.byref(h), C.byref(opts), _dp(cfgs), C.c_int64(cfgs.shape[0]), steps,
                                block_size, _seed(seed), C.byref(es), C.byref(th))
     return secs, es.value, th.value
+
+
+def statfor_block_sizes(n):
+    """Block-size schedule of scripts/statfor.rs:59-66."""
+    k = lib().orc_statfor_block_sizes(C.c_int64(n), None)
+    out = np.empty(k, dtype=np.int32)
+    if k:
+        lib().orc_statfor_block_sizes(C.c_int64(n), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def statfor(series, block_sizes=None):
+    """scripts/statfor.rs on one series (mean, variance, correlation, blocking)."""
+    x = np.ascontiguousarray(series, dtype=np.float64)
+    n = x.size
+    bs = statfor_block_sizes(n) if block_sizes is None else np.ascontiguousarray(block_sizes, dtype=np.int32)
+    lags = max(min(200, n - 1), 0)
+    st, corr, errs = np.empty(5), np.empty(lags), np.empty(bs.size)
+    lib().orc_statfor(_dp(x), C.c_int64(n), _dp(st), _dp(corr), C.c_int(bs.size), bs.ctypes.data_as(C.c_void_p), _dp(errs))
+    return dict(average=st[0], variance=st[1], tcorr=st[2], n_eff=st[3], sigma=st[4], corr=corr, block_sizes=bs,
+                block_errors=errs)

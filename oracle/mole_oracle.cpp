@@ -7,6 +7,7 @@
 #include <omp.h>
 #endif
 #include "oracle_mc.hpp"
+#include "oracle_stat.hpp"
 
 using namespace orc;
 
@@ -296,6 +297,23 @@ double orc_bench_vmc(const WfDesc* d, const HamDesc* h, const RunOptions* o, con
   const auto t1 = std::chrono::steady_clock::now();
   *energy_sum = total;
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// scripts/statfor.rs on one series: stats = {average, variance(ddof 1), tcorr, n_eff, sigma};
+// corr[min(200, n-1)] and errs[n_sizes] nullable.  Returns the number of lags.
+int orc_statfor(const double* data, int64_t n, double* stats, double* corr, int n_sizes, const int* sizes, double* errs) {
+  const double average = stat_mean(data, n);
+  const double var = stat_variance(data, n, 1);
+  double tcorr, neff, sigma;
+  const int lags = stat_correlation(data, n, average, var, corr, &tcorr, &neff, &sigma);
+  stats[0] = average; stats[1] = var; stats[2] = tcorr; stats[3] = neff; stats[4] = sigma;
+  for (int k = 0; k < n_sizes; ++k) errs[k] = stat_block_error(data, n, sizes[k]);
+  return lags;
+}
+int orc_statfor_block_sizes(int64_t n, int* sizes) {
+  const std::vector<int> v = stat_block_sizes(n);
+  if (sizes) std::copy(v.begin(), v.end(), sizes);
+  return (int)v.size();
 }
 
 }  // extern "C"

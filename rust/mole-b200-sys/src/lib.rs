@@ -25,8 +25,15 @@ pub const MOLE_ERR_ASSERT: i32 = 104;
 
 #[repr(C)] #[derive(Clone, Copy)] pub struct mole_wf_desc { pub kind: i32, pub n_elec: i32, pub n_params: i32, pub reserved: i32, pub params: [f64; 8], pub geom: [f64; 8] }
 #[repr(C)] #[derive(Clone, Copy)] pub struct mole_op_desc { pub kind: i32, pub n_ions: i32, pub ion_pos: [f64; 24], pub ion_charge: [i32; 8], pub frequency: f64 }
-#[repr(C)] pub struct mole_sweep_args { pub n_sweeps: i32, pub n_discard: i32, pub block_size: i32, pub observables: u32, pub compat: u32, pub reserved: i32,
+#[repr(C)] pub struct mole_sweep_args { pub n_sweeps: i32, pub n_discard: i32, pub block_size: i32, pub observables: u32, pub compat: u32, pub flags: u32,
     pub energy_trace: *mut f64, pub wfvalue_trace: *mut f64, pub kinetic_trace: *mut f64, pub pgrad_trace: *mut f64, pub accept_trace: *mut u8 }
+pub const MOLE_SWEEP_KEEP_SERIES: u32 = 1;
+pub const MOLE_SWEEP_APPEND_SERIES: u32 = 2;
+pub const MOLE_SERIES_MAX_LAG: usize = 200;
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct mole_series_stats { pub average: f64, pub variance: f64, pub tcorr: f64, pub n_eff: f64, pub sigma: f64 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct mole_block_log { pub block_nr: i32, pub block_size: i32, pub n_samples: f64, pub block_energy: f64,
+    pub running_energy: f64, pub block_kinetic: f64, pub block_wfvalue: f64, pub acceptance: f64 }
+pub type mole_log_fn = Option<unsafe extern "C" fn(user: *mut core::ffi::c_void, data: *const mole_block_log)>;
 #[repr(C)] #[derive(Clone, Copy)] pub struct mole_acc_host { pub n_samples: f64, pub sum_e: f64, pub sum_e2: f64, pub sum_b: f64, pub sum_b2: f64, pub n_blocks: f64,
     pub n_accept: f64, pub n_moves: f64, pub sum_t: f64, pub sum_psi: f64, pub sum_o: [f64; 8], pub sum_oe: [f64; 8], pub sum_oo: [f64; 36], pub n_params: i32, pub reserved: i32 }
 
@@ -93,4 +100,14 @@ extern "C" {
     pub fn mole_bench_fp64_peak(ctx: *mut mole_ctx_s, tflops: *mut f64) -> i32;
     pub fn mole_math_probe(ctx: *mut mole_ctx_s, which: i32, in_: *const f64, n: i64, out: *mut f64) -> i32;
     pub fn mole_ctx_launch_count(ctx: *mut mole_ctx_s, n: *mut i64) -> i32;
+    // series statistics (scripts/statfor.rs), Log callback (montecarlo/src/traits.rs:44-47), checkpoint / restart
+    pub fn mole_series_length(ens: *mut mole_ens_s, n: *mut i64) -> i32;
+    pub fn mole_series_clear(ens: *mut mole_ens_s) -> i32;
+    pub fn mole_series_block_sizes(n: i64, sizes: *mut i32, n_sizes: *mut i32) -> i32;
+    pub fn mole_series_analyze(ens: *mut mole_ens_s, drop_last: i32, mean_stats: *mut mole_series_stats, corr: *mut f64, n_sizes: i32, block_sizes: *const i32, block_errors: *mut f64, per_walker: *mut mole_series_stats, per_walker_corr: *mut f64, per_walker_block_errors: *mut f64) -> i32;
+    pub fn mole_series_get(ens: *mut mole_ens_s, walker: i64, out: *mut f64) -> i32;
+    pub fn mole_series_write_text(ens: *mut mole_ens_s, walker: i64, path: *const core::ffi::c_char) -> i32;
+    pub fn mole_runner_run_logged(ens: *mut mole_ens_s, wf: *mut mole_wf_s, m: *mut mole_metrop_s, op: *mut mole_op_s, observables: u32, compat: u32, steps: i32, block_size: i32, sweep_flags: u32, log: mole_log_fn, user: *mut core::ffi::c_void) -> i32;
+    pub fn mole_ensemble_save(ens: *mut mole_ens_s, path: *const core::ffi::c_char) -> i32;
+    pub fn mole_ensemble_load(ens: *mut mole_ens_s, path: *const core::ffi::c_char) -> i32;
 }
