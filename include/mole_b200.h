@@ -294,6 +294,14 @@ int32_t mole_dmc_step(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t o
 int32_t mole_branch(mole_ens_t ens, int32_t kind);
 /* source walker index of every walker after the last mole_branch (parity tests) */
 int32_t mole_branch_sources(mole_ens_t ens, int32_t* src);
+/* One block of DmcRunner::diffuse's inner loop (dmc.rs:84-141): n_steps x (time step, ensemble energy
+ * sum w E / sum w over ALL ranks, branch).  With SRBrancher the block is enqueued without host reads
+ * (the reference energy is constant within a block, dmc.rs:143-145): 3 launches per time step, the
+ * branching normalisation and the per-step energies are formed on the device, multi-rank sums go
+ * through NCCL on the same stream, and step_energies[n_steps] comes back with one copy.  Identical
+ * results to n_steps x (mole_dmc_step, mole_branch). */
+int32_t mole_dmc_block(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind,
+                       double time_step, double reference_energy, int32_t n_steps, double* step_energies);
 /* DmcRunner::diffuse (dmc.rs:69-153): returns n_out running energies and errors */
 int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind,
                          double time_step, double* reference_energy /* in/out */, int32_t num_iterations,

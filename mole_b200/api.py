@@ -12,6 +12,15 @@ from .ffi import MoleError, check, lib, seed32
 _default_ctx = None
 
 
+def _destroy(fn_name, obj):
+    """Destructor helper: safe during interpreter shutdown, when module globals are already cleared."""
+    h = getattr(obj, "handle", None)
+    l = getattr(ffi, "_lib", None) if ffi is not None else None
+    if h and l is not None:
+        getattr(l, fn_name)(h)
+    obj.handle = None
+
+
 def _h(obj):
     return obj.handle if obj is not None else None
 
@@ -178,9 +187,7 @@ class WaveFunction:
         return new
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            lib().mole_wf_destroy(self.handle)
-            self.handle = None
+        _destroy("mole_wf_destroy", self)
 
 
 class STO(WaveFunction):
@@ -275,9 +282,7 @@ class LocalOperator:
         return out.value
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            lib().mole_op_destroy(self.handle)
-            self.handle = None
+        _destroy("mole_op_destroy", self)
 
 
 class KineticEnergy(LocalOperator):
@@ -375,9 +380,7 @@ class _Metropolis:
         return s
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            lib().mole_metropolis_destroy(self.handle)
-            self.handle = None
+        _destroy("mole_metropolis_destroy", self)
 
 
 class MetropolisBox(_Metropolis):
@@ -604,6 +607,14 @@ class Ensemble:
                                     C.c_double(reference_energy), C.byref(swe), C.byref(sw)))
         return swe.value, sw.value
 
+    def dmc_block(self, wf, metrop, op, branch_kind, time_step, reference_energy, n_steps):
+        """n_steps x (time step, ensemble energy, branch) without host reads; returns the step energies."""
+        out = np.empty(n_steps)
+        self._c(lib().mole_dmc_block(self.handle, wf.handle, metrop.handle, op.handle, C.c_int32(branch_kind),
+                                     C.c_double(time_step), C.c_double(reference_energy), C.c_int32(n_steps),
+                                     out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def branch(self, kind):
         self._c(lib().mole_branch(self.handle, C.c_int32(kind)))
 
@@ -613,9 +624,7 @@ class Ensemble:
         return out
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            lib().mole_ensemble_destroy(self.handle)
-            self.handle = None
+        _destroy("mole_ensemble_destroy", self)
 
 
 def series_block_sizes(n):
@@ -662,9 +671,7 @@ class Optimizer:
         return S
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            lib().mole_opt_destroy(self.handle)
-            self.handle = None
+        _destroy("mole_opt_destroy", self)
 
 
 class SteepestDescent(Optimizer):

@@ -201,7 +201,7 @@ int32_t mole_ensemble_create(mole_ctx_t ctx, int64_t W, int32_t ne, const uint8_
   CU(ctx, cudaMalloc(&e->acc, ACC_LEN * sizeof(double)));
   e->partial_rows = ens_grid_rows(ctx);
   CU(ctx, cudaMalloc(&e->partials, (size_t)e->partial_rows * ACC_LEN * sizeof(double)));
-  CU(ctx, cudaMalloc(&e->ticket, sizeof(unsigned int)));
+  CU(ctx, cudaMalloc(&e->ticket, 2 * sizeof(unsigned int)));   // [0] accumulator reduction, [1] branching scan
   CU(ctx, cudaMalloc(&e->red, 8 * sizeof(double)));
   e->n_scan_blocks = cdiv(W, SCAN_TILE);
   CU(ctx, cudaMalloc(&e->cum, (size_t)W * sizeof(unsigned long long)));
@@ -210,7 +210,7 @@ int32_t mole_ensemble_create(mole_ctx_t ctx, int64_t W, int32_t ne, const uint8_
   CU(ctx, cudaMemsetAsync(e->x, 0, nx * sizeof(double), STREAM(ctx)));
   CU(ctx, cudaMemsetAsync(e->blk, 0, W * sizeof(double), STREAM(ctx)));
   CU(ctx, cudaMemsetAsync(e->acc, 0, ACC_LEN * sizeof(double), STREAM(ctx)));
-  CU(ctx, cudaMemsetAsync(e->ticket, 0, sizeof(unsigned int), STREAM(ctx)));
+  CU(ctx, cudaMemsetAsync(e->ticket, 0, 2 * sizeof(unsigned int), STREAM(ctx)));
   fill_kernel<<<cdiv(W, 256), 256, 0, STREAM(ctx)>>>(e->w, W, 1.0);   // dmc.rs:51 initial weight 1.0
   KERNEL_CHECK(ctx);
   *out = e;
@@ -224,7 +224,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->x0);
   cudaFree(e->x); cudaFree(e->x2); cudaFree(e->w); cudaFree(e->w2); cudaFree(e->el); cudaFree(e->el2);
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
-  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series);
+  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath);
   delete e;
   return MOLE_OK;
 }
@@ -539,8 +539,11 @@ int32_t mole_acc_device_ptr(mole_ens_t e, void** p, int32_t* n) {
 }
 
 // ------------------------------------------------------------------ DMC
-int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref,
-                      double* sum_w_e, double* sum_w) {
+}  // extern "C"
+
+// one time step for all walkers, enqueued on the stream; the reduction leaves
+// red[0..3] = {sum w E_old, sum w, sum w', max w'} on the device
+static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref) {
   if (!e || !wf || !m || !op) return mole_set_error(e ? e->ctx : nullptr, MOLE_ERR_INVALID_ARG, "mole_dmc_step: NULL argument");
   mole_ctx_s* ctx = e->ctx;
   if (m->kind != MOLE_METROP_DIFFUSE) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "DmcRunner takes a MetropolisDiffuse (dmc.rs:28)");
@@ -568,6 +571,43 @@ int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op,
   KERNEL_CHECK(ctx);
   e->el_cached = 1;
   e->wstats_valid = 1;
+  return MOLE_OK;
+}
+
+// SRBrancher::branch enqueued on the stream: fused weight scan (+ tile-total scan by the last CTA) and
+// the pick + gather on tile-local prefix sums.  Either the scalars (norm_factor, new_weight) come from
+// the host, or - max_ptr / local_sum_ptr non-null - they are formed on the device from the step
+// kernel's reduction, with the same arithmetic.
+static int32_t sr_branch_launch(mole_ens_t e, double norm_factor, double new_weight, const double* red_rows, int n_rows,
+                                double gcount, const double* local_sum_ptr, double* step_e_out) {
+  mole_ctx_s* ctx = e->ctx;
+  const int64_t W = e->W;
+  const int n = 3 * e->ne;
+  const int tiles = e->n_scan_blocks;
+  cudaStream_t st = STREAM(ctx);
+  if (!e->el_cached) CU(ctx, cudaMemsetAsync(e->el, 0, W * sizeof(double), st));
+  sr_weights_scan_fused_kernel<<<tiles, SCAN_THREADS, 0, st>>>(e->w, W, norm_factor, red_rows, n_rows, gcount, e->cum,
+                                                               e->blocksums, tiles, e->ticket + 1);
+  KERNEL_CHECK(ctx);
+  sr_pick_gather_tiled_kernel<<<cdiv(W, 128), 128, 0, st>>>(e->cum, e->blocksums, tiles, W, n, e->walker_offset, e->key, e->step,
+                                                            e->x, e->x2, e->el, e->el2, e->w2, new_weight, local_sum_ptr,
+                                                            red_rows, n_rows, step_e_out, e->src);
+  KERNEL_CHECK(ctx);
+  std::swap(e->x, e->x2);
+  std::swap(e->w, e->w2);
+  std::swap(e->el, e->el2);
+  e->wstats_valid = 0;
+  e->step += 1;
+  return MOLE_OK;
+}
+
+extern "C" {
+
+int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref,
+                      double* sum_w_e, double* sum_w) {
+  const int32_t rc = dmc_step_launch(e, wf, m, op, time_step, e_ref);
+  if (rc != MOLE_OK) return rc;
+  mole_ctx_s* ctx = e->ctx;
   double red[4];
   CU(ctx, cudaMemcpyAsync(red, e->red, 4 * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
   CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
@@ -576,6 +616,58 @@ int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op,
   return MOLE_OK;
 }
 
+// One block of DmcRunner::diffuse's inner loop (dmc.rs:84-141), SRBrancher: n_steps x (time step, ensemble
+// energy, branch) enqueued without any host read - the reference energy only changes between blocks
+// (dmc.rs:143-145) - then ONE copy of the per-step energies.  Multi-rank: the three per-step scalars are
+// all-reduced on the device (NCCL on the same stream).  Results are identical to the step-by-step entry
+// points (mole_dmc_step + mole_branch), which the other branchers and the parity tests use.
+int32_t mole_dmc_block(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind, double time_step,
+                       double e_ref, int32_t n_steps, double* step_energies) {
+  if (!e || !step_energies || n_steps < 0) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  int32_t rc;
+  if (branch_kind != MOLE_BRANCH_SR) {
+    for (int j = 0; j < n_steps; ++j) {
+      double swe, sw;
+      if ((rc = mole_dmc_step(e, wf, m, op, time_step, e_ref, &swe, &sw)) != MOLE_OK) return rc;
+      double s[2] = {swe, sw};
+      if ((rc = mole_comm_allreduce_host(ctx, s, 2, nullptr, 0)) != MOLE_OK) return rc;
+      step_energies[j] = s[0] / s[1];   // dmc.rs:133
+      if ((rc = mole_branch(e, branch_kind)) != MOLE_OK) return rc;
+    }
+    return MOLE_OK;
+  }
+  if (n_steps == 0) return MOLE_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = STREAM(ctx);
+  if (e->step_e_cap < n_steps) {
+    CU(ctx, cudaStreamSynchronize(st));
+    cudaFree(e->step_e);
+    e->step_e = nullptr;
+    CU(ctx, cudaMalloc(&e->step_e, (size_t)n_steps * sizeof(double)));
+    e->step_e_cap = n_steps;
+  }
+  const bool multi = ctx->nranks > 1;
+  double gcount = (double)e->W;
+  if (multi) {
+    double s[1] = {gcount};
+    if ((rc = mole_comm_allreduce_host(ctx, s, 1, nullptr, 0)) != MOLE_OK) return rc;
+    gcount = s[0];
+    if (!e->gath) CU(ctx, cudaMalloc(&e->gath, (size_t)ctx->nranks * 4 * sizeof(double)));
+  }
+  for (int j = 0; j < n_steps; ++j) {
+    if ((rc = dmc_step_launch(e, wf, m, op, time_step, e_ref)) != MOLE_OK) return rc;
+    const double* rows = e->red;         // {sum w E, sum w, sum w', max w'} of this rank
+    if (multi) {                         // one row per rank, ONE small collective per time step
+      if ((rc = mole_comm_allgather_device(ctx, e->red, e->gath, 4)) != MOLE_OK) return rc;
+      rows = e->gath;
+    }
+    if ((rc = sr_branch_launch(e, 0.0, 0.0, rows, multi ? ctx->nranks : 1, gcount, e->red + 2, e->step_e + j)) != MOLE_OK) return rc;
+  }
+  CU(ctx, cudaMemcpyAsync(step_energies, e->step_e, (size_t)n_steps * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  return MOLE_OK;
+}
 
 int32_t mole_branch(mole_ens_t e, int32_t kind) {
   if (!e) return MOLE_ERR_INVALID_ARG;
@@ -610,15 +702,7 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
     }
     const double norm_factor = gcount / gmax;                 // branching.rs:24 (global N, global w_max)
     const double new_weight = local_sum / (double)W;          // branching.rs:21 (stratified per rank)
-    sr_weights_scan_kernel<<<tiles, SCAN_THREADS, 0, st>>>(e->w, W, norm_factor, e->cum, e->blocksums);
-    KERNEL_CHECK(ctx);
-    scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(e->blocksums, tiles);
-    KERNEL_CHECK(ctx);
-    add_tile_offsets_kernel<<<cdiv(W, 256), 256, 0, st>>>(e->cum, W, e->blocksums);
-    KERNEL_CHECK(ctx);
-    sr_pick_gather_kernel<<<cdiv(W, 128), 128, 0, st>>>(e->cum, e->blocksums, tiles, W, n, e->walker_offset, e->key, e->step,
-                                                        e->x, e->x2, e->el, e->el2, e->w2, new_weight, e->src);
-    KERNEL_CHECK(ctx);
+    return sr_branch_launch(e, norm_factor, new_weight, nullptr, 0, 0.0, nullptr, nullptr);
   } else {
     int32_t* list = nullptr; int32_t* fen = nullptr; uint32_t* mask = nullptr;
     const int64_t cap = 3 * W;

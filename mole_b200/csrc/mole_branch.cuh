@@ -43,6 +43,78 @@ MOLE_D unsigned long long mole_tile_scan(unsigned long long v[SCAN_ITEMS]) {
 
 // pass 1 (SR): integer weights k_i = trunc(w_i * N/w_max) (branching.rs:24-30, `as u32` saturates),
 // tile-local inclusive scan -> cum, tile totals -> tile_sums
+// exclusive scan of the tile totals in place by ONE CTA (sequential carry over chunks);
+// tile_sums[n_tiles] receives the grand total
+MOLE_D void mole_scan_tile_sums(unsigned long long* tile_sums, int n_tiles) {
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0ull;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += SCAN_TILE) {
+    unsigned long long v[SCAN_ITEMS], orig[SCAN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      const int idx = base + threadIdx.x * SCAN_ITEMS + i;
+      orig[i] = v[i] = idx < n_tiles ? __ldcg(tile_sums + idx) : 0ull;   // written by other CTAs: read through L2
+    }
+    const unsigned long long tot = mole_tile_scan(v);
+    const unsigned long long c = carry;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      const int idx = base + threadIdx.x * SCAN_ITEMS + i;
+      if (idx < n_tiles) tile_sums[idx] = c + v[i] - orig[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_sums[n_tiles] = carry;
+}
+
+// Fused SR pass 1+2 for the launch-bound DMC loop: as sr_weights_scan_kernel, but the normalisation
+// N / w_max is read from the device (max_ptr, written by the step kernel's reduction or an NCCL max)
+// and the last CTA to finish (ticket) scans the tile totals, so no second launch and no host read.
+// cum stays TILE-LOCAL; sr_pick_gather_kernel searches tiles first.
+__global__ void __launch_bounds__(SCAN_THREADS) sr_weights_scan_fused_kernel(const double* __restrict__ w, int64_t W,
+                                                                             double norm_factor, const double* red_rows,
+                                                                             int n_rows, double gcount,
+                                                                             unsigned long long* cum,
+                                                                             unsigned long long* tile_sums, int n_tiles,
+                                                                             unsigned int* ticket) {
+  __shared__ bool is_last;
+  if (red_rows) {                                               // rows of {sum w E, sum w, sum w', max w'}, one per rank
+    double mx = red_rows[3];
+    for (int r = 1; r < n_rows; ++r) mx = fmax(mx, red_rows[4 * r + 3]);
+    norm_factor = gcount / mx;                                  // branching.rs:24 (global N, global w_max)
+  }
+  unsigned long long v[SCAN_ITEMS];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    unsigned long long k = 0;
+    if (base + i < W) {
+      const double s = w[base + i] * norm_factor;
+      k = (s >= 4294967295.0) ? 4294967295ull : (s > 0.0 ? (unsigned long long)(uint32_t)s : 0ull);
+    }
+    v[i] = k;
+  }
+  const unsigned long long tot = mole_tile_scan(v);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < W) cum[base + i] = v[i];
+  if (threadIdx.x == 0) {
+    tile_sums[blockIdx.x] = tot;
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    mole_scan_tile_sums(tile_sums, n_tiles);
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) sr_weights_scan_kernel(const double* __restrict__ w, int64_t W,
                                                                        double norm_factor, unsigned long long* cum,
                                                                        unsigned long long* tile_sums) {
@@ -67,28 +139,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) sr_weights_scan_kernel(const dou
 // pass 2: exclusive scan of the tile totals in place (single CTA, sequential carry over chunks);
 // tile_sums[n_tiles] receives the grand total
 __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(unsigned long long* tile_sums, int n_tiles) {
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) carry = 0ull;
-  __syncthreads();
-  for (int base = 0; base < n_tiles; base += SCAN_TILE) {
-    unsigned long long v[SCAN_ITEMS], orig[SCAN_ITEMS];
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-      const int idx = base + threadIdx.x * SCAN_ITEMS + i;
-      orig[i] = v[i] = idx < n_tiles ? tile_sums[idx] : 0ull;
-    }
-    const unsigned long long tot = mole_tile_scan(v);
-    const unsigned long long c = carry;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-      const int idx = base + threadIdx.x * SCAN_ITEMS + i;
-      if (idx < n_tiles) tile_sums[idx] = c + v[i] - orig[i];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) carry = c + tot;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) tile_sums[n_tiles] = carry;
+  mole_scan_tile_sums(tile_sums, n_tiles);
 }
 
 // pass 3: cum[i] += offset of its tile
@@ -112,6 +163,46 @@ __global__ void sr_pick_gather_kernel(const unsigned long long* __restrict__ cum
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
     if (cum[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  src[j] = (int32_t)lo;
+  for (int c = 0; c < n; ++c) x2[(size_t)c * W + j] = x[(size_t)c * W + lo];
+  el2[j] = el[lo];
+  w2[j] = new_weight;
+}
+
+// pass 4 (SR) on TILE-LOCAL prefix sums: the search goes over the exclusive tile offsets first and then
+// inside the tile - the same walker as the upper bound on the global prefix sums, without the pass that
+// adds the offsets.  The new weight and the step's ensemble energy are formed from device-side sums
+// (local_sum_ptr = sum of this rank's post-update weights; red_rows = one {sum w E, sum w, ..} row per
+// rank), exactly as the host does on the synchronous path, and the energy is written to *step_e_out
+// (dmc.rs:133).
+__global__ void sr_pick_gather_tiled_kernel(const unsigned long long* __restrict__ cum, const unsigned long long* tile_sums,
+                                            int n_tiles, int64_t W, int n, uint64_t walker_offset, RngKey key, uint32_t step,
+                                            const double* __restrict__ x, double* x2, const double* __restrict__ el,
+                                            double* el2, double* w2, double new_weight, const double* local_sum_ptr,
+                                            const double* red_rows, int n_rows, double* step_e_out, int32_t* src) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0 && step_e_out) {                                     // ensemble energy over all ranks, rank order
+    double swe = red_rows[0], sw = red_rows[1];
+    for (int r = 1; r < n_rows; ++r) { swe += red_rows[4 * r]; sw += red_rows[4 * r + 1]; }
+    *step_e_out = swe / sw;
+  }
+  if (j >= W) return;
+  if (local_sum_ptr) new_weight = *local_sum_ptr / (double)W;     // branching.rs:21
+  const unsigned long long total = tile_sums[n_tiles];
+  const Philox4 p = mole_draw(key, walker_offset + (uint64_t)j, step, DOM_BRANCH, 0, 0);
+  const unsigned long long u = __umul64hi(mole_u64(p), total);     // uniform integer in [0,total)
+  // last tile whose exclusive offset is <= u, skipping empty tiles by construction (offset[t+1] > u)
+  int tl = 0, th = n_tiles - 1;
+  while (tl < th) {
+    const int mid = (tl + th) >> 1;
+    if (tile_sums[mid + 1] > u) th = mid; else tl = mid + 1;
+  }
+  const unsigned long long ul = u - tile_sums[tl];
+  int64_t lo = (int64_t)tl * SCAN_TILE, hi = min(lo + SCAN_TILE, W) - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cum[mid] > ul) hi = mid; else lo = mid + 1;
   }
   src[j] = (int32_t)lo;
   for (int c = 0; c < n; ++c) x2[(size_t)c * W + j] = x[(size_t)c * W + lo];

@@ -22,6 +22,7 @@ struct NcclApi {
   int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
   int (*CommDestroy)(nccl_comm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -39,8 +40,9 @@ NcclApi& api() {
   a.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_unique_id, int))dlsym(a.handle, "ncclCommInitRank");
   a.CommDestroy = (int (*)(nccl_comm_t))dlsym(a.handle, "ncclCommDestroy");
   a.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(a.handle, "ncclAllReduce");
+  a.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(a.handle, "ncclAllGather");
   a.GetErrorString = (const char* (*)(int))dlsym(a.handle, "ncclGetErrorString");
-  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GetErrorString;
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather && a.GetErrorString;
   return a;
 }
 
@@ -64,6 +66,16 @@ int32_t mole_comm_allreduce_host(mole_ctx_s* ctx, double* sum_vals, int n_sum, d
   if (n_sum) cudaMemcpyAsync(sum_vals, d, n_sum * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (n_max) cudaMemcpyAsync(max_vals, d + n_sum, n_max * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (cudaStreamSynchronize(st) != cudaSuccess) return mole_set_error(ctx, MOLE_ERR_CUDA, "allreduce_host: stream sync failed");
+  return MOLE_OK;
+}
+
+// all-gather of n DEVICE doubles per rank on the context stream, no host synchronisation: the DMC block
+// loop exchanges {sum w E, sum w, sum w', max w'} with ONE small collective per time step and the
+// consuming kernels fold the nranks rows themselves (sums in rank order, max)
+int32_t mole_comm_allgather_device(mole_ctx_s* ctx, const double* send_dev, double* recv_dev, int n) {
+  if (!ctx || ctx->nranks <= 1 || !ctx->nccl_comm) return MOLE_OK;
+  const int rc = api().AllGather(send_dev, recv_dev, (size_t)n, NCCL_FLOAT64, ctx->nccl_comm, (cudaStream_t)ctx->stream);
+  if (rc != 0) return nccl_fail(ctx, "ncclAllGather", rc);
   return MOLE_OK;
 }
 

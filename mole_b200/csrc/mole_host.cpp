@@ -358,20 +358,14 @@ int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_
   double e_ref = *reference_energy;
   int32_t rc;
   int64_t t = 0;
+  std::vector<double> se((size_t)block_size);
   for (int block_nr = 0; block_nr < blocks; ++block_nr) {
+    // the whole block is enqueued without host reads: E_ref only changes between blocks (:143-145)
+    if ((rc = mole_dmc_block(ens, wf, m, op, branch_kind, time_step, e_ref, block_size, se.data())) != MOLE_OK) return rc;
     double sum = 0.0;
     for (int j = 0; j < block_size; ++j, ++t) {
-      double swe, sw;
-      if ((rc = mole_dmc_step(ens, wf, m, op, time_step, e_ref, &swe, &sw)) != MOLE_OK) return rc;
-      if (ctx->nranks > 1) {
-        double s[2] = {swe, sw};
-        if ((rc = mole_comm_allreduce_host(ctx, s, 2, nullptr, 0)) != MOLE_OK) return rc;
-        swe = s[0]; sw = s[1];
-      }
-      const double e = swe / sw;   // :133
-      sum += e;
-      if (step_energies) step_energies[t] = e;
-      if ((rc = mole_branch(ens, branch_kind)) != MOLE_OK) return rc;   // :139-140
+      sum += se[j];                // :133-135
+      if (step_energies) step_energies[t] = se[j];
     }
     const double energy = sum / (double)block_size;
     if (block_nr == num_eq_blocks) {   // :163-177

@@ -111,6 +111,9 @@ struct mole_ens_s {
   int32_t np_last = 0;      // P of the last sweep that touched acc
   double* series = nullptr; // [series_n][W] E_L samples kept on the device (MOLE_SWEEP_KEEP_SERIES)
   int64_t series_n = 0, series_cap = 0;
+  double* step_e = nullptr; // [step_e_cap] per-step ensemble energies of a DMC block (mole_dmc_block)
+  int64_t step_e_cap = 0;
+  double* gath = nullptr;   // [nranks][4] all-gathered per-step DMC reductions (multi-rank block loop)
 };
 
 // ---- host-only helpers (mole_host.cpp) ---------------------------------------------------------
@@ -119,3 +122,5 @@ int mole_set_error(mole_ctx_s* ctx, int code, const std::string& msg);
 int mole_oo_index(int P, int k, int l);  // k<=l
 // mole_comm.cpp: sum/max allreduce of a few host scalars over the ctx communicator (no-op for one rank)
 int32_t mole_comm_allreduce_host(mole_ctx_s* ctx, double* sum_vals, int n_sum, double* max_vals, int n_max);
+// all-gather of n device doubles per rank on the context stream, without a host synchronisation
+int32_t mole_comm_allgather_device(mole_ctx_s* ctx, const double* send_dev, double* recv_dev, int n);

@@ -332,6 +332,33 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepParams 
   mole_block_reduce_to_global<A::LEN>(acc.v, sp.partials, sp.acc, sp.ticket, [](int i) { return A::slot(i); });
 }
 
+// Last-CTA fold of the per-CTA DMC partial rows {sum w E, sum w, sum w', max w'} into red[0..3] by the
+// whole CTA: thread t takes rows t, t+T, ... in order, then warp shuffles and a per-warp pass in a fixed
+// order - deterministic for a given launch geometry (a serial fold over ~2000 rows cost 100 us per step).
+MOLE_D void mole_dmc_fold_partials(const double* partials, unsigned rows, double* red, double (*sm)[4]) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (unsigned b = threadIdx.x; b < rows; b += blockDim.x) {
+    const double* r = partials + (size_t)b * 4;
+    a0 += __ldcg(r); a1 += __ldcg(r + 1); a2 += __ldcg(r + 2); a3 = fmax(a3, __ldcg(r + 3));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 = fmax(a3, __shfl_xor_sync(0xffffffffu, a3, o));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; sm[warp][2] = a2; sm[warp][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int q = 0; q < nwarp; ++q) s = (threadIdx.x == 3) ? fmax(s, sm[q][3]) : s + sm[q][threadIdx.x];
+    red[threadIdx.x] = s;
+  }
+}
+
 // ------------------------------------------------------------------ DMC time step (dmc.rs:87-130)
 // red[0] += sum w E_old, red[1] += sum w (pre-update), red[2] = sum w (post-update), red[3] = max w (post-update)
 template <int KIND>
@@ -391,12 +418,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (threadIdx.x < 4) {
-      double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b)
-        s = (threadIdx.x == 3) ? fmax(s, dp.partials[(size_t)b * 4 + 3]) : s + dp.partials[(size_t)b * 4 + threadIdx.x];
-      dp.red[threadIdx.x] = s;
-    }
+    mole_dmc_fold_partials(dp.partials, gridDim.x, dp.red, sm);
   }
 }
 

@@ -853,12 +853,7 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_dmc_kernel(const D
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (threadIdx.x < 4) {
-      double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b)
-        s = (threadIdx.x == 3) ? fmax(s, dp.partials[(size_t)b * 4 + 3]) : s + dp.partials[(size_t)b * 4 + threadIdx.x];
-      dp.red[threadIdx.x] = s;
-    }
+    mole_dmc_fold_partials(dp.partials, gridDim.x, dp.red, smr);
   }
 }
 

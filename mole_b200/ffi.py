@@ -103,7 +103,7 @@ SYMBOLS = [
     "mole_runner_run", "mole_vmc_run_optimization", "mole_dmc_step", "mole_branch", "mole_branch_sources",
     "mole_dmc_diffuse", "mole_bench_fp64_peak", "mole_ctx_launch_count", "mole_math_probe",
     "mole_series_length", "mole_series_clear", "mole_series_block_sizes", "mole_series_analyze", "mole_series_get",
-    "mole_series_write_text", "mole_runner_run_logged", "mole_ensemble_save", "mole_ensemble_load",
+    "mole_series_write_text", "mole_runner_run_logged", "mole_ensemble_save", "mole_ensemble_load", "mole_dmc_block",
 ]
 
 _lib = None

@@ -210,3 +210,28 @@ def test_runner_log_callback_sees_block_reductions(mole, capsys):
     assert lg.n == 3
     with pytest.raises(mole.MoleError):
         ens.run_logged(wf, met, op, steps=15, block_size=10, log=log)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [700, 5000])
+def test_dmc_block_equals_step_by_step(mole, W):
+    """mole_dmc_block (no host reads, fused scan, device-side normalisation) == n x (mole_dmc_step, mole_branch)."""
+    seed = bytes(range(1, 33))
+    wf = mole.STO(0.9)
+    op = mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1])
+    met = mole.MetropolisDiffuse.from_rng(0.025, seed)
+    a = mole.DmcRunner.new(wf, W, -0.45, op, met, mole.SRBrancher.new(), identical_start=False).ensemble
+    b = mole.DmcRunner.new(wf, W, -0.45, op, met, mole.SRBrancher.new(), identical_start=False).ensemble
+    ea = []
+    for _ in range(23):
+        swe, sw = a.dmc_step(wf, met, op, 0.025, -0.47)
+        ea.append(swe / sw)
+        a.branch(mole.ffi.BRANCH_SR)
+    eb = b.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.025, -0.47, 23)
+    assert np.array_equal(np.array(ea), eb)
+    assert a.step == b.step == 23
+    assert np.array_equal(a.get_configs(), b.get_configs()) and np.array_equal(a.get_weights(), b.get_weights())
+    assert np.array_equal(a.branch_sources(), b.branch_sources())
+    # SimpleBranching goes through the step-by-step path inside mole_dmc_block
+    es = b.dmc_block(wf, met, op, mole.ffi.BRANCH_SIMPLE, 0.025, -0.47, 3)
+    assert np.isfinite(es).all() and b.step == 26
