@@ -10,7 +10,8 @@
 // the positions and a mailbox for the intra-walker exchanges.  The spin being moved always sits in
 // register slot 0 (the slots are swapped between the two halves of a sweep), so there is one copy of
 // the move code.  A single-electron move re-evaluates only what changed: one orbital row, a
-// Sherman-Morrison update of one 5x5 inverse (rebuilt from scratch every sweep), nine Jastrow pairs.
+// Sherman-Morrison update of one 5x5 inverse (rebuilt from scratch every SJ_REFRESH_EVERY sweeps), nine
+// Jastrow pairs; grad ln D of the own electrons is carried in registers and updated on accepted moves.
 // All reductions over the five lanes go through the mailbox in a fixed order (deterministic).
 // The per-walker shared-memory stride is 5 (mod 16) doubles, so the unit-stride-in-lane accesses of a
 // warp's 30 active lanes fall on distinct 8-byte banks.
@@ -289,171 +290,6 @@ MOLE_D void sj_swap_slots(SjLane& L) {
 
 // Metropolis::move_state for electron `el` of the spin in slot 0.  d = the pre-generated draws of THIS
 // lane's slot-0 electron (only the owner's are used).  Returns the accept decision (uniform over the group).
-#if 0   // v2 of the move (six warp syncs, lane-specialised exponentials), superseded by mole_sj_move.cuh
-template <int METROP>
-MOLE_D bool sj_move_v2(const SjConst& c, SjLane& L, int el, const MoveDraw& d, double param, double sd, double inv2tau,
-                       uint32_t compat) {   // superseded by mole_sj_move.cuh (kept for A/B timing; not instantiated)
-  const int spin = L.ph;
-  const int n = sj_spin_n(c, spin);
-  const bool isown = (L.gl == el);
-  const int sid_e = spin * 5 + el;
-  double* const mb = L.sm + SJ_OFF_MB;
-  const double* const minv = L.sm + SJ_OFF_MINV + spin * 25;
-  // this lane's column (cg) and the moved electron's column (ce) of the inverse
-  double cg[5], ce[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { cg[k] = minv[k * 5 + L.gl]; ce[k] = minv[k * 5 + el]; }
-  // drift of this lane's slot-0 electron at the current configuration
-  double Gown[3];
-  sj_gradlnD(c, L.x[0], L.orb[0], cg, Gown);
-  // ---- owner proposes, everybody reads the trial point
-  if (isown && L.wr) {
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const double xi = q == 0 ? d.a : (q == 1 ? d.b : d.c);
-      if (METROP == MOLE_METROP_BOX) {
-        const double lo = -0.5 * param, scale = 0.5 * param - lo;
-        mb[MB_XN + q] = L.x[0][q] + (lo + scale * xi);                              // metrop.rs:63-68
-      } else {
-        mb[MB_XN + q] = (L.x[0][q] + (Gown[q] + L.gf[0][q]) * param) + sd * xi;     // metrop.rs:155-160
-      }
-    }
-    mb[MB_XN + 3] = d.u;
-  }
-  sj_sync();
-  double xn[3], xo[3];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) { xn[q] = mb[MB_XN + q]; xo[q] = L.sm[SJ_OFF_XS + sid_e * 3 + q]; }
-  const double u_acc = mb[MB_XN + 3];
-  // ---- orbitals of the moved electron at the trial point: one exponential per lane, then shared
-  double on[5];
-  on[0] = m_sqrt_rsqrt(fma(xn[2], xn[2], fma(xn[1], xn[1], xn[0] * xn[0])), on[1]);
-  {
-    const double zm = L.gl == 0 ? c.z1 : (L.gl == 1 ? c.z2 : c.z3);
-    const double ex = m_exp(-zm * on[0]);
-    if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = ex;
-  }
-  // ---- nine Jastrow pairs of the moved electron, two per lane (independent of the exchange above)
-  double dfl = 0.0, ge[3] = {0.0, 0.0, 0.0}, gft[2][3];
-  SjPair P[2];
-  int pid[2];
-  bool pv[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int b = (t ^ L.ph) * 5 + L.gl;
-    pv[t] = L.val[t] && !(t == 0 && isown);
-    pid[t] = pv[t] ? sj_pidx(sid_e, b) : 0;
-    const double dnx = xn[0] - L.x[t][0], dny = xn[1] - L.x[t][1], dnz = xn[2] - L.x[t][2];
-    const double r2 = pv[t] ? fma(dnz, dnz, fma(dny, dny, dnx * dnx)) : 1.0;
-    P[t] = sj_pair(c, r2);
-    const double u_old = L.sm[SJ_OFF_PC + pid[t]], gr_old = L.sm[SJ_OFF_PC + SJ_NPAIR + pid[t]];
-    const double m = pv[t] ? 1.0 : 0.0;
-    dfl = fma(m, P[t].u - u_old, dfl);
-    const double gn_ = m * P[t].gr, go_ = m * gr_old;
-    // grad_b f changes by the (b,e) term: -(x_e - x_b) g/r
-    gft[t][0] = L.gf[t][0] + go_ * (xo[0] - L.x[t][0]) - gn_ * dnx;
-    gft[t][1] = L.gf[t][1] + go_ * (xo[1] - L.x[t][1]) - gn_ * dny;
-    gft[t][2] = L.gf[t][2] + go_ * (xo[2] - L.x[t][2]) - gn_ * dnz;
-    ge[0] = fma(gn_, dnx, ge[0]); ge[1] = fma(gn_, dny, ge[1]); ge[2] = fma(gn_, dnz, ge[2]);
-  }
-  // reduction round 1 inputs: df and grad_e f at the trial point (summed from scratch)
-  if (L.wr) {
-    mb[MB_RIN + L.gl] = dfl;
-    mb[MB_RIN + 5 + L.gl] = ge[0];
-    mb[MB_RIN + 10 + L.gl] = ge[1];
-    mb[MB_RIN + 15 + L.gl] = ge[2];
-  }
-  sj_sync();
-  on[2] = mb[MB_E]; on[3] = mb[MB_E + 1]; on[4] = mb[MB_E + 2];
-  if (L.gl < 4) {
-    const double* r = mb + MB_RIN + 5 * L.gl;
-    const double s = (((r[0] + r[1]) + r[2]) + r[3]) + r[4];
-    if (L.wr) mb[MB_ROUT + L.gl] = s;
-  }
-  // ---- determinant ratio and Sherman-Morrison update of this lane's column
-  double phin[5];
-  sj_phi(xn, on, n, phin);
-  double v = 0.0, ratio = 0.0;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { v = fma(phin[k], cg[k], v); ratio = fma(phin[k], ce[k], ratio); }
-  const double inv_ratio = m_rcp(ratio);
-  const double vr = v * inv_ratio;
-  double mt[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) mt[k] = isown ? ce[k] * inv_ratio : fma(-ce[k], vr, cg[k]);
-  sj_sync();
-  const double df = mb[MB_ROUT];
-  bool acc;
-  double q;
-  if (METROP == MOLE_METROP_DIFFUSE) {
-    if (isown) { gft[0][0] = mb[MB_ROUT + 1]; gft[0][1] = mb[MB_ROUT + 2]; gft[0][2] = mb[MB_ROUT + 3]; }
-    // Frobenius norms over ALL electrons' drift (metrop.rs:182-193)
-    double Gt[3], G1[3], c1[5];
-    sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], mt, Gt);
-    const double* minv1 = L.sm + SJ_OFF_MINV + (spin ^ 1) * 25;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) c1[k] = minv1[k * 5 + L.gl];
-    sj_gradlnD(c, L.x[1], L.orb[1], c1, G1);
-    double sh = 0.0, sl = 0.0;
-#pragma unroll
-    for (int qq = 0; qq < 3; ++qq) {
-      const double dx = isown ? xo[qq] - xn[qq] : 0.0;
-      const double a0 = dx - (Gt[qq] + gft[0][qq]) * param, b0 = -dx - (Gown[qq] + L.gf[0][qq]) * param;
-      const double a1 = (G1[qq] + gft[1][qq]) * param, b1 = (G1[qq] + L.gf[1][qq]) * param;
-      const double m0 = L.val[0] ? 1.0 : 0.0, m1 = L.val[1] ? 1.0 : 0.0;
-      sh = fma(m0 * a0, a0, fma(m1 * a1, a1, sh));
-      sl = fma(m0 * b0, b0, fma(m1 * b1, b1, sl));
-    }
-    if (L.wr) { mb[MB_RIN + L.gl] = sh; mb[MB_RIN + 5 + L.gl] = sl; }
-    sj_sync();
-    // exp(df), t_high, t_low: one exponential per lane (lanes 0, 1, 2)
-    double arg = df;
-    if (L.gl == 1 || L.gl == 2) {
-      const double* r = mb + MB_RIN + 5 * (L.gl - 1);
-      arg = -((((r[0] + r[1]) + r[2]) + r[3]) + r[4]) * inv2tau;
-    }
-    const double e3 = m_exp(arg);
-    if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = e3;
-    sj_sync();
-    const double ef = mb[MB_E], th = mb[MB_E + 1], tl = mb[MB_E + 2];
-    q = ratio * ef;                                            // psi'/psi
-    const bool node = !(ratio > 0.0);                          // signum(psi') != signum(psi) or NaN, :178-180
-    const double A = sj_clamp_acceptance(th * (q * q) / tl, compat);   // :195
-    acc = !node && (A > u_acc);
-  } else {
-    q = ratio * m_exp(df);
-    acc = sj_clamp_acceptance(q * q, compat) > u_acc;          // metrop.rs:80
-    if (isown) { gft[0][0] = mb[MB_ROUT + 1]; gft[0][1] = mb[MB_ROUT + 2]; gft[0][2] = mb[MB_ROUT + 3]; }
-  }
-  if (acc) {
-    if (isown) {
-#pragma unroll
-      for (int qq = 0; qq < 3; ++qq) L.x[0][qq] = xn[qq];
-#pragma unroll
-      for (int qq = 0; qq < 5; ++qq) L.orb[0][qq] = on[qq];
-      if (L.act)
-#pragma unroll
-        for (int qq = 0; qq < 3; ++qq) L.sm[SJ_OFF_XS + sid_e * 3 + qq] = xn[qq];
-    }
-    if (L.act) {
-      double* mw = L.sm + SJ_OFF_MINV + spin * 25;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) mw[k * 5 + L.gl] = mt[k];
-    }
-#pragma unroll
-    for (int qq = 0; qq < 3; ++qq) { L.gf[0][qq] = gft[0][qq]; L.gf[1][qq] = gft[1][qq]; }
-    L.psi *= q;
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (pv[t] && L.act) {
-        double* pc = L.sm + SJ_OFF_PC + pid[t];
-        pc[0] = P[t].u; pc[SJ_NPAIR] = P[t].gr; pc[2 * SJ_NPAIR] = P[t].lt; pc[3 * SJ_NPAIR] = P[t].ir; pc[4 * SJ_NPAIR] = P[t].R;
-      }
-  }
-  sj_sync();
-  return acc;
-}
-#endif
 
 #include "mole_sj_move.cuh"
 

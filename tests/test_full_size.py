@@ -1,0 +1,191 @@
+"""BASELINE.json's configurations at their FULL sizes on the GPU.
+
+The oracle cannot follow 2^16..2^18 walkers for thousands of sweeps in seconds, so at full size parity is
+checked through properties that do not depend on the size:
+  * sub-sample parity - Philox is keyed by the global walker id, so the oracle re-runs a handful of
+    walkers taken from both ends of the full ensemble and must land on the same final configurations
+    (one flipped accept/reject anywhere in the run would move a configuration by O(1));
+  * shard additivity - the two halves run as separate ensembles reproduce the same configurations bit for
+    bit and their accumulators add up to the full run's;
+  * counting identities of the accumulators, Cauchy-Schwarz / positive semi-definiteness of the SR moments;
+  * known-answer energies of the reference tests within statistical error bars.
+DMC config 4 is cheap per step, so one full-size time step and one full-size branching are compared with
+the oracle walker for walker."""
+import numpy as np
+import pytest
+
+from common import SEED0, cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mole():
+    import mole_b200
+    return mole_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+def _subsample_parity(mole, orc, c, ens_cfgs0, final, W, ids, metrop_kind, param, steps, block, nan_reject=0, tol=1e-8):
+    opts = orc.run_options(metrop_kind, param, orc.OBS_ENERGY, nan_reject=nan_reject)
+    for lo in ids:
+        sub = ens_cfgs0[lo:lo + 4]
+        r = orc.ensemble_run(c["owf"], c["oham"], opts, sub, SEED0, steps, block, walker_offset=lo, trace=False)
+        assert np.max(np.abs(r["cfgs"] - final[lo:lo + 4])) < tol, lo
+    return r
+
+
+def _shards_add_up(mole, wf, op, met, W, ne, init, sweep_kw, full_cfgs, full_acc):
+    accs = []
+    for k in range(2):
+        h = mole.Ensemble(W // 2, ne, SEED0, walker_offset=k * (W // 2))
+        init(h)
+        h.sweep(wf, met, op, **sweep_kw)
+        assert np.array_equal(h.get_configs(), full_cfgs[k * (W // 2):(k + 1) * (W // 2)])
+        accs.append(h.acc_get())
+    for f in ("n_samples", "n_blocks", "n_accept", "n_moves"):
+        assert getattr(accs[0], f) + getattr(accs[1], f) == getattr(full_acc, f)
+    for f in ("sum_e", "sum_e2", "sum_b", "sum_b2"):
+        assert abs(getattr(accs[0], f) + getattr(accs[1], f) - getattr(full_acc, f)) <= 1e-10 * abs(getattr(full_acc, f))
+    return accs
+
+
+def test_config1_h2_vmc_full_size(mole, orc):
+    """H2 Heitler-London, Diffuse tau = 0.25, 2^16 walkers, 250 blocks of 10 (hydrogen_molecule.rs:184-199,252)."""
+    c = cases()["h2"]
+    wf, op = c["make"](mole)
+    W, steps, block = 1 << 16, 2500, 10
+    met = mole.MetropolisDiffuse(0.25, SEED0)
+    ens = mole.Ensemble(W, 2, SEED0)
+    ens.init_uniform()
+    x0 = ens.get_configs().copy()
+    obs = mole.ffi.OBS_ENERGY | mole.ffi.OBS_PGRAD | mole.ffi.OBS_WFVALUE
+    kw = dict(n_sweeps=steps, n_discard=block, block_size=block, observables=obs)
+    ens.sweep(wf, met, op, **kw)
+    acc, xf = ens.acc_get(), ens.get_configs()
+    assert acc.n_samples == W * (steps - block) and acc.n_blocks == W * (steps // block - 1)
+    assert acc.n_moves == 2 * W * steps and 0.5 < acc.n_accept / acc.n_moves < 1.0
+    assert np.isfinite(xf).all()
+    _subsample_parity(mole, orc, c, x0, xf, W, (0, W // 2 - 2, W - 4), orc.METROP_DIFFUSE, 0.25, steps, block)
+    _shards_add_up(mole, wf, op, met, W, 2, lambda h: h.init_uniform(), kw, xf, acc)
+    e, err, accp, g = mole.acc_finalize(acc)
+    # E(alpha = 0.5, R = 1.4): the oracle's own long run of 256 walkers is the known answer
+    ref = orc.ensemble_run(c["owf"], c["oham"], orc.run_options(orc.METROP_DIFFUSE, 0.25, orc.OBS_ENERGY), x0[:256], SEED0,
+                           steps, block, trace=False)["energy"]
+    sig = ref.mean(axis=1).std() / np.sqrt(256)
+    assert abs(e - ref.mean()) < 5 * np.hypot(sig, err) and err < 2e-4
+    # <O> and <O E> moments: Cauchy-Schwarz on the P = 1 SR element
+    n = acc.n_samples
+    assert acc.sum_oo[0] * n >= acc.sum_o[0] ** 2 and np.isfinite(g).all()
+
+
+def test_config2_he_known_answer(mole):
+    """He product of 1s STOs: E(alpha) = alpha^2 - 27/8 alpha exactly (helium_lcao.rs:134 asserts it at alpha = 1.5);
+    4096 walkers x 2500 sweeps of Diffuse tau = 0.1."""
+    wf = mole.HeliumAtomWaveFunction(1.69)
+    op = mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [2])
+    met = mole.MetropolisDiffuse(0.1, SEED0)
+    ens = mole.Ensemble(4096, 2, SEED0)
+    ens.init_uniform()
+    ens.sweep(wf, met, op, n_sweeps=2500, n_discard=10, block_size=10, observables=mole.ffi.OBS_ENERGY)
+    e, err, accp, _ = mole.acc_finalize(ens.acc_get())
+    exact = 1.69 ** 2 - 27.0 / 8.0 * 1.69
+    assert abs(e - exact) < 5 * err and err < 5e-4
+
+
+def test_config3_h2plus_box_full_size(mole, orc):
+    """H2+ product wavefunction, MetropolisBox(1.0), 2^16 walkers x 10 000 sweeps, block 100
+    (hydrogen_molecular_ion_lcao.rs:103-140 asserts E ~ -0.565 within one sample standard deviation)."""
+    c = cases()["h2p"]
+    wf, op = c["make"](mole)
+    W, steps, block = 1 << 16, 10000, 100
+    met = mole.MetropolisBox(1.0, SEED0)
+    ens = mole.Ensemble(W, 1, SEED0)
+    ens.init_uniform()
+    x0 = ens.get_configs().copy()
+    ens.sweep(wf, met, op, n_sweeps=steps, n_discard=block, block_size=block, observables=mole.ffi.OBS_ENERGY)
+    acc, xf = ens.acc_get(), ens.get_configs()
+    assert acc.n_samples == W * (steps - block) and acc.n_moves == W * steps
+    _subsample_parity(mole, orc, c, x0, xf, W, (0, W - 4), orc.METROP_BOX, 1.0, steps, block)
+    e, err, accp, _ = mole.acc_finalize(acc)
+    std = np.sqrt(acc.sum_e2 / acc.n_samples - e * e)
+    assert abs(e - (-0.565)) < std and err < 1e-4                    # the reference's own criterion (:139-140)
+    # and the tight one: the oracle's run of 128 of these walkers agrees within the error bars
+    ref = orc.ensemble_run(c["owf"], c["oham"], orc.run_options(orc.METROP_BOX, 1.0, orc.OBS_ENERGY), x0[:128], SEED0,
+                           steps, block, trace=False)["energy"]
+    assert abs(e - ref.mean()) < 5 * np.hypot(ref.mean(axis=1).std() / np.sqrt(128), err)
+
+
+def test_config5_ne_slater_jastrow_full_size(mole, orc):
+    """Ne Slater-Jastrow, P = 7, Diffuse tau = 0.02, 2^17 walkers x 200 sweeps, block 10 (the bench workload)."""
+    c = cases()["sj_ne"]
+    wf, op = c["make"](mole)
+    W, steps, block = 1 << 17, 200, 10
+    met = mole.MetropolisDiffuse(0.02, SEED0)
+    ens = mole.Ensemble(W, 10, SEED0)
+    ens.init_normal(0.5)
+    x0 = ens.get_configs().copy()
+    obs = mole.ffi.OBS_ENERGY | mole.ffi.OBS_PGRAD | mole.ffi.OBS_WFVALUE
+    kw = dict(n_sweeps=steps, n_discard=block, block_size=block, observables=obs)
+    ens.sweep(wf, met, op, **kw)
+    acc, xf = ens.acc_get(), ens.get_configs()
+    assert acc.n_samples == W * (steps - block) and acc.n_moves == 10 * W * steps and acc.n_params == 7
+    assert np.isfinite(xf).all() and 0.5 < acc.n_accept / acc.n_moves < 1.0
+    _subsample_parity(mole, orc, c, x0, xf, W, (0, W - 4), orc.METROP_DIFFUSE, 0.02, steps, block, nan_reject=1, tol=1e-7)
+    accs = _shards_add_up(mole, wf, op, met, W, 10, lambda h: h.init_normal(0.5), kw, xf, acc)
+    P, n = 7, acc.n_samples
+    for k in range(P):
+        assert abs(accs[0].sum_o[k] + accs[1].sum_o[k] - acc.sum_o[k]) <= 1e-9 * abs(acc.sum_o[k]) + 1e-6
+    # SR moments: covariance matrix of O is symmetric positive semi-definite
+    S = np.empty((P, P))
+    for k in range(P):
+        for l in range(P):
+            S[k, l] = acc.oo(k, l) / n - acc.sum_o[k] * acc.sum_o[l] / n ** 2
+    ev = np.linalg.eigvalsh(S)
+    assert ev.min() > -1e-9 * ev.max()
+    e, err, accp, g = mole.acc_finalize(acc)
+    assert np.isfinite(e) and np.isfinite(err) and np.isfinite(g).all()   # 200 sweeps from N(0, 0.5): not yet equilibrated
+
+
+def test_config4_dmc_full_size_step_and_branch_match_oracle(mole, orc):
+    """DMC, Gaussian guide for the H atom, tau = 0.025, SRBrancher, 2^18 walkers (examples/dmc.rs): one full-size time
+    step and one full-size branching against the oracle, then the launch-bound block loop against the step loop."""
+    c = cases()["gauss_h"]
+    wf, op = c["make"](mole)
+    W = 1 << 18
+    seed = bytes([1] * 32)
+    met = mole.MetropolisDiffuse.from_rng(0.025, seed).fix_nodes()
+    dmc = mole.DmcRunner(wf, W, -0.45, op, met, mole.SRBrancher.new(), identical_start=False)
+    ens = dmc.ensemble
+    x = ens.get_configs().copy()
+    w = np.ones(W)
+    for t in range(2):
+        ens.set_configs(x); ens.set_weights(w); ens.step = t
+        e_o, tw_o, w, x = orc.dmc_step(c["owf"], c["oham"], w, x, 0.025, 0.025, -0.45, seed, t)
+        swe, sw = ens.dmc_step(wf, met, op, 0.025, -0.45)
+        assert abs(swe / sw - e_o) < 1e-10 * abs(e_o) and abs(sw - tw_o) < 1e-10 * tw_o
+        assert np.max(np.abs(ens.get_weights() - w)) < 1e-12 and np.max(np.abs(ens.get_configs() - x)) < 1e-12
+        ens.set_configs(x); ens.set_weights(w)
+        w, x = orc.branch(orc.BRANCH_SR, 1, w, x, seed, t)
+        ens.branch(mole.ffi.BRANCH_SR)
+        assert np.array_equal(ens.get_configs(), x)                   # 2^18 picks, bit for bit
+        assert np.allclose(ens.get_weights(), w, rtol=1e-13, atol=0)
+        src = ens.branch_sources()
+        assert src.min() >= 0 and src.max() < W and ens.n_walkers == W     # population conserved
+    a = mole.DmcRunner(wf, W, -0.45, op, met, mole.SRBrancher.new(), identical_start=False).ensemble
+    b = mole.DmcRunner(wf, W, -0.45, op, met, mole.SRBrancher.new(), identical_start=False).ensemble
+    ea = []
+    for _ in range(12):
+        swe, sw = a.dmc_step(wf, met, op, 0.025, -0.47)
+        ea.append(swe / sw)
+        a.branch(mole.ffi.BRANCH_SR)
+    eb = b.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.025, -0.47, 12)
+    assert np.array_equal(np.array(ea), eb) and np.array_equal(a.get_configs(), b.get_configs())
+    wts = b.get_weights()
+    assert np.all(wts == wts[0])                                       # every walker carries the mean weight (branching.rs:32-37)
