@@ -45,7 +45,10 @@ constexpr int SJ_OFF_ACC = SJ_OFF_MB + SJ_MB;              // [42] sum O_k, sum 
 constexpr int SJ_NMOM = 42;
 constexpr int SJ_STRIDE = 373;                             // >= SJ_OFF_ACC + SJ_NMOM and == 5 (mod 16)
 static_assert(SJ_STRIDE >= SJ_OFF_ACC + SJ_NMOM && SJ_STRIDE % 16 == 5, "per-walker stride");
-constexpr int SJ_REFRESH_EVERY = 4;                        // sweeps between from-scratch rebuilds of the inverses
+#ifndef MOLE_SJ_REFRESH_EVERY
+#define MOLE_SJ_REFRESH_EVERY 8
+#endif
+constexpr int SJ_REFRESH_EVERY = MOLE_SJ_REFRESH_EVERY;    // sweeps between from-scratch rebuilds of the inverses
 constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
 // mailbox slots
 constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] old position of the moved electron
