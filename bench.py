@@ -111,10 +111,12 @@ def main():
     ap.add_argument("--impl", default="mole_b200", choices=["mole_b200", "reference"])
     ap.add_argument("--walkers", type=int, default=1 << 17, help="walkers per GPU (2^20 over 8 GPUs)")
     ap.add_argument("--sweeps", type=int, default=200, help="sweeps per optimisation iteration (first block discarded)")
-    ap.add_argument("--ref-walkers", type=int, default=256)
-    ap.add_argument("--ref-sweeps", type=int, default=20)
-    ap.add_argument("--cpu-baseline-walkers", type=int, default=256)
-    ap.add_argument("--cpu-baseline-sweeps", type=int, default=100)
+    # CPU legs: bounded samples of the same workload (~4e4 walker-steps/s on 16 cores):
+    # reference arm ~1 s per step, cpu_baseline ~10 s in total
+    ap.add_argument("--ref-walkers", type=int, default=1024)
+    ap.add_argument("--ref-sweeps", type=int, default=40)
+    ap.add_argument("--cpu-baseline-walkers", type=int, default=1024)
+    ap.add_argument("--cpu-baseline-sweeps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--equil-box-sweeps", type=int, default=200)
