@@ -111,3 +111,22 @@ extern "C" {
     pub fn mole_ensemble_save(ens: *mut mole_ens_s, path: *const core::ffi::c_char) -> i32;
     pub fn mole_ensemble_load(ens: *mut mole_ens_s, path: *const core::ffi::c_char) -> i32;
 }
+
+// enumerations of include/mole_b200.h
+pub const MOLE_METROP_BOX: i32 = 0;
+pub const MOLE_METROP_DIFFUSE: i32 = 1;
+pub const MOLE_OBS_ENERGY: u32 = 1;
+pub const MOLE_OBS_PGRAD: u32 = 2;
+pub const MOLE_OBS_WFVALUE: u32 = 4;
+pub const MOLE_OBS_KINETIC: u32 = 8;
+pub const MOLE_OPT_SD: i32 = 0;
+pub const MOLE_OPT_MOMENTUM: i32 = 1;
+pub const MOLE_OPT_NESTEROV: i32 = 2;
+pub const MOLE_OPT_LBFGS: i32 = 3;
+pub const MOLE_OPT_SR: i32 = 4;
+pub const MOLE_BRANCH_SR: i32 = 0;
+pub const MOLE_BRANCH_SIMPLE: i32 = 1;
+pub const MOLE_VMC_RESTART_EACH_ITER: u32 = 1;
+extern "C" {
+    pub fn mole_dmc_block(ens: *mut mole_ens_s, wf: *mut mole_wf_s, m: *mut mole_metrop_s, op: *mut mole_op_s, branch_kind: i32, time_step: f64, reference_energy: f64, n_steps: i32, step_energies: *mut f64) -> i32;
+}

@@ -10,10 +10,13 @@ use optimize::Optimize;
 use std::ptr;
 use wavefunction_traits::{Differentiate, Function, WaveFunction};
 
-type Result<T> = std::result::Result<T, Error>;
+pub(crate) type Result<T> = std::result::Result<T, Error>;
+
+mod drivers;
+pub use drivers::{BlockLog, EmptyLogger, GpuDmcRunner, GpuLog, GpuMetropolis, GpuOptimizer, GpuSampler};
 
 /// status code -> errors::Error (src/errors/src/lib.rs:8-15); codes >= 100 are CUDA/NCCL/argument failures
-fn check(rc: i32) -> Result<()> {
+pub(crate) fn check(rc: i32) -> Result<()> {
     match rc {
         sys::MOLE_OK => Ok(()),
         sys::MOLE_ERR_FUNC => Err(Error::FuncError),
