@@ -225,6 +225,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->x); cudaFree(e->x2); cudaFree(e->w); cudaFree(e->w2); cudaFree(e->el); cudaFree(e->el2);
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
   cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath);
+  cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen);
   delete e;
   return MOLE_OK;
 }
@@ -704,11 +705,15 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
     const double new_weight = local_sum / (double)W;          // branching.rs:21 (stratified per rank)
     return sr_branch_launch(e, norm_factor, new_weight, nullptr, 0, 0.0, nullptr, nullptr);
   } else {
-    int32_t* list = nullptr; int32_t* fen = nullptr; uint32_t* mask = nullptr;
+    // scratch of the clone list (<= 3 copies per walker, branching.rs:60) lives with the ensemble: no
+    // allocation or synchronisation per time step
     const int64_t cap = 3 * W;
-    CU(ctx, cudaMalloc(&list, cap * sizeof(int32_t)));
-    CU(ctx, cudaMalloc(&mask, (cap / 32 + 2) * sizeof(uint32_t)));
-    CU(ctx, cudaMalloc(&fen, (cap / 32 + 3) * sizeof(int32_t)));
+    if (!e->sb_list) {
+      CU(ctx, cudaMalloc(&e->sb_list, cap * sizeof(int32_t)));
+      CU(ctx, cudaMalloc(&e->sb_mask, (cap / 32 + 2) * sizeof(uint32_t)));
+      CU(ctx, cudaMalloc(&e->sb_fen, (cap / 32 + 3) * sizeof(int32_t)));
+    }
+    int32_t* list = e->sb_list; int32_t* fen = e->sb_fen; uint32_t* mask = e->sb_mask;
     simple_copies_scan_kernel<<<tiles, SCAN_THREADS, 0, st>>>(e->w, W, e->walker_offset, e->key, e->step, e->cum, e->blocksums);
     KERNEL_CHECK(ctx);
     scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(e->blocksums, tiles);
@@ -721,8 +726,6 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
     KERNEL_CHECK(ctx);
     gather_by_list_kernel<<<cdiv(W, 128), 128, 0, st>>>(e->src, W, n, e->x, e->x2, e->el, e->el2, e->w, e->w2, e->src);
     KERNEL_CHECK(ctx);
-    CU(ctx, cudaStreamSynchronize(st));
-    cudaFree(list); cudaFree(mask); cudaFree(fen);
   }
   std::swap(e->x, e->x2);
   std::swap(e->w, e->w2);

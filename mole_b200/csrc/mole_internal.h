@@ -114,6 +114,7 @@ struct mole_ens_s {
   double* step_e = nullptr; // [step_e_cap] per-step ensemble energies of a DMC block (mole_dmc_block)
   int64_t step_e_cap = 0;
   double* gath = nullptr;   // [nranks][4] all-gathered per-step DMC reductions (multi-rank block loop)
+  int32_t* sb_list = nullptr; int32_t* sb_fen = nullptr; uint32_t* sb_mask = nullptr;   // SimpleBranching scratch
 };
 
 // ---- host-only helpers (mole_host.cpp) ---------------------------------------------------------
