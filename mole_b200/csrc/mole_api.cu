@@ -225,7 +225,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->x); cudaFree(e->x2); cudaFree(e->w); cudaFree(e->w2); cudaFree(e->el); cudaFree(e->el2);
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
   cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath);
-  cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen);
+  cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen); cudaFree(e->sb_draws);
   delete e;
   return MOLE_OK;
 }
@@ -712,6 +712,7 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
       CU(ctx, cudaMalloc(&e->sb_list, cap * sizeof(int32_t)));
       CU(ctx, cudaMalloc(&e->sb_mask, (cap / 32 + 2) * sizeof(uint32_t)));
       CU(ctx, cudaMalloc(&e->sb_fen, (cap / 32 + 3) * sizeof(int32_t)));
+      CU(ctx, cudaMalloc(&e->sb_draws, 2 * W * sizeof(int64_t)));
     }
     int32_t* list = e->sb_list; int32_t* fen = e->sb_fen; uint32_t* mask = e->sb_mask;
     simple_copies_scan_kernel<<<tiles, SCAN_THREADS, 0, st>>>(e->w, W, e->walker_offset, e->key, e->step, e->cum, e->blocksums);
@@ -722,7 +723,16 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
     KERNEL_CHECK(ctx);
     simple_build_list_kernel<<<cdiv(W, 256), 256, 0, st>>>(e->cum, e->blocksums, tiles, W, e->walker_offset, e->key, e->step, list);
     KERNEL_CHECK(ctx);
-    simple_remove_kernel<<<1, 1024, 0, st>>>(list, e->blocksums, tiles, W, e->walker_offset, e->key, e->step, mask, fen, e->src);
+    // bitmask + Fenwick tree in shared memory when 3W/32 words fit (W <= ~2.6e5), else in the global scratch
+    int smem_words = (int)(cap / 32 + 3);
+    if ((size_t)smem_words * 8 > 200 * 1024) smem_words = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU(ctx, cudaFuncSetAttribute(simple_remove_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    simple_remove_kernel<<<1, 1024, (size_t)smem_words * 8, st>>>(list, e->blocksums, tiles, W, e->walker_offset, e->key, e->step,
+                                                                 mask, fen, e->sb_draws, smem_words, e->src);
     KERNEL_CHECK(ctx);
     gather_by_list_kernel<<<cdiv(W, 128), 128, 0, st>>>(e->src, W, n, e->x, e->x2, e->el, e->el2, e->w, e->w2, e->src);
     KERNEL_CHECK(ctx);

@@ -264,11 +264,13 @@ __global__ void simple_build_list_kernel(const unsigned long long* __restrict__ 
 
 // pass 4b: remove `excess` random entries one at a time, each index drawn from the CURRENT list
 // length (:83-89).  Sequential by definition; done by one CTA with an alive-bitmask and a Fenwick
-// tree of per-word popcounts in global scratch.  Writes the compacted list in place.
+// tree of per-word popcounts (shared memory when they fit, else global scratch); the draws themselves
+// are generated in parallel beforehand.  Writes the compacted list to list_out.
 __global__ void __launch_bounds__(1024) simple_remove_kernel(int32_t* list, const unsigned long long* tile_sums,
                                                              int n_tiles, int64_t W, uint64_t walker_offset, RngKey key,
-                                                             uint32_t step, uint32_t* mask /* words */, int32_t* fen /* words+1 */,
-                                                             int32_t* list_out) {
+                                                             uint32_t step, uint32_t* mask_g /* words */, int32_t* fen_g /* words+1 */,
+                                                             int64_t* draws /* 2W */, int smem_words, int32_t* list_out) {
+  extern __shared__ uint32_t sb_smem[];
   const unsigned long long total = tile_sums[n_tiles];
   const int64_t n_new = (int64_t)(total >> 32) + (int64_t)(total & 0xffffffffull);
   if (n_new <= W) {
@@ -276,6 +278,17 @@ __global__ void __launch_bounds__(1024) simple_remove_kernel(int32_t* list, cons
     return;
   }
   const int64_t words = (n_new + 31) / 32;
+  // the bitmask and the Fenwick tree sit in shared memory whenever they fit (the walk below is a chain of
+  // dependent loads: ~30 cycles each there against ~600 in global memory)
+  const bool in_smem = words + 1 <= (int64_t)smem_words;
+  uint32_t* mask = in_smem ? sb_smem : mask_g;
+  int32_t* fen = in_smem ? (int32_t*)(sb_smem + smem_words) : fen_g;
+  const int64_t excess = n_new - W;
+  // the j-th removal draws from the CURRENT length n_new - j, which is known in advance: all draws in parallel
+  for (int64_t j = threadIdx.x; j < excess; j += blockDim.x) {
+    const Philox4 p = mole_draw(key, walker_offset + (uint64_t)j, step, DOM_BRANCH, 2, 0);
+    draws[j] = (int64_t)__umul64hi(mole_u64(p), (unsigned long long)(n_new - j));
+  }
   for (int64_t q = threadIdx.x; q < words; q += blockDim.x) {
     const int64_t rem = n_new - q * 32;
     mask[q] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
@@ -291,11 +304,8 @@ __global__ void __launch_bounds__(1024) simple_remove_kernel(int32_t* list, cons
     }
     int64_t top = 1;
     while (top * 2 <= words) top *= 2;
-    int64_t len = n_new;
-    const int64_t excess = n_new - W;
-    for (int64_t j = 0; j < excess; ++j, --len) {
-      const Philox4 p = mole_draw(key, walker_offset + (uint64_t)j, step, DOM_BRANCH, 2, 0);
-      int64_t k = (int64_t)__umul64hi(mole_u64(p), (unsigned long long)len);   // k-th (0-based) alive entry
+    for (int64_t j = 0; j < excess; ++j) {
+      int64_t k = draws[j];                                            // k-th (0-based) alive entry
       int64_t pos = 0;
       for (int64_t bit = top; bit > 0; bit >>= 1) {
         const int64_t nxt = pos + bit;

@@ -115,6 +115,7 @@ struct mole_ens_s {
   int64_t step_e_cap = 0;
   double* gath = nullptr;   // [nranks][4] all-gathered per-step DMC reductions (multi-rank block loop)
   int32_t* sb_list = nullptr; int32_t* sb_fen = nullptr; uint32_t* sb_mask = nullptr;   // SimpleBranching scratch
+  int64_t* sb_draws = nullptr;
 };
 
 // ---- host-only helpers (mole_host.cpp) ---------------------------------------------------------
