@@ -211,6 +211,7 @@ __global__ void fill_kernel(double* p, int64_t n, double v) {
 template <int KIND>
 __global__ void eval_kernel(const double* __restrict__ x, int64_t W, WfParams p, HamParams h, int have_ham,
                             double* psi, double* grad, double* lap, double* hpsi, double* pgrad) {
+  mole_math_smem_init();
   using WF = WfDev<KIND>;
   constexpr int NE = WF::NE;
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,6 +247,7 @@ __global__ void eval_kernel(const double* __restrict__ x, int64_t W, WfParams p,
 // [+ sample E_L, O_k, moments]) -> store state -> block-tree reduction of the accumulators.
 template <int KIND, int METROP, bool OPT>
 __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepParams sp) {
+  mole_math_smem_init();
   using WF = WfDev<KIND>;
   constexpr int NE = WF::NE;
   constexpr int NP = OPT ? WF::NP : 0;
@@ -363,6 +365,7 @@ MOLE_D void mole_dmc_fold_partials(const double* partials, unsigned rows, double
 // red[0] += sum w E_old, red[1] += sum w (pre-update), red[2] = sum w (post-update), red[3] = max w (post-update)
 template <int KIND>
 __global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams dp) {
+  mole_math_smem_init();
   using WF = WfDev<KIND>;
   constexpr int NE = WF::NE;
   const WfParams& p = dp.wf;
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams
 
 // ------------------------------------------------------------------ math probe
 __global__ void math_probe_kernel(int which, const double* __restrict__ in, int64_t n, double* out) {
+  mole_math_smem_init();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double x = in[i];

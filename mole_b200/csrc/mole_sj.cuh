@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
                                                               int have_ham, double* psi, double* grad, double* lap,
                                                               double* hpsi, double* pgrad) {
   extern __shared__ double sj_smem[];
+  mole_math_smem_init();
   const SjConst c = sj_const(p);
   const int g = (threadIdx.x & 31) / 5;
   const int64_t w = ((int64_t)blockIdx.x * SJ_WARPS + (threadIdx.x >> 5)) * SJ_WPW + g;
@@ -494,6 +495,7 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
 template <int METROP, bool OPT>
 __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const SweepParams sp) {
   extern __shared__ double sj_smem[];
+  mole_math_smem_init();
   const SjConst c = sj_const(sp.wf);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / 5;
@@ -636,6 +638,7 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
 // ------------------------------------------------------------------ DMC time step (dmc.rs:87-130)
 __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_dmc_kernel(const DmcParams dp) {
   extern __shared__ double sj_smem[];
+  mole_math_smem_init();
   const SjConst c = sj_const(dp.wf);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / 5;
