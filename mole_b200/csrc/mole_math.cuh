@@ -14,7 +14,9 @@
 
 #if defined(__CUDACC__)
 
-// 1/x for finite normal x != 0  (MUFU.RCP64H seed, cubic + quadratic Newton step)
+// 1/x for finite normal x != 0.  The MUFU.RCP64H seed carries 20 mantissa bits (the low word is zero), so
+// ONE cubic Newton step y (1 + e + e^2), e = 1 - x y exact in the fma, leaves a truncation error e^3 < 2^-57
+// and a single final rounding: <= 0.6 ulp.  (-DMOLE_NEWTON2 adds the former second, quadratic step.)
 template <int N>
 MOLE_D void m_rcp_n(const double (&x)[N], double (&y)[N]) {
   double e[N];
@@ -26,10 +28,12 @@ MOLE_D void m_rcp_n(const double (&x)[N], double (&y)[N]) {
   for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
 #pragma unroll
   for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);          // y (1 + e + e^2)
+#ifdef MOLE_NEWTON2
 #pragma unroll
   for (int i = 0; i < N; ++i) e[i] = fma(-x[i], y[i], 1.0);
 #pragma unroll
   for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+#endif
 }
 MOLE_D double m_rcp(double x) {
   const double a[1] = {x};
@@ -38,7 +42,9 @@ MOLE_D double m_rcp(double x) {
   return y[0];
 }
 
-// 1/sqrt(x) for finite normal x > 0  (MUFU.RSQ64H seed, cubic + quadratic Newton step)
+// 1/sqrt(x) for finite normal x > 0.  MUFU.RSQ64H seed (20 mantissa bits), then ONE cubic Newton step
+// y (1 + e + 1.5 e^2) with e = (1 - x y^2)/2: truncation 2.5 e^3 < 2^-56; the rounding of x y/2 inside e and
+// the final rounding give ~1 ulp.  (-DMOLE_NEWTON2 adds the former second, quadratic step: ~0.6 ulp.)
 template <int N>
 MOLE_D void m_rsqrt_n(const double (&x)[N], double (&y)[N]) {
   double hx[N], e[N];
@@ -50,10 +56,12 @@ MOLE_D void m_rsqrt_n(const double (&x)[N], double (&y)[N]) {
   for (int i = 0; i < N; ++i) e[i] = fma(-hx[i] * y[i], y[i], 0.5);   // (1 - x y^2)/2
 #pragma unroll
   for (int i = 0; i < N; ++i) y[i] = fma(y[i], fma(1.5 * e[i], e[i], e[i]), y[i]);
+#ifdef MOLE_NEWTON2
 #pragma unroll
   for (int i = 0; i < N; ++i) e[i] = fma(-hx[i] * y[i], y[i], 0.5);
 #pragma unroll
   for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+#endif
 }
 MOLE_D double m_rsqrt(double x) {
   const double a[1] = {x};
@@ -68,8 +76,10 @@ MOLE_D void m_sqrt_rsqrt_n(const double (&x)[N], double (&s)[N], double (&rinv)[
   m_rsqrt_n<N>(x, rinv);
 #pragma unroll
   for (int i = 0; i < N; ++i) s[i] = x[i] * rinv[i];
+#ifdef MOLE_SQRT_CORR   // one Heron correction: <= 0.6 ulp instead of <= 2 ulp, two more dependent FMAs per value
 #pragma unroll
   for (int i = 0; i < N; ++i) s[i] = fma(fma(-s[i], s[i], x[i]), 0.5 * rinv[i], s[i]);
+#endif
 }
 MOLE_D double m_sqrt_rsqrt(double x, double& rinv) {
   const double a[1] = {x};
