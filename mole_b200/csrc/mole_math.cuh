@@ -55,7 +55,7 @@ MOLE_D void m_rsqrt_n(const double (&x)[N], double (&y)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) e[i] = fma(-hx[i] * y[i], y[i], 0.5);   // (1 - x y^2)/2
 #pragma unroll
-  for (int i = 0; i < N; ++i) y[i] = fma(y[i], fma(1.5 * e[i], e[i], e[i]), y[i]);
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i] * e[i], fma(1.5, e[i], 1.0), y[i]);   // y + (y e)(1 + 1.5 e): two levels after e
 #ifdef MOLE_NEWTON2
 #pragma unroll
   for (int i = 0; i < N; ++i) e[i] = fma(-hx[i] * y[i], y[i], 0.5);
@@ -166,14 +166,15 @@ MOLE_D void m_exp_n(const double (&xin)[N], double (&y)[N]) {
   for (int i = 0; i < N; ++i) b0[i] = fma(b1[i], r2[i], b0[i]);
 #pragma unroll
   for (int i = 0; i < N; ++i) b0[i] = fma(r2[i], b0[i], r[i]);                             // e^r - 1
-#pragma unroll
-  for (int i = 0; i < N; ++i) b0[i] = fma(T[i], b0[i], T[i]);
+  // two-step 2^k scaling (covers denormals / overflow); the first factor is folded into the table value, off
+  // the polynomial's dependency chain
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const int k = n[i] >> 6;
-    const int n1 = k >> 1, n2 = k - n1;                                                    // two-step scaling covers denormals / overflow
+    const int n1 = k >> 1, n2 = k - n1;
     const double s1 = __hiloint2double((n1 + 1023) << 20, 0), s2 = __hiloint2double((n2 + 1023) << 20, 0);
-    y[i] = (b0[i] * s1) * s2;
+    const double Ts = T[i] * s1;
+    y[i] = fma(Ts, b0[i], Ts) * s2;
   }
 }
 #else

@@ -140,8 +140,10 @@ MOLE_D void sj_phi(const double* x, const double* o, int n, double* phi) {
 // grad_i ln D = sum_k grad phi_k(r_i) Minv[k][i] from the radial cache and the electron's column m[]:
 //   grad phi_0 = -z1 e1 x/r,  grad phi_1 = (1 - z2 r) e2 x/r,  grad phi_{2+a} = e3 (e_a - z3 x_a x/r)
 MOLE_D void sj_gradlnD(const SjConst& c, const double* x, const double* o, const double* m, double* G) {
+  // s = (A - B xm) / r with A, B independent of xm, evaluated as fma(-B/r, xm, A/r): one dependent op after xm
   const double xm = fma(x[2], m[4], fma(x[1], m[3], x[0] * m[2]));
-  const double s = (fma(-c.z1 * o[2], m[0], (1.0 - c.z2 * o[0]) * o[3] * m[1]) - c.z3 * o[4] * xm) * o[1];
+  const double A = fma(-c.z1 * o[2], m[0], (1.0 - c.z2 * o[0]) * o[3] * m[1]);
+  const double s = fma(-(c.z3 * o[4]) * o[1], xm, A * o[1]);
   G[0] = fma(s, x[0], o[4] * m[2]);
   G[1] = fma(s, x[1], o[4] * m[3]);
   G[2] = fma(s, x[2], o[4] * m[4]);

@@ -108,15 +108,15 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const double* r = mb + MB_RIN + 5 * j;
-    red[j] = (((r[0] + r[1]) + r[2]) + r[3]) + r[4];
+    red[j] = ((r[0] + r[1]) + (r[2] + r[3])) + r[4];             // fixed order, three dependent adds instead of four
   }
   const double df = red[0];
   if (isown) { gft[0][0] = red[1]; gft[0][1] = red[2]; gft[0][2] = red[3]; }
   double phin[5];
   sj_phi(xn, on, n, phin);
-  double v = 0.0, ratio = 0.0;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { v = fma(phin[k], cg[k], v); ratio = fma(phin[k], ce[k], ratio); }
+  // phi'.Minv columns as two partial dot products each (dependent depth 4 instead of 6)
+  const double v = fma(phin[2], cg[2], fma(phin[1], cg[1], phin[0] * cg[0])) + fma(phin[4], cg[4], phin[3] * cg[3]);
+  const double ratio = fma(phin[2], ce[2], fma(phin[1], ce[1], phin[0] * ce[0])) + fma(phin[4], ce[4], phin[3] * ce[3]);
   const double inv_ratio = m_rcp(ratio);
   const double vr = v * inv_ratio;
   double mt[5];
@@ -128,23 +128,24 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     // Frobenius norms over ALL electrons' drift (metrop.rs:182-193)
     sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], mt, Gt);
     const double* const G1 = L.G[1];
-    double sh = 0.0, sl = 0.0;
+    double ph[3], pl[3];                                           // per-component partial sums: short chains
     const double m0 = L.val[0] ? 1.0 : 0.0, m1 = L.val[1] ? 1.0 : 0.0;
 #pragma unroll
     for (int qq = 0; qq < 3; ++qq) {
       const double dx = isown ? xo[qq] - xn[qq] : 0.0;
       const double a0 = dx - (Gt[qq] + gft[0][qq]) * param, b0 = -dx - (Gown[qq] + L.gf[0][qq]) * param;
       const double a1 = (G1[qq] + gft[1][qq]) * param, b1 = (G1[qq] + L.gf[1][qq]) * param;
-      sh = fma(m0 * a0, a0, fma(m1 * a1, a1, sh));
-      sl = fma(m0 * b0, b0, fma(m1 * b1, b1, sl));
+      ph[qq] = fma(m0 * a0, a0, (m1 * a1) * a1);
+      pl[qq] = fma(m0 * b0, b0, (m1 * b1) * b1);
     }
+    const double sh = (ph[0] + ph[1]) + ph[2], sl = (pl[0] + pl[1]) + pl[2];
     if (L.wr) { mb[MB_RIN + 20 + L.gl] = sh; mb[MB_RIN + 25 + L.gl] = sl; }
     sj_sync();
     // ---- D: exp(df), t_high and t_low: three chains together
     const double* rh = mb + MB_RIN + 20;
     const double* rl = mb + MB_RIN + 25;
-    const double targ[3] = {df, -((((rh[0] + rh[1]) + rh[2]) + rh[3]) + rh[4]) * inv2tau,
-                            -((((rl[0] + rl[1]) + rl[2]) + rl[3]) + rl[4]) * inv2tau};
+    const double targ[3] = {df, -(((rh[0] + rh[1]) + (rh[2] + rh[3])) + rh[4]) * inv2tau,
+                            -(((rl[0] + rl[1]) + (rl[2] + rl[3])) + rl[4]) * inv2tau};
     double tv[3];
     m_exp_n<3>(targ, tv);
     q = ratio * tv[0];                                             // psi'/psi
