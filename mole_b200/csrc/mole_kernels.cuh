@@ -245,8 +245,14 @@ __global__ void eval_kernel(const double* __restrict__ x, int64_t W, WfParams p,
 // ------------------------------------------------------------------ fused sweep
 // One thread per walker (grid-stride).  Per launch: load state -> n_sweeps x (N_e Metropolis moves
 // [+ sample E_L, O_k, moments]) -> store state -> block-tree reduction of the accumulators.
+// Occupancy target (measured at 2^20 walkers): 16 warps/SM (128 registers) is +3..4 % for the one- and
+// two-electron STO / Gaussian kinds and +10 % at 2^16 walkers; the H2 Heitler-London kind would spill there
+// and keeps 12 warps/SM.
+#ifndef MOLE_SWEEP_MIN_CTAS
+#define MOLE_SWEEP_MIN_CTAS(KIND) ((KIND) == K_H2_HL_STO ? 3 : 4)
+#endif
 template <int KIND, int METROP, bool OPT>
-__global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepParams sp) {
+__global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) sweep_kernel(const SweepParams sp) {
   mole_math_smem_init();
   using WF = WfDev<KIND>;
   constexpr int NE = WF::NE;
