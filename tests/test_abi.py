@@ -139,3 +139,16 @@ def test_optimizer_errors(mole):
     with pytest.raises(mole.MoleError) as ei:
         opt.compute_parameter_update(np.zeros(2), acc)
     assert ei.value.code == mole.ffi.ERR_LINALG
+
+
+def test_series_block_sizes_match_statfor_schedule(mole, orc):
+    """mole_series_block_sizes (host-only) against the oracle's restatement of scripts/statfor.rs:59-66."""
+    import numpy as np
+    for n in (0, 19, 20, 57, 400, 1999, 2000, 2001, 5000, 123457):
+        assert np.array_equal(mole.series_block_sizes(n), orc.statfor_block_sizes(n)), n
+
+
+def test_struct_sizes_of_series_and_log_records(mole):
+    import ctypes as C
+    assert C.sizeof(mole.ffi.SeriesStats) == 40 and C.sizeof(mole.ffi.BlockLog) == 56
+    assert C.sizeof(mole.ffi.SweepArgs) == 24 + 5 * 8
