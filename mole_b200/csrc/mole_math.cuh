@@ -2,7 +2,7 @@
 //
 // Why: (1) CUDA's exp(), sqrt() and '/' each carry a rarely-taken slow path whose branch splits the
 // basic block; (2) ptxas schedules a Horner / Newton chain as one serial run of DFMAs, and a dependent
-// DFMA issues only every ~9.4 cycles on B200 (measured, scratch/ubench/dfma.cu) while the FP64 pipe
+// DFMA issues only every ~9.4 cycles on B200 (measured, tools/ubench/dfma.cu) while the FP64 pipe
 // accepts one per 2 cycles per SM sub-partition.  With the 3 warps per scheduler the Slater-Jastrow
 // kernel affords, a serial chain leaves the pipe ~75% idle.  The functions below are straight-line
 // code, take N independent arguments at once and are written stage-major, so the N chains (and the
