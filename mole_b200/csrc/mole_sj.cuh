@@ -34,19 +34,26 @@ constexpr int SJ_WARPS = MOLE_SJ_WARPS;
 constexpr int SJ_THREADS = 32 * SJ_WARPS;
 constexpr int SJ_WPB = SJ_WPW * SJ_WARPS;       // walkers per CTA
 constexpr int SJ_MIN_CTAS = MOLE_SJ_MIN_CTAS;   // CTAs per SM the register budget is tuned for
+// ptxas derives the register cap of __launch_bounds__(threads, ctas) as if the CTA had a multiple of four
+// warps; -DMOLE_SJ_MAXNREG=n states the cap directly (e.g. 3 warps x 3 CTAs at 224 registers = 9 warps/SM)
+#ifdef MOLE_SJ_MAXNREG
+#define SJ_BOUNDS __maxnreg__(MOLE_SJ_MAXNREG)
+#else
+#define SJ_BOUNDS __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS)
+#endif
 constexpr int SJ_NPAIR = 45;
 constexpr int SJ_PCV = 5;                       // cached values per pair: u, g/r, lap term, 1/r, R
 // shared memory per walker (offsets in doubles)
 constexpr int SJ_OFF_PC = 0;                               // [SJ_PCV][45]
 constexpr int SJ_OFF_MINV = SJ_OFF_PC + SJ_PCV * SJ_NPAIR; // [2][5][5] inverse Slater matrices, (spin, k, j)
-constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 50 doubles
-constexpr int SJ_MB = 50;
+constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 56 doubles
+constexpr int SJ_MB = 56;
 constexpr int SJ_OFF_ACC = SJ_OFF_MB + SJ_MB;              // [42] sum O_k, sum O_k E_L, sum O_k O_l of this walker slot
 constexpr int SJ_NMOM = 42;
 constexpr int SJ_STRIDE = 373;                             // >= SJ_OFF_ACC + SJ_NMOM and == 5 (mod 16)
 static_assert(SJ_STRIDE >= SJ_OFF_ACC + SJ_NMOM && SJ_STRIDE % 16 == 5, "per-walker stride");
 #ifndef MOLE_SJ_REFRESH_EVERY
-#define MOLE_SJ_REFRESH_EVERY 8
+#define MOLE_SJ_REFRESH_EVERY 16
 #endif
 constexpr int SJ_REFRESH_EVERY = MOLE_SJ_REFRESH_EVERY;    // sweeps between from-scratch rebuilds of the inverses
 constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
@@ -54,7 +61,8 @@ constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
 constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] old position of the moved electron
 constexpr int MB_E = 8;       // [3] orbital exponentials at the trial position
 constexpr int MB_RIN = 12;    // [6][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles)
-constexpr int MB_ROUT = 42;   // [8] O_k staging (v2 move: reduction outputs)
+// measurement (sj_measure): [9][5] per-lane partial sums at 0..44, results at MB_OUT
+constexpr int MB_OUT = 45;    // [0..6] O_k, [7] 1.0, [8] E_L, [9..10] spare: every moment is a product out[k] * out[l]
 constexpr int SJ_NP = 7;
 constexpr int SJ_NACC = 10 + 2 * SJ_NP + SJ_NP * (SJ_NP + 1) / 2;   // 52 compact accumulator entries
 constexpr int SJ_ACC_PER_LANE = (SJ_NACC + 4) / 5;                   // 11
@@ -65,8 +73,26 @@ struct SjConst {
   double kappa, ikappa, z1, z2, z3, b1, b2, b3, b4;
 };
 
-__constant__ signed char c_sj_pair_a[SJ_NPAIR], c_sj_pair_b[SJ_NPAIR];   // slot ids of pair p (a<b)
-__constant__ signed char c_sj_oo_k[28], c_sj_oo_l[28];                   // (k<=l) of packed O_k O_l entry q
+// operand indices (k << 4 | l) into the MB_OUT block of the 42 per-walker optimisation moments:
+// sum O_k = out[k] * 1, sum O_k E_L = out[k] * E_L, sum O_k O_l (k <= l, packed by rows).  Shared memory,
+// because the index is lane-divergent (a divergent index into the constant bank serialises).
+__shared__ unsigned char s_sj_mom[48];
+__device__ __forceinline__ void sj_mom_table_init() {
+  const int j = threadIdx.x;
+  if (j < 48) {
+    int k = 7, l = 7;                                    // padding entries: 1.0 * 1.0, never accumulated
+    if (j < SJ_NP) { k = j; l = 7; }
+    else if (j < 2 * SJ_NP) { k = j - SJ_NP; l = 8; }
+    else if (j < SJ_NMOM) {
+      int q = j - 2 * SJ_NP;
+      k = 0;
+      while (q >= SJ_NP - k) { q -= SJ_NP - k; ++k; }
+      l = k + q;
+    }
+    s_sj_mom[j] = (unsigned char)(k << 4 | l);
+  }
+  __syncthreads();
+}
 
 MOLE_D int sj_pidx(int a, int b) {              // unordered pair of slot ids (0..9) -> 0..44
   const int lo = a < b ? a : b, hi = a < b ? b : a;
@@ -83,7 +109,8 @@ struct SjLane {
   double orb[2][5];    // r, 1/r, exp(-z1 r), exp(-z2 r), exp(-z3 r) at own electrons
   double gf[2][3];     // grad_i f
   double G[2][3];      // grad_i ln D
-  double psi;          // replicated over the group
+  double psi, fj;      // psi = L.psi * exp(L.fj): accepted moves multiply psi by the determinant ratio and add the
+                       // Jastrow change to fj; sj_fold_psi / sj_refresh bring fj back to 0.  Replicated over the group
   double* sm;          // this walker's shared-memory region
 };
 
@@ -235,9 +262,10 @@ MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
   const double d0 = sj_refresh_slot(c, L, 0);
   const double d1 = sj_refresh_slot(c, L, 1);
   double fl = 0.0;
-  for (int p = L.gl; p < SJ_NPAIR; p += 5)
-    if (sj_slot_valid(c, c_sj_pair_a[p]) && sj_slot_valid(c, c_sj_pair_b[p])) fl += L.sm[SJ_OFF_PC + p];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) fl += L.sm[SJ_OFF_PC + L.gl + 5 * i];   // cache slots of absent pairs hold zeros
   L.psi = d0 * d1 * m_exp(sj_gsum(fl, L));
+  L.fj = 0.0;
 }
 
 // full initialisation of the cooperative state from the positions in L.x (slot t = spin t)
@@ -279,6 +307,12 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
   sj_refresh(c, L);
 }
 
+// psi of the current configuration from the carried determinant part and Jastrow change
+MOLE_D void sj_fold_psi(SjLane& L) {
+  L.psi *= m_exp(L.fj);
+  L.fj = 0.0;
+}
+
 // exchange the two register slots (the spin to be moved must sit in slot 0)
 MOLE_D void sj_swap_slots(SjLane& L) {
 #pragma unroll
@@ -299,10 +333,17 @@ MOLE_D void sj_swap_slots(SjLane& L) {
 #include "mole_sj_move.cuh"
 
 // Local quantities of the current configuration:
-//   kin = -0.5 sum_i lap_i psi / psi,  pot = V (so that E_L = kin + pot),  O[k] = d ln psi / d p_k
+//   kin = -0.5 sum_i lap_i psi / psi,  pot = V (so that E_L = kin + pot), replicated over the group; with OPT the
+//   mailbox block MB_OUT holds O[k] = d ln psi / d p_k (k < 7), 1.0 and E_L on return (visible to all lanes).
 // Gout (optional): grad ln D of the two own electrons.
+// Straight-line: the nine pairs of this lane (gl, gl+5, ..) are summed without validity tests (cache slots of
+// absent pairs hold zeros, so they contribute nothing), their reciprocals go through one 9-wide batch, and the
+// nine group reductions share two warp syncs: every lane stores its partials as rows of the mailbox, every lane
+// sums rows 0 and 1 (kinetic, potential), lane gl sums rows 2+gl and 7+gl into MB_OUT.
+MOLE_D double sj_row5(const double* r) { return ((r[0] + r[1]) + (r[2] + r[3])) + r[4]; }   // fixed order, lanes 0..4
+
 template <bool OPT>
-MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& kin, double& pot, double* O,
+MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& kin, double& pot, uint32_t compat = 0,
                        double (*Gout)[3] = nullptr) {
   double kl = 0.0, vl = 0.0, dz[3] = {0.0, 0.0, 0.0};
   const bool want_ion = h.kind == MOLE_OP_IONIC_POT || h.kind == MOLE_OP_IONIC || h.kind == MOLE_OP_ELECTRONIC;
@@ -310,7 +351,6 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int spin = t ^ L.ph;
-    const int a = spin * 5 + L.gl;
     const int n = sj_spin_n(c, spin);
     const double* x = L.x[t];
     const double* o = L.orb[t];
@@ -324,18 +364,11 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     const double cp = o[4] * (c.z3 * c.z3 - 4.0 * c.z3 * ir);
     double lapD = (0 < n ? c.z1 * o[2] * (c.z1 - 2.0 * ir) : 0.0) * m[0];
     lapD = fma(1 < n ? (c.z2 * c.z2 * r - 4.0 * c.z2 + 2.0 * ir) * o[3] : 0.0, m[1], lapD);
-    lapD = fma(2 < n ? x[0] * cp : 0.0, m[2], lapD);
-    lapD = fma(3 < n ? x[1] * cp : 0.0, m[3], lapD);
-    lapD = fma(4 < n ? x[2] * cp : 0.0, m[4], lapD);
-    double Lf = 0.0;
-    for (int b = 0; b < 10; ++b) {
-      const bool pv = b != a && sj_slot_valid(c, b);
-      Lf += pv ? L.sm[SJ_OFF_PC + 2 * SJ_NPAIR + sj_pidx(a, pv ? b : (a == 0 ? 1 : 0))] : 0.0;
-    }
+    const double lapP = fma(4 < n ? x[2] * cp : 0.0, m[4], fma(3 < n ? x[1] * cp : 0.0, m[3], (2 < n ? x[0] * cp : 0.0) * m[2]));
     const double gg = G[0] * L.gf[t][0] + G[1] * L.gf[t][1] + G[2] * L.gf[t][2];
     const double ff = L.gf[t][0] * L.gf[t][0] + L.gf[t][1] * L.gf[t][1] + L.gf[t][2] * L.gf[t][2];
     const double mk = L.val[t] ? 1.0 : 0.0;
-    kl = fma(mk, lapD + 2.0 * gg + Lf + ff, kl);
+    kl = fma(mk, (lapD + lapP) + (2.0 * gg + ff), kl);
     if (want_ion) {                                              // IonicPotential::value, operator.rs:25-36
       double p = 0.0;
       for (int i = 0; i < h.n_ions; ++i) {
@@ -349,38 +382,77 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
       const double d0 = -r * o[2], d1 = -r * r * o[3], dp = -r * o[4];
       dz[0] = fma(mk * (0 < n ? d0 : 0.0), m[0], dz[0]);
       dz[1] = fma(mk * (1 < n ? d1 : 0.0), m[1], dz[1]);
-      dz[2] = fma(mk * (2 < n ? dp * x[0] : 0.0), m[2], dz[2]);
-      dz[2] = fma(mk * (3 < n ? dp * x[1] : 0.0), m[3], dz[2]);
-      dz[2] = fma(mk * (4 < n ? dp * x[2] : 0.0), m[4], dz[2]);
+      const double s2 = fma(4 < n ? x[2] : 0.0, m[4], fma(3 < n ? x[1] : 0.0, m[3], (2 < n ? x[0] : 0.0) * m[2]));
+      dz[2] = fma(mk * dp, s2, dz[2]);
     }
   }
-  // pair sums: V_ee and df/db
+  // pair sums: sum_i lap_i f = 2 sum_pairs div(rhat g), V_ee = sum 1/r (ElectronicPotential::value,
+  // operator.rs:80-90) and df/db (jastrow.tex:109-119)
+  const double* pc = L.sm + SJ_OFF_PC + L.gl;
+  double lt[9], pir[9], R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    lt[i] = pc[2 * SJ_NPAIR + 5 * i];
+    pir[i] = pc[3 * SJ_NPAIR + 5 * i];
+    R[i] = pc[4 * SJ_NPAIR + 5 * i];
+  }
+  const double lts = (((lt[0] + lt[1]) + (lt[2] + lt[3])) + ((lt[4] + lt[5]) + (lt[6] + lt[7]))) + lt[8];
+  kl = fma(2.0, lts, kl);
+  if (want_ee) vl += (((pir[0] + pir[1]) + (pir[2] + pir[3])) + ((pir[4] + pir[5]) + (pir[6] + pir[7]))) + pir[8];
   double db[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int p = L.gl; p < SJ_NPAIR; p += 5) {
-    if (!(sj_slot_valid(c, c_sj_pair_a[p]) && sj_slot_valid(c, c_sj_pair_b[p]))) continue;
-    if (want_ee) vl += L.sm[SJ_OFF_PC + 3 * SJ_NPAIR + p];       // ElectronicPotential::value, operator.rs:80-90
+  if (OPT) {
+    double den[9], id[9], a0[3] = {0.0, 0.0, 0.0}, a1[3] = {0.0, 0.0, 0.0}, a2[3] = {0.0, 0.0, 0.0}, a3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) den[i] = fma(c.b2, R[i], 1.0);
+    m_rcp_n<9>(den, id);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {                                // three interleaved partial sums per quantity
+      const double q = R[i] * id[i], R2 = R[i] * R[i];
+      a0[i % 3] += q;
+      a1[i % 3] = fma(q, q, a1[i % 3]);
+      a2[i % 3] += R2;
+      a3[i % 3] = fma(R2, R[i], a3[i % 3]);
+    }
+    db[0] = (a0[0] + a0[1]) + a0[2];
+    db[1] = -c.b1 * ((a1[0] + a1[1]) + a1[2]);
+    db[2] = (a2[0] + a2[1]) + a2[2];
+    db[3] = (a3[0] + a3[1]) + a3[2];
+  }
+  double* const mb = L.sm + SJ_OFF_MB;
+  if (L.wr) {
+    mb[L.gl] = kl;
+    mb[5 + L.gl] = vl;
     if (OPT) {
-      const double R = L.sm[SJ_OFF_PC + 4 * SJ_NPAIR + p];
-      const double id = m_rcp(fma(c.b2, R, 1.0));
-      db[0] = fma(R, id, db[0]);                                 // jastrow.tex:109-119
-      db[1] = fma(-c.b1 * R * R, id * id, db[1]);
-      db[2] = fma(R, R, db[2]);
-      db[3] = fma(R * R, R, db[3]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mb[10 + 5 * k + L.gl] = dz[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mb[25 + 5 * k + L.gl] = db[k];
     }
   }
-  kin = -0.5 * sj_gsum(kl, L);
-  pot = sj_gsum(vl, L);
+  sj_sync();
+  kin = -0.5 * sj_row5(mb);
+  pot = sj_row5(mb + 5);
   if (want_ion) pot += h.ionic_repulsion;
   const bool has_kin = h.kind == MOLE_OP_KINETIC || h.kind == MOLE_OP_IONIC || h.kind == MOLE_OP_ELECTRONIC ||
                        h.kind == MOLE_OP_HARMONIC;
   if (!has_kin) kin = 0.0;
   if (h.kind == MOLE_OP_KINETIC) pot = 0.0;
   if (OPT) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) O[k] = sj_gsum(dz[k], L);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) O[3 + k] = sj_gsum(db[k], L);
+    double oa = sj_row5(mb + 10 + 5 * L.gl);                       // O[gl]
+    double ob = sj_row5(mb + 35 + 5 * (L.gl < 2 ? L.gl : 0));      // O[5 + gl], lanes 0 and 1
+    if (compat & MOLE_COMPAT_VECTOR_DIV) {
+      // stored sample 1/d_k psi (operator/src/traits.rs:149-150) => O_k = 1/(psi^2 O_k^intended)
+      oa = 1.0 / (L.psi * L.psi * oa);
+      ob = 1.0 / (L.psi * L.psi * ob);
+    }
+    if (L.wr) {
+      mb[MB_OUT + L.gl] = oa;
+      if (L.gl < 2) mb[MB_OUT + 5 + L.gl] = ob;
+      if (L.gl == 2) mb[MB_OUT + 7] = 1.0;
+      if (L.gl == 3) mb[MB_OUT + 8] = kin + pot;
+    }
   }
+  sj_sync();
 }
 
 MOLE_D SjConst sj_const(const WfParams& p) {
@@ -471,9 +543,11 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
   HamParams hk = h;
   hk.kind = MOLE_OP_KINETIC;
   double kin, pot, O[SJ_NP], G[2][3];
-  sj_measure<true>(c, hk, L, kin, pot, O, G);
-  double kin_h = 0.0, pot_h = 0.0, O2[SJ_NP];
-  if (have_ham) sj_measure<false>(c, h, L, kin_h, pot_h, O2);
+  sj_measure<true>(c, hk, L, kin, pot, 0, G);
+#pragma unroll
+  for (int k = 0; k < SJ_NP; ++k) O[k] = L.sm[SJ_OFF_MB + MB_OUT + k];
+  double kin_h = 0.0, pot_h = 0.0;
+  if (have_ham) sj_measure<false>(c, h, L, kin_h, pot_h);
   if (!L.act) return;
   if (grad)
 #pragma unroll
@@ -495,9 +569,10 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
 
 // ------------------------------------------------------------------ fused sweep
 template <int METROP, bool OPT>
-__global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const SweepParams sp) {
+__global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
   extern __shared__ double sj_smem[];
   mole_math_smem_init();
+  if (OPT) sj_mom_table_init();
   const SjConst c = sj_const(sp.wf);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / 5;
@@ -537,8 +612,9 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
       }
       if (s < sp.n_discard) continue;                                 // montecarlo.rs:36
       const int64_t si = s - sp.n_discard;
-      double kin = 0.0, pot = 0.0, O[SJ_NP];
-      if (want_e || OPT || (sp.observables & MOLE_OBS_KINETIC)) sj_measure<OPT>(c, sp.ham, L, kin, pot, O);
+      double kin = 0.0, pot = 0.0;
+      sj_fold_psi(L);
+      if (want_e || OPT || (sp.observables & MOLE_OBS_KINETIC)) sj_measure<OPT>(c, sp.ham, L, kin, pot, sp.compat);
       const double el = kin + pot;
       double bm = 0.0;
       bool closed = false;
@@ -561,28 +637,21 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
         }
       }
       if (OPT) {
-        if (sp.compat & MOLE_COMPAT_VECTOR_DIV) {
-          // stored sample 1/d_k psi (operator/src/traits.rs:149-150) => O_k = 1/(psi^2 O_k^intended)
+        // sum O_k, sum O_k E_L, sum O_k O_l: entry j of this walker slot is out[k_j] * out[l_j]; lane gl owns j == gl (mod 5)
+        const double* os = L.sm + SJ_OFF_MB + MB_OUT;
+        if (sp.tr_pgrad && L.act && L.gl == 0) {
 #pragma unroll
-          for (int k = 0; k < SJ_NP; ++k) O[k] = 1.0 / (L.psi * L.psi * O[k]);
+          for (int k = 0; k < SJ_NP; ++k) sp.tr_pgrad[((size_t)si * SJ_NP + k) * W + w] = L.psi * os[k];   // d_k psi, or 1/d_k psi under the quirk
         }
-        double* os = L.sm + SJ_OFF_MB + MB_ROUT;
-        if (L.act && L.gl == 0) {
-#pragma unroll
-          for (int k = 0; k < SJ_NP; ++k) {
-            os[k] = O[k];
-            if (sp.tr_pgrad) sp.tr_pgrad[((size_t)si * SJ_NP + k) * W + w] = L.psi * O[k];   // d_k psi, or 1/d_k psi under the quirk
-          }
-        }
-        sj_sync();
         if (L.act) {
           double* am = L.sm + SJ_OFF_ACC;
-          for (int j = L.gl; j < SJ_NMOM; j += 5) {                   // 0 .. 2P+NOO-1, lane gl owns j == gl (mod 5)
-            double add;
-            if (j < SJ_NP) add = os[j];
-            else if (j < 2 * SJ_NP) add = os[j - SJ_NP] * el;
-            else add = os[c_sj_oo_k[j - 2 * SJ_NP]] * os[c_sj_oo_l[j - 2 * SJ_NP]];
-            am[j] += add;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const int j = L.gl + 5 * i;
+            if (i < 8 || j < SJ_NMOM) {
+              const unsigned id = s_sj_mom[j];
+              am[j] = fma(os[id >> 4], os[id & 15], am[j]);
+            }
           }
         }
         sj_sync();
@@ -638,7 +707,7 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_sweep_kernel(const
 }
 
 // ------------------------------------------------------------------ DMC time step (dmc.rs:87-130)
-__global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_dmc_kernel(const DmcParams dp) {
+__global__ void SJ_BOUNDS sj_dmc_kernel(const DmcParams dp) {
   extern __shared__ double sj_smem[];
   mole_math_smem_init();
   const SjConst c = sj_const(dp.wf);
@@ -655,13 +724,13 @@ __global__ void __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS) sj_dmc_kernel(const D
     sj_load(L, c, dp.x, w, W);
     sj_init(c, L);
     const uint64_t wid = dp.walker_offset + (uint64_t)(w < W ? w : W - 1);
-    double kin, pot, O[SJ_NP];
+    double kin, pot;
     double e_old;
     if (dp.el_cached) e_old = L.act ? dp.el[w] : 0.0;
-    else { sj_measure<false>(c, dp.ham, L, kin, pot, O); e_old = kin + pot; }
+    else { sj_measure<false>(c, dp.ham, L, kin, pot); e_old = kin + pot; }
     sj_sweep_moves<MOLE_METROP_DIFFUSE>(c, L, dp.key, wid, dp.step, dp.tau_move, sd, inv2tau, dp.compat, nullptr, 0);
     sj_refresh(c, L);
-    sj_measure<false>(c, dp.ham, L, kin, pot, O);
+    sj_measure<false>(c, dp.ham, L, kin, pot);
     const double e_new = kin + pot;
     if (L.act && L.gl == 0) {
       const double wt = dp.w[w];
@@ -708,18 +777,7 @@ static inline cudaError_t sj_upload_tables() {
   cudaGetDevice(&dev);
   bool& done = done_dev[dev & 63];
   if (done) return cudaSuccess;
-  signed char pa[SJ_NPAIR], pb[SJ_NPAIR], ok[28], ol[28];
-  int p = 0;
-  for (int a = 0; a < 10; ++a)
-    for (int b = a + 1; b < 10; ++b, ++p) { pa[p] = (signed char)a; pb[p] = (signed char)b; }
-  int q = 0;
-  for (int k = 0; k < SJ_NP; ++k)
-    for (int l = k; l < SJ_NP; ++l, ++q) { ok[q] = (signed char)k; ol[q] = (signed char)l; }
   cudaError_t e;
-  if ((e = cudaMemcpyToSymbol(c_sj_pair_a, pa, sizeof(pa))) != cudaSuccess) return e;
-  if ((e = cudaMemcpyToSymbol(c_sj_pair_b, pb, sizeof(pb))) != cudaSuccess) return e;
-  if ((e = cudaMemcpyToSymbol(c_sj_oo_k, ok, sizeof(ok))) != cudaSuccess) return e;
-  if ((e = cudaMemcpyToSymbol(c_sj_oo_l, ol, sizeof(ol))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sj_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SJ_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sj_dmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SJ_SMEM_BYTES)) != cudaSuccess) return e;
 #define SJ_ATTR(M, O) \

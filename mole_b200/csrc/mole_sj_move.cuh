@@ -122,7 +122,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   double mt[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) mt[k] = isown ? ce[k] * inv_ratio : fma(-ce[k], vr, cg[k]);
-  double q, Gt[3];
+  double Gt[3];
   bool acc;
   if (METROP == MOLE_METROP_DIFFUSE) {
     // Frobenius norms over ALL electrons' drift (metrop.rs:182-193)
@@ -141,20 +141,30 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     const double sh = (ph[0] + ph[1]) + ph[2], sl = (pl[0] + pl[1]) + pl[2];
     if (L.wr) { mb[MB_RIN + 20 + L.gl] = sh; mb[MB_RIN + 25 + L.gl] = sl; }
     sj_sync();
-    // ---- D: exp(df), t_high and t_low: three chains together
+    // ---- D: acceptance A = t_high psi'^2 / (t_low psi^2) (metrop.rs:182-195) with psi'/psi = ratio exp(df),
+    // t = exp(-s/2tau).  In the regular range the three exponentials and the division are ONE exponential,
+    // A = ratio^2 exp(2 df + (s_low - s_high)/2tau): the same real number, |relative difference| ~1e-16.  Where the
+    // reference's t_high / t_low leave the normal range (walkers next to a node: denormal, 0, 0/0 = NaN) or
+    // exp(df) could overflow, the reference's own sequence of operations is evaluated instead (rare branch).
     const double* rh = mb + MB_RIN + 20;
     const double* rl = mb + MB_RIN + 25;
-    const double targ[3] = {df, -(((rh[0] + rh[1]) + (rh[2] + rh[3])) + rh[4]) * inv2tau,
-                            -(((rl[0] + rl[1]) + (rl[2] + rl[3])) + rl[4]) * inv2tau};
-    double tv[3];
-    m_exp_n<3>(targ, tv);
-    q = ratio * tv[0];                                             // psi'/psi
+    const double shs = (((rh[0] + rh[1]) + (rh[2] + rh[3])) + rh[4]) * inv2tau;   // -ln t_high
+    const double sls = (((rl[0] + rl[1]) + (rl[2] + rl[3])) + rl[4]) * inv2tau;   // -ln t_low
     const bool node = !(ratio > 0.0);                              // signum(psi') != signum(psi) or NaN, :178-180
-    const double A = sj_clamp_acceptance(tv[1] * (q * q) / tv[2], compat);   // :195
+    double A;
+    if (fmax(shs, sls) < 700.0 && fabs(df) < 300.0 && shs == shs && sls == sls) {
+      A = sj_clamp_acceptance((ratio * ratio) * m_exp(fma(2.0, df, sls - shs)), compat);
+    } else {
+      const double targ[3] = {df, -shs, -sls};
+      double tv[3];
+      m_exp_n<3>(targ, tv);
+      const double qq = ratio * tv[0];                             // psi'/psi
+      A = sj_clamp_acceptance(tv[1] * (qq * qq) / tv[2], compat);  // :195
+    }
     acc = !node && (A > u_acc);
   } else {
-    q = ratio * m_exp(df);
-    acc = sj_clamp_acceptance(q * q, compat) > u_acc;              // metrop.rs:80
+    const double qb = ratio * m_exp(df);
+    acc = sj_clamp_acceptance(qb * qb, compat) > u_acc;            // metrop.rs:80
   }
   if (acc) {
     if (isown) {
@@ -176,7 +186,8 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     }
 #pragma unroll
     for (int qq = 0; qq < 3; ++qq) { L.gf[0][qq] = gft[0][qq]; L.gf[1][qq] = gft[1][qq]; }
-    L.psi *= q;
+    L.psi *= ratio;                                                // psi = L.psi exp(L.fj), folded by sj_fold_psi
+    L.fj += df;
 #pragma unroll
     for (int t = 0; t < 2; ++t)
       if (pv[t] && L.act) {

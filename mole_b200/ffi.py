@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmole_b200.so")
+# MOLE_B200_LIB: a variant build of the same library (tools/ab_sj.py times several against each other)
+LIB_PATH = os.environ.get("MOLE_B200_LIB") or os.path.join(_HERE, "libmole_b200.so")
 
 # ---- status codes (include/mole_b200.h) ----
 OK = 0
