@@ -501,7 +501,8 @@ MOLE_D void sj_store(const SjLane& L, const SjConst& c, double* x, int64_t w, in
 }
 
 // one sweep: N_e single-electron moves, spin up then spin down (Sampler::move_state, samplers.rs:106-117)
-// returns the number of accepted moves (uniform over the group)
+// returns the number of accepted moves (uniform over the group); tr_accept is non-null only in the lane that
+// writes the trace (so that nothing about the walker's identity is tested per move)
 template <int METROP>
 MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid, uint32_t step, double param, double sd,
                           double inv2tau, uint32_t compat, uint8_t* tr_accept, size_t tr_stride) {
@@ -519,7 +520,7 @@ MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid,
     for (int el = 0; el < n; ++el) {
       const bool ok = sj_move<METROP>(c, L, el, d, param, sd, inv2tau, compat);
       n_acc += ok ? 1 : 0;
-      if (tr_accept && L.act && L.gl == 0) tr_accept[(size_t)(spin == 0 ? el : c.nup + el) * tr_stride] = ok ? 1 : 0;
+      if (tr_accept) tr_accept[(size_t)(spin == 0 ? el : c.nup + el) * tr_stride] = ok ? 1 : 0;
     }
     sj_swap_slots(L);
   }
@@ -604,7 +605,7 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
     for (int s = 0; s < sp.n_sweeps; ++s) {
       const uint32_t step = sp.step0 + (uint32_t)s;
       if (s > 0 && (s % SJ_REFRESH_EVERY) == 0) sj_refresh(c, L);
-      uint8_t* tra = sp.tr_accept ? sp.tr_accept + (size_t)s * ne * W + (w < W ? w : 0) : nullptr;
+      uint8_t* tra = (sp.tr_accept && L.act && L.gl == 0) ? sp.tr_accept + (size_t)s * ne * W + w : nullptr;   // lane 0 of a real walker
       const int n_acc = sj_sweep_moves<METROP>(c, L, sp.key, wid, step, sp.metrop_param, sd, inv2tau, sp.compat, tra, (size_t)W);
       if (L.act) {
         if (L.gl == 1) accv[1] += (double)n_acc;                      // ACC_NACC = 6 -> lane 1, idx 1

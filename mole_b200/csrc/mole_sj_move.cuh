@@ -179,7 +179,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     } else {
       sj_gradlnD(c, L.x[0], L.orb[0], mt, L.G[0]);
     }
-    if (L.act) {
+    if (L.wr) {                                                    // (a phantom group past W owns its slot too; testing
       double* mw = L.sm + SJ_OFF_MINV + spin * 25;
 #pragma unroll
       for (int k = 0; k < 5; ++k) mw[k * 5 + L.gl] = mt[k];
@@ -190,7 +190,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     L.fj += df;
 #pragma unroll
     for (int t = 0; t < 2; ++t)
-      if (pv[t] && L.act) {
+      if (pv[t] && L.wr) {                                           // w < W here would be re-derived for every move)
         double* pc = L.sm + SJ_OFF_PC + pid[t];
         pc[0] = pu[t]; pc[SJ_NPAIR] = pgr[t]; pc[2 * SJ_NPAIR] = plt[t]; pc[3 * SJ_NPAIR] = iv[1 + t]; pc[4 * SJ_NPAIR] = Rs[t];
       }

@@ -20,26 +20,25 @@ for l in lines[start + 1:]:
     if m:
         seq.append((m.group(2), tuple(chain))); fresh = True
 assert len(seq) == len(data), (len(seq), len(data))
+import os
+SJ = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'mole_b200', 'csrc', 'mole_sj.cuh')
+# line -> enclosing function of mole_sj.cuh, derived from the source (MOLE_D / __global__ / static inline definitions)
+FN = [(0, 'hdr')]
+for i, l in enumerate(open(SJ), 1):
+    m = re.match(r'^(?:template.*>\s*)?(?:MOLE_D|__global__|__device__ __forceinline__|static inline)\b.*?\b(\w+)\(', l)
+    if m and not l.startswith(' '): FN.append((i, m.group(1)))
+def fn_of(ln): return [n for a, n in FN if a <= ln][-1]
+PHASE = ('sj_measure', 'sj_refresh', 'sj_refresh_slot', 'sj_init', 'sj_invert', 'sj_swap_slots', 'sj_fold_psi')
 def classify(ch):
     files = [f for f, _ in ch]
     if 'mole_rng.cuh' in files: return 'rng'
-    # outermost frame within mole_sj_move.cuh / mole_sj.cuh
-    for f, ln in reversed(ch):
-        if f == 'mole_sj_move.cuh':
-            return 'move:%03d' % (ln // 10 * 10)
-    FN=[(0,'hdr'),(91,'gsum'),(104,'pair'),(122,'phi'),(132,'gradlnD'),(140,'radial'),(150,'invert'),(198,'refresh_slot'),(222,'refresh'),(232,'init'),(271,'swap'),(287,'movev2'),(457,'measure'),(539,'const/setup/load/store'),(586,'sweep_moves'),(611,'evalk'),(649,'sweepk')]
-    outer=None
-    for f, ln in reversed(ch):
-        if f == 'mole_sj.cuh':
-            if ln >= 649:    # kernel frame: look for the callee frame
-                continue
-            name=[n for a,n in FN if a<=ln][-1]
-            if name in ('measure','refresh','refresh_slot','init','invert','swap','sweep_moves'):
-                return 'sj:'+name+(':%03d'%(ln//10*10) if name=='measure' else '')
-            outer = outer or name
-    if outer: return 'sj:'+outer
-    for f, ln in reversed(ch):
-        if f == 'mole_sj.cuh': return 'sjk:%04d' % (ln // 10 * 10)
+    for f, ln in reversed(ch):                       # outermost frame within mole_sj_move.cuh
+        if f == 'mole_sj_move.cuh': return 'move:%03d' % (ln // 10 * 10)
+    names = [fn_of(ln) for f, ln in ch if f == 'mole_sj.cuh']
+    for n in PHASE:
+        if n in names: return n
+    if 'sj_sweep_moves' in names: return 'sj_sweep_moves (loop, draws)'
+    if names: return names[-1]
     return files[-1] if files else '?'
 cnt = collections.Counter(); smp = collections.Counter(); tot = 0; ts = 0
 mathc = collections.Counter()
@@ -50,4 +49,4 @@ for (t, ch), r in zip(seq, data):
 print("total warp-instr %d samples %d" % (tot, ts))
 for k in sorted(cnt):
     if cnt[k] * 1000 > tot or smp[k] * 1000 > ts:
-        print("%-12s instr %5.1f%%  samples %5.1f%%  (math.cuh share of this bucket %4.1f%%)" % (k, 100 * cnt[k] / tot, 100 * smp[k] / ts, 100 * mathc[k] / max(cnt[k], 1)))
+        print("%-30s instr %5.1f%%  samples %5.1f%%  (math.cuh share of this bucket %4.1f%%)" % (k, 100 * cnt[k] / tot, 100 * smp[k] / ts, 100 * mathc[k] / max(cnt[k], 1)))
