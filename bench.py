@@ -270,7 +270,7 @@ def main():
                      "frac_of_nominal": achieved / nominal, "f_alg_per_walker_step": f_alg,
                      "kernel_ms_per_launch": kms, "kernel_walker_steps_per_s_per_gpu": kernel_rate,
                      "frac_from_scratch_count": kernel_rate * FLOPS["ne_slater_jastrow_vmc_sr"]["f_from_scratch_per_walker_step"] / 1e12 / fp64_peak,
-                     # NOT measured in this run: ncu counters of the same launch (profiles/r01_sj_sweep_v5_*), for context
+                     # NOT measured in this run: ncu counters of the same launch (profiles/r01b_sj_sweep_v8_*), for context
                      "ncu_reference": FLOPS["ne_slater_jastrow_vmc_sr"].get("ncu_executed_fp64")},
         "e2e": {"value": value_e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": W * 30 * 8 * world,
                 "d2h_bytes_per_step": 62 * 8 * world, "ms_per_step": ms_e2e / args.steps},

@@ -141,25 +141,27 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     const double sh = (ph[0] + ph[1]) + ph[2], sl = (pl[0] + pl[1]) + pl[2];
     if (L.wr) { mb[MB_RIN + 20 + L.gl] = sh; mb[MB_RIN + 25 + L.gl] = sl; }
     sj_sync();
-    // ---- D: acceptance A = t_high psi'^2 / (t_low psi^2) (metrop.rs:182-195) with psi'/psi = ratio exp(df),
-    // t = exp(-s/2tau).  In the regular range the three exponentials and the division are ONE exponential,
-    // A = ratio^2 exp(2 df + (s_low - s_high)/2tau): the same real number, |relative difference| ~1e-16.  Where the
-    // reference's t_high / t_low leave the normal range (walkers next to a node: denormal, 0, 0/0 = NaN) or
-    // exp(df) could overflow, the reference's own sequence of operations is evaluated instead (rare branch).
+    // ---- D: acceptance A = (t_high psi'^2) / (t_low psi^2) (metrop.rs:182-195), t = exp(-s/2tau),
+    // psi' = psi ratio exp(df).  Where none of the reference's intermediate products can leave the normal
+    // range (bounds below: t >= e^-200, psi^2 and psi'^2 within 1e-207 .. 1e207) the three exponentials and the
+    // division are ONE exponential, A = ratio^2 exp(2 df + (s_low - s_high)/2tau): the same real number,
+    // relative difference ~1e-16.  Everywhere else (walkers next to a node: t denormal or 0, t psi^2
+    // underflowing, 0/0 = NaN) the reference's own sequence of operations on the absolute psi is evaluated.
     const double* rh = mb + MB_RIN + 20;
     const double* rl = mb + MB_RIN + 25;
     const double shs = (((rh[0] + rh[1]) + (rh[2] + rh[3])) + rh[4]) * inv2tau;   // -ln t_high
     const double sls = (((rl[0] + rl[1]) + (rl[2] + rl[3])) + rl[4]) * inv2tau;   // -ln t_low
     const bool node = !(ratio > 0.0);                              // signum(psi') != signum(psi) or NaN, :178-180
+    const double r2 = ratio * ratio, ap = fabs(L.psi);
     double A;
-    if (fmax(shs, sls) < 700.0 && fabs(df) < 300.0 && shs == shs && sls == sls) {
-      A = sj_clamp_acceptance((ratio * ratio) * m_exp(fma(2.0, df, sls - shs)), compat);
+    if (fmax(shs, sls) < 200.0 && fabs(df) < 50.0 && fabs(L.fj) < 50.0 && ap > 1e-40 && ap < 1e40 && r2 > 1e-40 && r2 < 1e40) {
+      A = sj_clamp_acceptance(r2 * m_exp(fma(2.0, df, sls - shs)), compat);
     } else {
-      const double targ[3] = {df, -shs, -sls};
-      double tv[3];
-      m_exp_n<3>(targ, tv);
-      const double qq = ratio * tv[0];                             // psi'/psi
-      A = sj_clamp_acceptance(tv[1] * (qq * qq) / tv[2], compat);  // :195
+      const double targ[4] = {df, -shs, -sls, L.fj};
+      double tv[4];
+      m_exp_n<4>(targ, tv);
+      const double psi_old = L.psi * tv[3], psi_new = psi_old * (ratio * tv[0]);
+      A = sj_clamp_acceptance((tv[1] * (psi_new * psi_new)) / (tv[2] * (psi_old * psi_old)), compat);   // :195
     }
     acc = !node && (A > u_acc);
   } else {
