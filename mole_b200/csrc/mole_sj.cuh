@@ -645,14 +645,23 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
           for (int k = 0; k < SJ_NP; ++k) sp.tr_pgrad[((size_t)si * SJ_NP + k) * W + w] = L.psi * os[k];   // d_k psi, or 1/d_k psi under the quirk
         }
         if (L.act) {
+          // all loads first: the nine read-modify-writes would otherwise serialise (the compiler cannot tell that
+          // the stores to am[] do not alias the os[] loads of the next entry)
           double* am = L.sm + SJ_OFF_ACC;
+          double fa[9], fb[9], fm[9];
 #pragma unroll
           for (int i = 0; i < 9; ++i) {
             const int j = L.gl + 5 * i;
-            if (i < 8 || j < SJ_NMOM) {
-              const unsigned id = s_sj_mom[j];
-              am[j] = fma(os[id >> 4], os[id & 15], am[j]);
-            }
+            const int jj = (i < 8 || j < SJ_NMOM) ? j : L.gl;      // entries 42, 43 do not exist (lanes 2..4, i = 8)
+            const unsigned id = s_sj_mom[jj];
+            fa[i] = os[id >> 4]; fb[i] = os[id & 15]; fm[i] = am[jj];
+          }
+#pragma unroll
+          for (int i = 0; i < 9; ++i) fm[i] = fma(fa[i], fb[i], fm[i]);
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const int j = L.gl + 5 * i;
+            if (i < 8 || j < SJ_NMOM) am[j] = fm[i];
           }
         }
         sj_sync();
