@@ -129,14 +129,15 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], mt, Gt);
     const double* const G1 = L.G[1];
     double ph[3], pl[3];                                           // per-component partial sums: short chains
-    const double m0 = L.val[0] ? 1.0 : 0.0, m1 = L.val[1] ? 1.0 : 0.0;
+    // absent electrons (slot validity) drop out through a zero time step: their drift is finite, their dx is 0
+    const double tau0 = L.val[0] ? param : 0.0, tau1 = L.val[1] ? param : 0.0;
 #pragma unroll
     for (int qq = 0; qq < 3; ++qq) {
       const double dx = isown ? xo[qq] - xn[qq] : 0.0;
-      const double a0 = dx - (Gt[qq] + gft[0][qq]) * param, b0 = -dx - (Gown[qq] + L.gf[0][qq]) * param;
-      const double a1 = (G1[qq] + gft[1][qq]) * param, b1 = (G1[qq] + L.gf[1][qq]) * param;
-      ph[qq] = fma(m0 * a0, a0, (m1 * a1) * a1);
-      pl[qq] = fma(m0 * b0, b0, (m1 * b1) * b1);
+      const double a0 = dx - (Gt[qq] + gft[0][qq]) * tau0, b0 = -dx - (Gown[qq] + L.gf[0][qq]) * tau0;
+      const double a1 = (G1[qq] + gft[1][qq]) * tau1, b1 = (G1[qq] + L.gf[1][qq]) * tau1;
+      ph[qq] = fma(a0, a0, a1 * a1);
+      pl[qq] = fma(b0, b0, b1 * b1);
     }
     const double sh = (ph[0] + ph[1]) + ph[2], sl = (pl[0] + pl[1]) + pl[2];
     if (L.wr) { mb[MB_RIN + 20 + L.gl] = sh; mb[MB_RIN + 25 + L.gl] = sl; }
