@@ -136,11 +136,22 @@ MOLE_D bool mole_move_state(const WfParams& p, Walker<WF>& wk, int e, double par
       sl = fma(b, b, sl);
     }
     const double i2t = 0.5 / param;
-    const double targ[2] = {-sh * i2t, -sl * i2t};
-    double tv[2];
-    m_exp_n<2, true>(targ, tv);                                  // t_high, t_low as two interleaved chains
-    const double th = tv[0], tl = tv[1];
-    const double A = mole_clamp_acceptance(th * (pn * pn) / (tl * (wk.psi * wk.psi)), compat);     // :195
+    const double shs = sh * i2t, sls = sl * i2t;                 // -ln t_high, -ln t_low
+    const double ao = fabs(wk.psi), an = fabs(pn);
+    double A;
+    if (fmax(shs, sls) < 200.0 && ao > 1e-40 && ao < 1e40 && an > 1e-40 && an < 1e40) {
+      // none of the reference's intermediate products (t >= e^-200, psi^2 within 1e-80 .. 1e80) can leave the normal
+      // range: (t_high psi'^2) / (t_low psi^2) = (psi'/psi)^2 exp((s_low - s_high)/2tau), one exponential and no
+      // division, the same real number to ~1e-16
+      const double q = pn * inv_o;
+      A = mole_clamp_acceptance((q * q) * m_exp(sls - shs), compat);
+    } else {
+      // next to a node (t denormal or 0, t psi^2 underflowing, 0/0): the reference's own sequence of operations
+      const double targ[2] = {-shs, -sls};
+      double tv[2];
+      m_exp_n<2, true>(targ, tv);
+      A = mole_clamp_acceptance(tv[0] * (pn * pn) / (tv[1] * (wk.psi * wk.psi)), compat);           // :195
+    }
     if (A > d.u) {
       wk.st = tr;
       wk.psi = pn;

@@ -8,6 +8,37 @@ import os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def one_small(kind, reps):
+    """the thread-per-walker kinds at 2^20 walkers x 200 sweeps (H2 Heitler-London + SR, He, Gaussian / H atom)"""
+    sys.path.insert(0, ROOT)
+    import mole_b200 as m
+    ctx = m.default_context()
+    SEED = bytes(32)
+    W, NS = 1 << 20, 200
+    if kind == "h2":
+        wf, op, ne, tau = m.HydrogenMoleculeWaveFunction(1.4, [0.5]), m.ElectronicHamiltonian.from_ions([[-0.7, 0, 0], [0.7, 0, 0]], [1, 1]), 2, 0.25
+    elif kind == "he":
+        wf, op, ne, tau = m.HeliumAtomWaveFunction(1.69), m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [2]), 2, 0.1
+    else:
+        wf, op, ne, tau = m.GaussianWaveFunction(1.0), m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1]), 1, 0.025
+    ens = m.Ensemble(W, ne, SEED); ens.init_uniform()
+    met = m.MetropolisDiffuse(tau, SEED)
+    obs = m.ffi.OBS_ENERGY | m.ffi.OBS_PGRAD | m.ffi.OBS_WFVALUE
+    ens.sweep(wf, met, op, n_sweeps=20, block_size=10, observables=obs)
+    ctx.synchronize()
+    ts = []
+    for _ in range(reps):
+        ens.acc_reset(); ctx.synchronize()
+        t0 = time.perf_counter()
+        ens.sweep(wf, met, op, n_sweeps=NS, n_discard=10, block_size=10, observables=obs)
+        ctx.synchronize()
+        ts.append(1e3 * (time.perf_counter() - t0))
+    e, de, acc, g = m.acc_finalize(ens.acc_get())
+    print("%-28s %-6s ms/launch %s  best %.2f  = %.3e walker-steps/s  E %.10f acc %.6f" % (
+        os.path.basename(os.environ.get("MOLE_B200_LIB", "default")), kind, " ".join("%.2f" % t for t in ts), min(ts),
+        W * NS / (min(ts) * 1e-3), e, acc), flush=True)
+
+
 def one(W, NS, reps):
     sys.path.insert(0, ROOT)
     import mole_b200 as m
@@ -41,6 +72,13 @@ def one(W, NS, reps):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         one(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--one-small":
+        one_small(sys.argv[2], int(sys.argv[3]))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--small":          # python tools/ab_sj.py --small lib1.so lib2.so
+        for kind in ("h2", "he", "gauss"):
+            for lib in [a for a in sys.argv[2:] if a.endswith(".so")]:
+                env = dict(os.environ, MOLE_B200_LIB=os.path.abspath(lib))
+                subprocess.run([sys.executable, os.path.abspath(__file__), "--one-small", kind, "3"], env=env, timeout=300)
     else:
         libs = [a for a in sys.argv[1:] if a.endswith(".so")]
         nums = [int(a) for a in sys.argv[1:] if a.isdigit()]
