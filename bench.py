@@ -132,6 +132,9 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # NCCL_DEBUG=VERSION makes NCCL print its version banner on stdout, ahead of the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     import mole_b200 as m
@@ -292,6 +295,7 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        del ens                                                     # before its context (the library also defers the free)
         ctx.close()
         dist.destroy_process_group()
 

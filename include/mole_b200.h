@@ -51,6 +51,7 @@ typedef struct mole_opt_s* mole_opt_t;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int32_t mole_ctx_create(int32_t device, mole_ctx_t* ctx);
+/* A context destroyed while ensembles created on it are alive is freed with the last of them. */
 int32_t mole_ctx_destroy(mole_ctx_t ctx);
 int32_t mole_ctx_synchronize(mole_ctx_t ctx);
 const char* mole_last_error_string(mole_ctx_t ctx); /* ctx may be NULL: last global error */

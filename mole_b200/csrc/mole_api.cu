@@ -71,11 +71,16 @@ int32_t mole_ctx_create(int32_t device, mole_ctx_t* out) {
   return MOLE_OK;
 }
 
-int32_t mole_ctx_destroy(mole_ctx_t ctx) {
-  if (!ctx) return MOLE_OK;
+static void ctx_free(mole_ctx_s* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(STREAM(ctx));
   delete ctx;
+}
+
+int32_t mole_ctx_destroy(mole_ctx_t ctx) {
+  if (!ctx) return MOLE_OK;
+  if (ctx->live_ens > 0) { ctx->closing = true; return MOLE_OK; }   // freed by the last mole_ensemble_destroy
+  ctx_free(ctx);
   return MOLE_OK;
 }
 
@@ -213,6 +218,7 @@ int32_t mole_ensemble_create(mole_ctx_t ctx, int64_t W, int32_t ne, const uint8_
   CU(ctx, cudaMemsetAsync(e->ticket, 0, 2 * sizeof(unsigned int), STREAM(ctx)));
   fill_kernel<<<cdiv(W, 256), 256, 0, STREAM(ctx)>>>(e->w, W, 1.0);   // dmc.rs:51 initial weight 1.0
   KERNEL_CHECK(ctx);
+  ++ctx->live_ens;
   *out = e;
   return MOLE_OK;
 }
@@ -226,7 +232,9 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
   cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath);
   cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen); cudaFree(e->sb_draws);
+  mole_ctx_s* ctx = e->ctx;
   delete e;
+  if (--ctx->live_ens == 0 && ctx->closing) ctx_free(ctx);
   return MOLE_OK;
 }
 

@@ -84,6 +84,10 @@ struct mole_ctx_s {
   void* nccl_comm = nullptr;
   double* comm_scratch = nullptr;  // device, 16 doubles
   int nranks = 1, rank = 0;
+  // ensembles keep a pointer to their context: a context destroyed while ensembles are alive is only marked and
+  // is freed with the last of them (bindings with garbage-collected wrappers destroy in arbitrary order)
+  int live_ens = 0;
+  bool closing = false;
 };
 
 struct mole_wf_s { mole_ctx_s* ctx; WfParams p; };

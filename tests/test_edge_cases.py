@@ -136,3 +136,18 @@ def test_slater_jastrow_accept_test_next_to_a_node(mole, orc, name, nan_accept):
     # accepted NaN moves carry drifts ~ 1/d ~ 1e4..1e7 whose rounding (condition number of the Slater matrix ~ 1/d)
     # lands in the positions: 1e-9 holds under the default policy, where such moves are rejected
     assert np.allclose(fin[ok], rfin[ok], rtol=1e-5 if nan_accept else 1e-9, atol=1e-12)
+
+
+def test_context_closed_before_its_ensembles(mole):
+    """Garbage-collected bindings destroy objects in arbitrary order: a context closed while ensembles are alive
+    is freed with the last of them (mole_ctx_destroy), never under them."""
+    ctx = mole.Context(0)
+    wf = mole.GaussianWaveFunction(1.0, ctx=ctx)
+    op = mole.HarmonicHamiltonian(1.0, ctx=ctx)
+    a = mole.Ensemble(64, 1, SEED0, ctx=ctx)
+    b = mole.Ensemble(32, 1, SEED0, ctx=ctx)
+    a.init_uniform()
+    a.sweep(wf, mole.MetropolisBox(1.0, SEED0), op, n_sweeps=4, observables=0)
+    ctx.close()
+    del a          # synchronises the (still valid) stream of the closed context
+    del b          # frees the context
