@@ -145,7 +145,7 @@ MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   o.R = (1.0 - E) * c.ikappa;
   const double iden = m_rcp(fma(c.b2, o.R, 1.0));
   const double R2 = o.R * o.R;
-  o.u = fma(c.b1 * o.R, iden, fma(c.b4 * R2, o.R, c.b3 * R2));
+  o.u = fma(R2, fma(c.b4, o.R, c.b3), (c.b1 * o.R) * iden);
   const double id2 = iden * iden;
   const double du = fma(c.b1, id2, fma(3.0 * c.b4, R2, 2.0 * c.b3 * o.R));
   const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden, fma(6.0 * c.b4, o.R, 2.0 * c.b3));

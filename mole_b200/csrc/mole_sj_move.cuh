@@ -19,7 +19,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   // this lane's column (cg) and the moved electron's column (ce) of the inverse
   double cg[5], ce[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) { cg[k] = minv[k * 5 + L.gl]; ce[k] = minv[k * 5 + el]; }
+  for (int k = 0; k < 5; ++k) { cg[k] = isown ? 0.0 : minv[k * 5 + L.gl]; ce[k] = minv[k * 5 + el]; }   // owner: see the column update
   // grad ln D of the own electrons is carried in L.G (rebuilt by sj_refresh, updated on accepted moves)
   const double* const Gown = L.G[0];
   // ---- A: the owner proposes, everybody reads the trial point
@@ -71,7 +71,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const double R2 = Rs[t] * Rs[t], id2 = iden[t] * iden[t], E = ev[1 + t];
-    pu[t] = fma(c.b1 * Rs[t], iden[t], fma(c.b4 * R2, Rs[t], c.b3 * R2));
+    pu[t] = fma(R2, fma(c.b4, Rs[t], c.b3), (c.b1 * Rs[t]) * iden[t]);
     const double du = fma(c.b1, id2, fma(3.0 * c.b4, R2, 2.0 * c.b3 * Rs[t]));
     const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden[t], fma(6.0 * c.b4, Rs[t], 2.0 * c.b3));
     const double g = E * du;
@@ -79,16 +79,18 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     plt[t] = fma(2.0, pgr[t], fma(E * E, d2u, -c.kappa * g));   // div(rhat g) = 2 g/r + dg/dr
   }
   double dfl = 0.0, ge[3] = {0.0, 0.0, 0.0}, gft[2][3];
+  const double dmv[3] = {xn[0] - xo[0], xn[1] - xo[1], xn[2] - xo[2]};
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const double u_old = L.sm[SJ_OFF_PC + pid[t]], gr_old = L.sm[SJ_OFF_PC + SJ_NPAIR + pid[t]];
     const double m = pv[t] ? 1.0 : 0.0;
     dfl = fma(m, pu[t] - u_old, dfl);
-    const double gn_ = m * pgr[t], go_ = m * gr_old;
+    const double gn_ = m * pgr[t], go_ = m * gr_old, gd_ = go_ - gn_;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      // grad_b f changes by the (b,e) term: -(x_e - x_b) g/r
-      gft[t][q] = L.gf[t][q] + go_ * (xo[q] - L.x[t][q]) - gn_ * dn[t][q];
+      // grad_b f changes by the (b,e) term -(x_e - x_b) g/r: old term back in, new term out, with
+      // x_e - x_b = dn - (x' - x) at the old point: gf + go (dn - dmove) - gn dn = gf + (go - gn) dn - go dmove
+      gft[t][q] = fma(-go_, dmv[q], fma(gd_, dn[t][q], L.gf[t][q]));
       ge[q] = fma(gn_, dn[t][q], ge[q]);
     }
   }
@@ -118,10 +120,12 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   const double v = fma(phin[2], cg[2], fma(phin[1], cg[1], phin[0] * cg[0])) + fma(phin[4], cg[4], phin[3] * cg[3]);
   const double ratio = fma(phin[2], ce[2], fma(phin[1], ce[1], phin[0] * ce[0])) + fma(phin[4], ce[4], phin[3] * ce[3]);
   const double inv_ratio = m_rcp(ratio);
-  const double vr = v * inv_ratio;
+  // Sherman-Morrison column as ONE fma for every lane: the moved electron's own column is ce / ratio = 0 - ce (-1/ratio)
+  // (its cg was loaded as zeros), the others are cg - ce (v / ratio)
+  const double vr = isown ? -inv_ratio : v * inv_ratio;
   double mt[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) mt[k] = isown ? ce[k] * inv_ratio : fma(-ce[k], vr, cg[k]);
+  for (int k = 0; k < 5; ++k) mt[k] = fma(-ce[k], vr, cg[k]);
   double Gt[3];
   bool acc;
   if (METROP == MOLE_METROP_DIFFUSE) {
