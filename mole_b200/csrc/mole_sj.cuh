@@ -3,11 +3,11 @@
 //   f_ee = sum_{i<j} u(R_ij), u(R) = b1 R/(1+b2 R) + b3 R^2 + b4 R^3, R = (1-exp(-kappa r))/kappa
 //   (theory/jastrow.tex:23-31 with the erratum of SURVEY.md §8(c)).
 //
-// Layout (v2): FIVE lanes cooperate on one walker, six walkers per warp (lanes 30/31 idle).  Lane gl
+// Layout: FIVE lanes cooperate on one walker, six walkers per warp (lanes 30/31 idle).  Lane gl
 // owns one electron of each spin.  Registers hold the positions, the radial cache (r, 1/r and the three
 // orbital exponentials) and grad f of the two own electrons; shared memory holds, per walker, the pair
 // cache (u, g/r, laplacian term, 1/r, R for the 45 pairs), both inverse Slater matrices, a copy of
-// the positions and a mailbox for the intra-walker exchanges.  The spin being moved always sits in
+// the positions, a mailbox for the intra-walker exchanges and the 42 optimisation moments.  The spin being moved always sits in
 // register slot 0 (the slots are swapped between the two halves of a sweep), so there is one copy of
 // the move code.  A single-electron move re-evaluates only what changed: one orbital row, a
 // Sherman-Morrison update of one 5x5 inverse (rebuilt from scratch every SJ_REFRESH_EVERY sweeps), nine

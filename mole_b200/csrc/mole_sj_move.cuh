@@ -1,10 +1,12 @@
 // Metropolis::move_state for one electron of the Slater-Jastrow kind (included from mole_sj.cuh).
 //
-// v3: the three independent transcendental chains of a move (orbital radial part and the two Jastrow
-// pairs of each lane) go through the batched, stage-major math of mole_math.cuh, the exp(df) /
-// 1/ratio and t_high / t_low chains are paired the same way, and every lane sums the mailbox rows
-// itself (four warp syncs per move instead of six).  Semantics: src/metropolis/src/metrop.rs:60-96
-// (box) and :150-212 (diffusion), Frobenius norms over ALL electrons' drift.
+// The three independent transcendental chains of a move (orbital radial part and the two Jastrow pairs
+// of each lane) go through the batched, stage-major math of mole_math.cuh and every lane sums the
+// mailbox rows itself (four warp syncs per move: proposal, pair/orbital exchange, drift norms, commit).
+// The kernel is bound by the FP64 pipe plus exposed dependency latency: what counts
+// here is the number of FP64 instructions and the length of dependent chains, not integer work or syncs.
+// Semantics: src/metropolis/src/metrop.rs:60-96 (box) and :150-212 (diffusion), Frobenius norms over
+// ALL electrons' drift; the accept test is documented at phase D.
 #pragma once
 
 template <int METROP>
