@@ -72,7 +72,15 @@ enum {
   MOLE_WF_H2P_PRODUCT = 4,    /* tests/hydrogen_molecular_ion_lcao.rs:51-98 geom: [R], params[0]=alpha, P=0 */
   MOLE_WF_SLATER_JASTROW = 5, /* SURVEY.md §8(c) config 5 + theory/jastrow.tex; geom: [kappa,n_up,n_dn];
                                  params: zeta1,zeta2,zeta3,b1,b2,b3,b4 (P=7) */
-  MOLE_WF_CONSTANT = 6        /* src/metropolis/src/metrop.rs:225-255 WaveFunctionMock; geom: [value] */
+  MOLE_WF_CONSTANT = 6,       /* src/metropolis/src/metrop.rs:225-255 WaveFunctionMock; geom: [value] */
+  /* LCAO determinants over a hydrogen-1s basis chi_c(r) = exp(-|r - R_c| / width): the Hydrogen1sBasis / Orbital /
+     SingleDeterminant / SpinDeterminantProduct API that tests/helium_lcao.rs:94-101 and
+     tests/hydrogen_molecular_ion_lcao.rs:103-107 name (commented out upstream).  geom: [mode, 1/width, R_0 (3), R_1 (3)];
+     params: orbital coefficients C[k][c] at k * n_centres + c, all variational.  mode 0: spin product
+     phi_0(x_0) phi_1(x_1) (SpinDeterminantProduct, n_up = 1); mode 1: 2x2 determinant (SingleDeterminant). */
+  MOLE_WF_LCAO_1E_2C = 7,     /* one electron, two centres (H2+):   psi = phi_0(x_0)             P=2 */
+  MOLE_WF_LCAO_2E_1C = 8,     /* two electrons, one centre (He):    two orbitals                 P=2 */
+  MOLE_WF_LCAO_2E_2C = 9      /* two electrons, two centres (H2 MO): two orbitals                P=4 */
 };
 #define MOLE_WF_MAX_PARAMS 8
 #define MOLE_WF_MAX_GEOM 8

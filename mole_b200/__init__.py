@@ -6,7 +6,8 @@ the reference's trait surface.  No CPU fallback exists.
 """
 from . import ffi
 from .ffi import MoleError
-from .api import (Context, default_context, comm_unique_id, derive_seed, WaveFunction, STO, GaussianWaveFunction,
+from .api import (Context, default_context, comm_unique_id, derive_seed, WaveFunction, STO, GaussianWaveFunction, Hydrogen1sBasis, Orbital, SingleDeterminant,
+                  SpinDeterminantProduct,
                   HeliumAtomWaveFunction, HydrogenMoleculeWaveFunction, H2WF, SlaterJastrow, WaveFunctionMock,
                   LocalOperator, KineticEnergy, IonicPotential, ElectronicPotential, IonicHamiltonian,
                   ElectronicHamiltonian, HarmonicHamiltonian, ParameterGradient, WavefunctionValue, operators,

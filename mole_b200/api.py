@@ -234,6 +234,67 @@ class H2WF(WaveFunction):
         return False
 
 
+# ---- LCAO determinants over a hydrogen-1s basis: the API the reference's tests name (commented out upstream:
+# tests/helium_lcao.rs:94-101, tests/hydrogen_molecular_ion_lcao.rs:103-107), SURVEY.md 8(f) row 3
+class Hydrogen1sBasis:
+    """Hydrogen1sBasis::new(ion_pos, widths): one function exp(-|r - R_c| / width) per centre.
+    The device kinds take one width and one or two centres (closed set, like every other kind)."""
+
+    def __init__(self, ion_pos, widths):
+        self.ion_pos = np.asarray(ion_pos, dtype=np.float64).reshape(-1, 3)
+        self.widths = [float(w) for w in widths]
+        if len(self.widths) != 1 or not 1 <= len(self.ion_pos) <= 2:
+            raise MoleError(ffi.ERR_SHAPE, "Hydrogen1sBasis on the device: one width, one or two centres")
+
+    def clone(self):
+        return self
+
+
+class Orbital:
+    """Orbital::new(coefficients (n_centres x n_widths), basis): phi(r) = sum_c C[c][0] chi_c(r)."""
+
+    def __init__(self, coefficients, basis):
+        self.basis = basis
+        self.coefficients = np.asarray(coefficients, dtype=np.float64).reshape(-1)
+        if self.coefficients.size != len(basis.ion_pos):
+            raise MoleError(ffi.ERR_SHAPE, "Orbital: one coefficient per (centre, width)")
+
+
+class _LcaoWaveFunction(WaveFunction):
+    def __init__(self, orbitals, n_elec, mode, ctx=None):
+        basis = orbitals[0].basis
+        if any(o.basis is not basis and (o.basis.widths != basis.widths or not np.array_equal(o.basis.ion_pos, basis.ion_pos))
+               for o in orbitals):
+            raise MoleError(ffi.ERR_SHAPE, "all orbitals must share one basis")
+        nc = len(basis.ion_pos)
+        kind = {(1, 2): ffi.WF_LCAO_1E_2C, (2, 1): ffi.WF_LCAO_2E_1C, (2, 2): ffi.WF_LCAO_2E_2C}.get((n_elec, nc))
+        if kind is None or len(orbitals) != n_elec:
+            raise MoleError(ffi.ERR_SHAPE, "LCAO on the device: (electrons, centres) in {(1, 2), (2, 1), (2, 2)}, one orbital per electron")
+        self.KIND = kind
+        pos = np.zeros(6)
+        pos[:3 * nc] = basis.ion_pos.reshape(-1)
+        coeff = np.concatenate([o.coefficients for o in orbitals])
+        super().__init__(list(coeff), [float(mode), 1.0 / basis.widths[0]] + list(pos), n_elec=n_elec, ctx=ctx)
+
+
+class SingleDeterminant(_LcaoWaveFunction):
+    """SingleDeterminant::new(orbitals): det[phi_k(x_i)], all electrons of one spin
+    (tests/hydrogen_molecular_ion_lcao.rs:107)."""
+
+    def __init__(self, orbitals, ctx=None):
+        super().__init__(orbitals, len(orbitals), 1 if len(orbitals) == 2 else 0, ctx=ctx)
+
+
+class SpinDeterminantProduct(_LcaoWaveFunction):
+    """SpinDeterminantProduct::new(orbitals, n_up): det_up * det_dn (tests/helium_lcao.rs:101); on the device
+    two electrons with n_up = 1: psi = phi_0(x_0) phi_1(x_1)."""
+
+    def __init__(self, orbitals, n_up, ctx=None):
+        if len(orbitals) != 2 or n_up != 1:
+            raise MoleError(ffi.ERR_SHAPE, "SpinDeterminantProduct on the device: two orbitals, n_up = 1")
+        super().__init__(orbitals, 2, 0, ctx=ctx)
+
+
 class SlaterJastrow(WaveFunction):
     """det_up * det_dn * exp(f_ee) over STO 1s/2s/2p orbitals with the Pade+polynomial Jastrow of
     theory/jastrow.tex (SURVEY.md §8(c) synthetic config 5).  params = (zeta1,zeta2,zeta3,b1,b2,b3,b4)."""

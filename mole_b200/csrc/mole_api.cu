@@ -13,7 +13,9 @@
 #include "mole_sj.cuh"
 #include "mole_stats.cuh"
 
-static std::string g_last_error;
+// errors raised without a context (NULL handles, mole_ctx_create); per thread, because different contexts may be
+// driven from different threads (include/mole_b200.h)
+static thread_local std::string g_last_error;
 
 int mole_set_error(mole_ctx_s* ctx, int code, const std::string& msg) {
   if (ctx) ctx->last_error = msg;
@@ -61,11 +63,11 @@ int32_t mole_ctx_create(int32_t device, mole_ctx_t* out) {
   if (prop.major != 10)
     return mole_set_error(nullptr, MOLE_ERR_NO_DEVICE,
                           "device is not sm_100 (B200): this library ships sm_100a code only");
+  cudaStream_t s;
+  CU(nullptr, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   mole_ctx_s* c = new mole_ctx_s();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  cudaStream_t s;
-  CU(nullptr, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   c->stream = (void*)s;
   *out = c;
   return MOLE_OK;
@@ -106,8 +108,8 @@ int32_t mole_ctx_launch_count(mole_ctx_t ctx, int64_t* n) {
 // ------------------------------------------------------------------ wavefunction descriptors
 static int wf_kind_ne(const mole_wf_desc* d) {
   switch (d->kind) {
-    case MOLE_WF_STO_1S: case MOLE_WF_GAUSSIAN: case MOLE_WF_H2P_PRODUCT: case MOLE_WF_CONSTANT: return 1;
-    case MOLE_WF_STO_PRODUCT: case MOLE_WF_H2_HL_STO: return 2;
+    case MOLE_WF_STO_1S: case MOLE_WF_GAUSSIAN: case MOLE_WF_H2P_PRODUCT: case MOLE_WF_CONSTANT: case MOLE_WF_LCAO_1E_2C: return 1;
+    case MOLE_WF_STO_PRODUCT: case MOLE_WF_H2_HL_STO: case MOLE_WF_LCAO_2E_1C: case MOLE_WF_LCAO_2E_2C: return 2;
     case MOLE_WF_SLATER_JASTROW: return (int)d->geom[1] + (int)d->geom[2];
   }
   return -1;
@@ -117,6 +119,8 @@ static int wf_kind_np(int kind) {
     case MOLE_WF_STO_1S: case MOLE_WF_GAUSSIAN: case MOLE_WF_STO_PRODUCT: case MOLE_WF_H2_HL_STO: return 1;
     case MOLE_WF_H2P_PRODUCT: case MOLE_WF_CONSTANT: return 0;
     case MOLE_WF_SLATER_JASTROW: return 7;
+    case MOLE_WF_LCAO_1E_2C: case MOLE_WF_LCAO_2E_1C: return 2;   // coefficients C[k][c]
+    case MOLE_WF_LCAO_2E_2C: return 4;
   }
   return -1;
 }
@@ -131,6 +135,10 @@ int32_t mole_wf_create(mole_ctx_t ctx, const mole_wf_desc* d, mole_wf_t* out) {
     const int nu = (int)d->geom[1], nd = (int)d->geom[2];
     if (nu < 0 || nd < 0 || nu > 5 || nd > 5 || nu + nd < 1 || !(d->geom[0] > 0.0))
       return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "Slater-Jastrow needs kappa>0 and 0<=n_up,n_dn<=5");
+  }
+  if (d->kind >= MOLE_WF_LCAO_1E_2C && d->kind <= MOLE_WF_LCAO_2E_2C) {
+    if (!(d->geom[1] > 0.0) || (d->geom[0] != 0.0 && d->geom[0] != 1.0))
+      return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "LCAO needs alpha = 1/width > 0 and mode 0 (spin product) or 1 (determinant)");
   }
   mole_wf_s* w = new mole_wf_s();
   w->ctx = ctx;
@@ -338,7 +346,7 @@ static int32_t eval_device(mole_ctx_s* ctx, const WfParams& wp, const HamParams*
   const int blocks = cdiv(W, 128);
   switch (wp.kind) {
 #define EV(K) case K: eval_kernel<K><<<blocks, 128, 0, STREAM(ctx)>>>(x_dev, W, wp, h, hp != nullptr, d_psi, d_grad, d_lap, d_h, d_pg); break;
-    EV(K_STO_1S) EV(K_GAUSSIAN) EV(K_STO_PRODUCT) EV(K_H2_HL_STO) EV(K_H2P_PRODUCT) EV(K_CONSTANT)
+    EV(K_STO_1S) EV(K_GAUSSIAN) EV(K_STO_PRODUCT) EV(K_H2_HL_STO) EV(K_H2P_PRODUCT) EV(K_CONSTANT) EV(K_LCAO_1E_2C) EV(K_LCAO_2E_1C) EV(K_LCAO_2E_2C)
 #undef EV
     case K_SLATER_JASTROW:
       sj_eval_launch(STREAM(ctx), x_dev, W, wp, h, hp != nullptr, d_psi, d_grad, d_lap, d_h, d_pg);
@@ -494,7 +502,7 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
     const int blocks = std::min(cdiv(W, SWEEP_THREADS), e->partial_rows);
     switch (wf->p.kind) {
 #define SW(K) case K: launch_sweep_kind<K>(STREAM(ctx), blocks, sp, m->kind, opt); break;
-      SW(K_STO_1S) SW(K_GAUSSIAN) SW(K_STO_PRODUCT) SW(K_H2_HL_STO) SW(K_H2P_PRODUCT) SW(K_CONSTANT)
+      SW(K_STO_1S) SW(K_GAUSSIAN) SW(K_STO_PRODUCT) SW(K_H2_HL_STO) SW(K_H2P_PRODUCT) SW(K_CONSTANT) SW(K_LCAO_1E_2C) SW(K_LCAO_2E_1C) SW(K_LCAO_2E_2C)
 #undef SW
       default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
     }
@@ -572,7 +580,7 @@ static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
     const int blocks = std::min(cdiv(e->W, SWEEP_THREADS), e->partial_rows);
     switch (wf->p.kind) {
 #define DM(K) case K: dmc_step_kernel<K><<<blocks, SWEEP_THREADS, 0, STREAM(ctx)>>>(dp); break;
-      DM(K_STO_1S) DM(K_GAUSSIAN) DM(K_STO_PRODUCT) DM(K_H2_HL_STO) DM(K_H2P_PRODUCT)
+      DM(K_STO_1S) DM(K_GAUSSIAN) DM(K_STO_PRODUCT) DM(K_H2_HL_STO) DM(K_H2P_PRODUCT) DM(K_LCAO_1E_2C) DM(K_LCAO_2E_1C) DM(K_LCAO_2E_2C)
 #undef DM
       default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
     }

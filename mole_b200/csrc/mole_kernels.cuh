@@ -258,9 +258,9 @@ __global__ void eval_kernel(const double* __restrict__ x, int64_t W, WfParams p,
 // [+ sample E_L, O_k, moments]) -> store state -> block-tree reduction of the accumulators.
 // Occupancy target (measured at 2^20 walkers): 16 warps/SM (128 registers) is +3..4 % for the one- and
 // two-electron STO / Gaussian kinds and +10 % at 2^16 walkers; the H2 Heitler-London kind would spill there
-// and keeps 12 warps/SM.
+// and keeps 12 warps/SM, like the two-electron LCAO kinds.
 #ifndef MOLE_SWEEP_MIN_CTAS
-#define MOLE_SWEEP_MIN_CTAS(KIND) ((KIND) == K_H2_HL_STO ? 3 : 4)
+#define MOLE_SWEEP_MIN_CTAS(KIND) ((KIND) == K_H2_HL_STO || (KIND) == K_LCAO_2E_1C || (KIND) == K_LCAO_2E_2C ? 3 : 4)
 #endif
 template <int KIND, int METROP, bool OPT>
 __global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) sweep_kernel(const SweepParams sp) {

@@ -13,7 +13,7 @@
 #include "mole_math.cuh"
 
 enum { K_STO_1S = 0, K_GAUSSIAN = 1, K_STO_PRODUCT = 2, K_H2_HL_STO = 3, K_H2P_PRODUCT = 4, K_SLATER_JASTROW = 5,
-       K_CONSTANT = 6 };
+       K_CONSTANT = 6, K_LCAO_1E_2C = 7, K_LCAO_2E_1C = 8, K_LCAO_2E_2C = 9 };
 
 template <int KIND> struct WfDev;
 
@@ -181,6 +181,108 @@ template <> struct WfDev<K_H2P_PRODUCT> {
   }
   MOLE_D static void pgrad(const WfParams&, const State&, double*) {}
 };
+
+// ---- LCAO determinants over a hydrogen-1s basis: the API the reference's tests name but keep commented out
+// (Hydrogen1sBasis / Orbital / SingleDeterminant / SpinDeterminantProduct, tests/helium_lcao.rs:94-101,
+// tests/hydrogen_molecular_ion_lcao.rs:103-107).
+//   chi_c(r) = exp(-alpha |r - R_c|), alpha = 1 / width;   phi_k(r) = sum_c C[k][c] chi_c(r)
+//   NE = 1: psi = phi_0(x_0)                                            SingleDeterminant([phi_0])
+//   NE = 2, mode 0: psi = phi_0(x_0) phi_1(x_1)                         SpinDeterminantProduct([phi_0, phi_1], n_up = 1)
+//   NE = 2, mode 1: psi = phi_0(x_0) phi_1(x_1) - phi_0(x_1) phi_1(x_0) SingleDeterminant([phi_0, phi_1])
+// geom: [0] mode, [1] alpha, [2 + 3c ..] centre R_c;  params: C[k][c] at k * NC + c (P = NK * NC, all variational).
+// The State caches r, 1/r and chi per (electron, centre): a single-electron move re-evaluates NC exponentials.
+template <int NE_, int NC>
+struct LcaoDev {
+  static constexpr int NE = NE_, NK = NE_, NP = NK * NC;
+  struct State { double x[3 * NE_]; double r[NE_][NC], ir[NE_][NC], ch[NE_][NC]; };
+  MOLE_D static void one(const WfParams& p, State& s, int e) {
+    double n2[NC], a[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      n2[c] = mole_norm2_3(s.x[3 * e] - p.geom[2 + 3 * c], s.x[3 * e + 1] - p.geom[3 + 3 * c], s.x[3 * e + 2] - p.geom[4 + 3 * c]);
+    m_sqrt_rsqrt_n<NC>(n2, s.r[e], s.ir[e]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a[c] = -p.geom[1] * s.r[e][c];
+    m_exp_n<NC, true>(a, s.ch[e]);
+  }
+  MOLE_D static void init(const WfParams& p, State& s) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) one(p, s, e);
+  }
+  MOLE_D static void move(const WfParams& p, State& s, int e, const double xn[3]) {
+    s.x[3 * e] = xn[0]; s.x[3 * e + 1] = xn[1]; s.x[3 * e + 2] = xn[2];
+    one(p, s, e);
+  }
+  // orbital k at electron e: value, gradient, laplacian
+  MOLE_D static double phi(const WfParams& p, const State& s, int k, int e) {
+    double v = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v = fma(p.p[k * NC + c], s.ch[e][c], v);
+    return v;
+  }
+  MOLE_D static void gphi(const WfParams& p, const State& s, int k, int e, double* g) {
+    g[0] = g[1] = g[2] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double f = -p.geom[1] * p.p[k * NC + c] * s.ch[e][c] * s.ir[e][c];   // grad chi = -alpha chi (r - R_c) / |r - R_c|
+      g[0] = fma(f, s.x[3 * e] - p.geom[2 + 3 * c], g[0]);
+      g[1] = fma(f, s.x[3 * e + 1] - p.geom[3 + 3 * c], g[1]);
+      g[2] = fma(f, s.x[3 * e + 2] - p.geom[4 + 3 * c], g[2]);
+    }
+  }
+  MOLE_D static double lphi(const WfParams& p, const State& s, int k, int e) {
+    double v = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)                                                // lap chi = alpha chi (alpha r - 2) / r
+      v = fma(p.p[k * NC + c] * (p.geom[1] * s.ch[e][c] * s.ir[e][c]), fma(p.geom[1], s.r[e][c], -2.0), v);
+    return v;
+  }
+  MOLE_D static double psi(const WfParams& p, const State& s) {
+    if (NE == 1) return phi(p, s, 0, 0);
+    const double m = p.geom[0] != 0.0 ? 1.0 : 0.0;
+    return phi(p, s, 0, 0) * phi(p, s, NK - 1, NE - 1) - m * (phi(p, s, 0, NE - 1) * phi(p, s, NK - 1, 0));
+  }
+  MOLE_D static void grad(const WfParams& p, const State& s, double* g) {
+    if (NE == 1) { gphi(p, s, 0, 0, g); return; }
+    const double m = p.geom[0] != 0.0 ? 1.0 : 0.0;
+    double a[3], b[3];
+    // electron 0: grad phi_0(x_0) phi_1(x_1) - m phi_0(x_1) grad phi_1(x_0)
+    gphi(p, s, 0, 0, a); gphi(p, s, NK - 1, 0, b);
+    const double p11 = phi(p, s, NK - 1, NE - 1), p01 = phi(p, s, 0, NE - 1);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g[q] = a[q] * p11 - m * (p01 * b[q]);
+    // electron 1: phi_0(x_0) grad phi_1(x_1) - m grad phi_0(x_1) phi_1(x_0)
+    gphi(p, s, NK - 1, NE - 1, a); gphi(p, s, 0, NE - 1, b);
+    const double p00 = phi(p, s, 0, 0), p10 = phi(p, s, NK - 1, 0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g[3 * (NE - 1) + q] = p00 * a[q] - m * (b[q] * p10);
+  }
+  MOLE_D static double lap(const WfParams& p, const State& s) {
+    if (NE == 1) return lphi(p, s, 0, 0);
+    const double m = p.geom[0] != 0.0 ? 1.0 : 0.0;
+    const double p00 = phi(p, s, 0, 0), p11 = phi(p, s, NK - 1, NE - 1), p01 = phi(p, s, 0, NE - 1), p10 = phi(p, s, NK - 1, 0);
+    const double direct = lphi(p, s, 0, 0) * p11 + p00 * lphi(p, s, NK - 1, NE - 1);
+    const double exch = p01 * lphi(p, s, NK - 1, 0) + lphi(p, s, 0, NE - 1) * p10;
+    return direct - m * exch;
+  }
+  MOLE_D static void pgrad(const WfParams& p, const State& s, double* o) {
+    if (NE == 1) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) o[c] = s.ch[0][c];
+      return;
+    }
+    const double m = p.geom[0] != 0.0 ? 1.0 : 0.0;
+    const double p00 = phi(p, s, 0, 0), p11 = phi(p, s, NK - 1, NE - 1), p01 = phi(p, s, 0, NE - 1), p10 = phi(p, s, NK - 1, 0);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      o[c] = s.ch[0][c] * p11 - m * (s.ch[NE - 1][c] * p10);                    // d / d C[0][c]
+      o[(NK - 1) * NC + c] = p00 * s.ch[NE - 1][c] - m * (p01 * s.ch[0][c]);    // d / d C[1][c]
+    }
+  }
+};
+template <> struct WfDev<K_LCAO_1E_2C> : LcaoDev<1, 2> {};   // H2+ LCAO, tests/hydrogen_molecular_ion_lcao.rs:103-107
+template <> struct WfDev<K_LCAO_2E_1C> : LcaoDev<2, 1> {};   // He LCAO, tests/helium_lcao.rs:94-101
+template <> struct WfDev<K_LCAO_2E_2C> : LcaoDev<2, 2> {};   // H2 molecular orbitals (singlet product or triplet determinant)
 
 // ---- WaveFunctionMock, psi = const                         src/metropolis/src/metrop.rs:225-255
 template <> struct WfDev<K_CONSTANT> {

@@ -20,6 +20,7 @@ _ERR_NAMES = {1: "LinalgError", 2: "ShapeError", 3: "FuncError", 4: "OperatorVal
               102: "InvalidArgument", 103: "NoDevice", 104: "AssertionFailed"}
 
 WF_STO_1S, WF_GAUSSIAN, WF_STO_PRODUCT, WF_H2_HL_STO, WF_H2P_PRODUCT, WF_SLATER_JASTROW, WF_CONSTANT = range(7)
+WF_LCAO_1E_2C, WF_LCAO_2E_1C, WF_LCAO_2E_2C = 7, 8, 9
 OP_KINETIC, OP_IONIC_POT, OP_ELEC_POT, OP_IONIC, OP_ELECTRONIC, OP_HARMONIC = range(6)
 METROP_BOX, METROP_DIFFUSE = 0, 1
 OBS_ENERGY, OBS_PGRAD, OBS_WFVALUE, OBS_KINETIC = 1, 2, 4, 8

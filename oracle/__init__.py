@@ -21,6 +21,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libmole_oracle.so")
 
 # enums (oracle_wf.hpp / oracle_mc.hpp)
 WF_STO_1S, WF_GAUSSIAN, WF_STO_PRODUCT, WF_H2_HL_STO, WF_H2P_PRODUCT, WF_SLATER_JASTROW, WF_CONSTANT = range(7)
+WF_LCAO_1E_2C, WF_LCAO_2E_1C, WF_LCAO_2E_2C = 7, 8, 9
 HAM_KINETIC, HAM_IONIC_POT, HAM_ELEC_POT, HAM_IONIC, HAM_ELECTRONIC, HAM_HARMONIC = range(6)
 METROP_BOX, METROP_DIFFUSE = 0, 1
 OBS_ENERGY, OBS_PGRAD, OBS_WFVALUE, OBS_KINETIC = 1, 2, 4, 8
@@ -84,7 +85,7 @@ def _seed(seed):
 # ------------------------------------------------------------------ descriptors
 def wf_desc(kind, params=(), geom=(), n_elec=None):
     ne = {WF_STO_1S: 1, WF_GAUSSIAN: 1, WF_STO_PRODUCT: 2, WF_H2_HL_STO: 2, WF_H2P_PRODUCT: 1,
-          WF_CONSTANT: 1}.get(kind)
+          WF_CONSTANT: 1, WF_LCAO_1E_2C: 1, WF_LCAO_2E_1C: 2, WF_LCAO_2E_2C: 2}.get(kind)
     if kind == WF_SLATER_JASTROW:
         ne = int(geom[1]) + int(geom[2])
     if n_elec is not None:

@@ -56,6 +56,12 @@ enum WfKind : int32_t {
   WF_H2P_PRODUCT = 4,     // tests/hydrogen_molecular_ion_lcao.rs:51-98
   WF_SLATER_JASTROW = 5,  // SURVEY.md §8(c) synthetic config 5 + theory/jastrow.tex (erratum applied)
   WF_CONSTANT = 6,        // src/metropolis/src/metrop.rs:225-255 (WaveFunctionMock)
+  // LCAO determinants over a hydrogen-1s basis: the API the reference's tests name but keep commented out
+  // (tests/helium_lcao.rs:94-101, tests/hydrogen_molecular_ion_lcao.rs:103-107).  No upstream implementation exists;
+  // the restatement is built from the reference's STO (hydrogen_molecular_ion_lcao.rs:25-49) shifted to each centre.
+  WF_LCAO_1E_2C = 7,      // SingleDeterminant([phi_0]) over two centres (H2+)
+  WF_LCAO_2E_1C = 8,      // two orbitals over one centre (He)
+  WF_LCAO_2E_2C = 9,      // two orbitals over two centres (H2 molecular orbitals)
 };
 
 constexpr int WF_MAX_PARAMS = 8;
@@ -122,6 +128,40 @@ template <class R> inline R sto_laplacian(R alpha, const R* x) {
 }
 template <class R> inline R sto_pgrad(R alpha, const R* x) {
   return -norm_l2(x, 3) * sto_value(alpha, x);  // hydrogen_molecule.rs:55-57
+}
+
+// ---- LCAO over a hydrogen-1s basis (kinds 7-9): chi_c(r) = STO(alpha)(r - R_c), phi_k = sum_c C[k][c] chi_c.
+// geom: [mode, alpha = 1/width, R_0 (3), R_1 (3)]; params: C[k][c] at k * nc + c.  mode 0: psi = phi_0(x_0) phi_1(x_1)
+// (SpinDeterminantProduct, n_up = 1); mode 1: psi = phi_0(x_0) phi_1(x_1) - phi_0(x_1) phi_1(x_0) (SingleDeterminant).
+inline bool wf_is_lcao(int kind) { return kind >= WF_LCAO_1E_2C && kind <= WF_LCAO_2E_2C; }
+inline int lcao_nc(int kind) { return kind == WF_LCAO_2E_1C ? 1 : 2; }
+template <class R>
+struct LcaoOrb {   // orbital k evaluated at one electron position
+  R v, g[3], l;
+};
+template <class R>
+inline LcaoOrb<R> lcao_orbital(const Wf<R>& wf, int k, const R* x) {
+  const int nc = lcao_nc(wf.kind);
+  const R al = R(wf.geom[1]);
+  LcaoOrb<R> o;
+  o.v = R(0.0); o.l = R(0.0);
+  for (int q = 0; q < 3; ++q) o.g[q] = R(0.0);
+  for (int c = 0; c < nc; ++c) {
+    R d[3], gc[3];
+    for (int q = 0; q < 3; ++q) d[q] = x[q] - R(wf.geom[2 + 3 * c + q]);
+    const R C = wf.p[k * nc + c];
+    sto_gradient(al, d, gc);
+    o.v += C * sto_value(al, d);
+    o.l += C * sto_laplacian(al, d);
+    for (int q = 0; q < 3; ++q) o.g[q] += C * gc[q];
+  }
+  return o;
+}
+template <class R>
+inline R lcao_chi(const Wf<R>& wf, int c, const R* x) {
+  R d[3];
+  for (int q = 0; q < 3; ++q) d[q] = x[q] - R(wf.geom[2 + 3 * c + q]);
+  return sto_value(R(wf.geom[1]), d);
 }
 
 // ---- small dense determinant (partial pivoting), used only by the Slater-Jastrow oracle
@@ -317,6 +357,14 @@ R wf_value(const Wf<R>& wf, const R* cfg) {
     }
     case WF_CONSTANT:  // metrop.rs:240-242
       return R(wf.geom[0]);
+    case WF_LCAO_1E_2C:
+      return lcao_orbital(wf, 0, cfg).v;
+    case WF_LCAO_2E_1C:
+    case WF_LCAO_2E_2C: {
+      const R direct = lcao_orbital(wf, 0, cfg).v * lcao_orbital(wf, 1, cfg + 3).v;
+      if (wf.geom[0] == 0.0) return direct;
+      return direct - lcao_orbital(wf, 0, cfg + 3).v * lcao_orbital(wf, 1, cfg).v;
+    }
   }
   throw std::runtime_error("wf_value: unknown kind");
 }
@@ -385,6 +433,21 @@ void wf_gradient(const Wf<R>& wf, const R* cfg, R* out) {
       }
       return;
     }
+    case WF_LCAO_1E_2C: {
+      const LcaoOrb<R> a = lcao_orbital(wf, 0, cfg);
+      for (int q = 0; q < 3; ++q) out[q] = a.g[q];
+      return;
+    }
+    case WF_LCAO_2E_1C:
+    case WF_LCAO_2E_2C: {
+      const LcaoOrb<R> a0 = lcao_orbital(wf, 0, cfg), b1 = lcao_orbital(wf, 1, cfg + 3);
+      for (int q = 0; q < 3; ++q) { out[q] = a0.g[q] * b1.v; out[3 + q] = a0.v * b1.g[q]; }
+      if (wf.geom[0] != 0.0) {
+        const LcaoOrb<R> a1 = lcao_orbital(wf, 0, cfg + 3), b0 = lcao_orbital(wf, 1, cfg);
+        for (int q = 0; q < 3; ++q) { out[q] -= a1.v * b0.g[q]; out[3 + q] -= a1.g[q] * b0.v; }
+      }
+      return;
+    }
     case WF_CONSTANT:  // metrop.rs:248-250: unimplemented!()
       throw std::runtime_error("WaveFunctionMock::gradient is unimplemented in the reference");
   }
@@ -446,6 +509,16 @@ R wf_laplacian(const Wf<R>& wf, const R* cfg) {
       }
       return lap;
     }
+    case WF_LCAO_1E_2C:
+      return lcao_orbital(wf, 0, cfg).l;
+    case WF_LCAO_2E_1C:
+    case WF_LCAO_2E_2C: {
+      const LcaoOrb<R> a0 = lcao_orbital(wf, 0, cfg), b1 = lcao_orbital(wf, 1, cfg + 3);
+      const R direct = a0.l * b1.v + a0.v * b1.l;
+      if (wf.geom[0] == 0.0) return direct;
+      const LcaoOrb<R> a1 = lcao_orbital(wf, 0, cfg + 3), b0 = lcao_orbital(wf, 1, cfg);
+      return direct - (a1.v * b0.l + a1.l * b0.v);
+    }
     case WF_CONSTANT:  // metrop.rs:252-254
       return R(1.0);
   }
@@ -488,6 +561,26 @@ void wf_parameter_gradient(const Wf<R>& wf, const R* cfg, R* out) {
       for (int m = 0; m < 3; ++m)
         out[m] = (s.dzdet[0][m] * s.det[1] + s.det[0] * s.dzdet[1][m]) * J;
       for (int m = 0; m < 4; ++m) out[3 + m] = s.det[0] * s.det[1] * J * s.dbf[m];  // jastrow.tex:123-126
+      return;
+    }
+    case WF_LCAO_1E_2C:
+      for (int c = 0; c < 2; ++c) out[c] = lcao_chi(wf, c, cfg);
+      return;
+    case WF_LCAO_2E_1C:
+    case WF_LCAO_2E_2C: {
+      const int nc = lcao_nc(wf.kind);
+      const R a0 = lcao_orbital(wf, 0, cfg).v, b1 = lcao_orbital(wf, 1, cfg + 3).v;
+      for (int c = 0; c < nc; ++c) {
+        out[c] = lcao_chi(wf, c, cfg) * b1;             // d / d C[0][c]
+        out[nc + c] = a0 * lcao_chi(wf, c, cfg + 3);    // d / d C[1][c]
+      }
+      if (wf.geom[0] != 0.0) {
+        const R a1 = lcao_orbital(wf, 0, cfg + 3).v, b0 = lcao_orbital(wf, 1, cfg).v;
+        for (int c = 0; c < nc; ++c) {
+          out[c] -= lcao_chi(wf, c, cfg + 3) * b0;
+          out[nc + c] -= a1 * lcao_chi(wf, c, cfg);
+        }
+      }
       return;
     }
     case WF_CONSTANT:

@@ -37,6 +37,27 @@ def cases(mole=None):
     sj("sj_ne", 5, 5, [9.64, 2.88, 2.88, 0.5, 1.0, 0.1, -0.05], 1.0, 10)     # SURVEY.md §8(c) synthetic config 5
     sj("sj_be", 2, 2, [3.68, 0.96, 0.96, 0.5, 1.0, 0.2, 0.1], 1.0, 4)
     sj("sj_li", 2, 1, [2.69, 0.64, 0.64, 0.4, 0.8, 0.0, 0.0], 1.5, 3)
+    # LCAO determinants over a hydrogen-1s basis (the API named at tests/helium_lcao.rs:94-101 and
+    # tests/hydrogen_molecular_ion_lcao.rs:103-107), same numbers as tests/golden/make_golden.py
+    def lcao(name, kind, coeff, width_inv, pos, charges, mk):
+        geom = [1 if name.endswith("triplet") else 0, width_inv] + list(np.asarray(pos, dtype=float).reshape(-1)) + [0.0] * (6 - 3 * len(pos))
+        add(name, O.wf_desc(kind, coeff, geom), O.ham_desc(O.HAM_ELECTRONIC, pos, charges),
+            lambda m: (mk(m), m.ElectronicHamiltonian.from_ions(pos, charges)))
+
+    def orbs(m, pos, width, rows):
+        basis = m.Hydrogen1sBasis(pos, [width])
+        return [m.Orbital(np.array(r).reshape(-1, 1), basis.clone()) for r in rows]
+
+    p2 = [[-1.25, 0, 0], [1.25, 0, 0]]
+    lcao("lcao_h2p", O.WF_LCAO_1E_2C, [1.0, 1.0], 1.0, p2, [1, 1], lambda m: m.SingleDeterminant(orbs(m, p2, 1.0, [[1.0, 1.0]])))
+    lcao("lcao_he", O.WF_LCAO_2E_1C, [1.0, 1.0], 1.0 / (1.0 / 1.69), [[0, 0, 0]], [2],
+         lambda m: m.SpinDeterminantProduct(orbs(m, [[0, 0, 0]], 1.0 / 1.69, [[1.0], [1.0]]), 1))
+    ps = [[-0.7, 0, 0], [0.7, 0, 0]]
+    lcao("lcao_h2_singlet", O.WF_LCAO_2E_2C, [1.0, 0.9, 0.8, 1.1], 1.0 / 0.85, ps, [1, 1],
+         lambda m: m.SpinDeterminantProduct(orbs(m, ps, 0.85, [[1.0, 0.9], [0.8, 1.1]]), 1))
+    pt = [[-0.7, 0.1, 0], [0.7, -0.1, 0.2]]
+    lcao("lcao_h2_triplet", O.WF_LCAO_2E_2C, [1.0, 1.0, 1.0, -1.0], 1.0 / 0.85, pt, [1, 1],
+         lambda m: m.SingleDeterminant(orbs(m, pt, 0.85, [[1.0, 1.0], [1.0, -1.0]])))
     return c
 
 

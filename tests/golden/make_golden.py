@@ -10,9 +10,13 @@ so the fixtures do not share any derivative formula with the oracle or the CUDA 
   Gauss   examples/dmc.rs:47-50
   STO     examples/dmc.rs:108-111
   SJ      SURVEY.md §8(c) synthetic config 5; Jastrow f_ee of theory/jastrow.tex:23-26
+  LCAO    Hydrogen1sBasis / Orbital / SingleDeterminant / SpinDeterminantProduct as named (commented out) at
+          tests/helium_lcao.rs:94-101 and tests/hydrogen_molecular_ion_lcao.rs:103-107: phi_k = sum_c C[k][c]
+          exp(-|r - R_c| / width); geom = [mode, 1/width, R_0, R_1], params = C[k][c]
 Potentials: src/operator/src/operator.rs:25-36,80-90; SHO examples/custom_operator.rs:56-58.
 
-Run from the repo root:  python tests/golden/make_golden.py
+Run from the repo root:  python tests/golden/make_golden.py            (everything; the SJ cases take minutes)
+                         python tests/golden/make_golden.py --only lcao  (keeps the other entries of the JSON)
 """
 import json
 import os
@@ -54,6 +58,19 @@ def psi_gauss(x, p, g):
 
 def psi_sto(x, p, g):
     return mp.exp(-p[0] * norm(x))
+
+
+def psi_lcao(ne, nc):
+    def psi(x, p, g):
+        mode, alpha = g[0], g[1]
+
+        def phi(k, r):
+            return sum(p[k * nc + c] * sto(alpha, [r[q] - g[2 + 3 * c + q] for q in range(3)]) for c in range(nc))
+        if ne == 1:
+            return phi(0, x[0:3])
+        direct = phi(0, x[0:3]) * phi(1, x[3:6])
+        return direct - phi(0, x[3:6]) * phi(1, x[0:3]) if mode else direct
+    return psi
 
 
 def det(m):
@@ -136,13 +153,30 @@ CASES = {
     "sj_ne": (psi_sj, [9.64, 2.88, 2.88, 0.5, 1.0, 0.1, -0.05], [1.0, 5, 5], 10, 7, ("electronic", [[0, 0, 0]], [10])),
     "sj_be": (psi_sj, [3.68, 0.96, 0.96, 0.5, 1.0, 0.2, 0.1], [1.0, 2, 2], 4, 7, ("electronic", [[0, 0, 0]], [4])),
     "sj_li": (psi_sj, [2.69, 0.64, 0.64, 0.4, 0.8, 0.0, 0.0], [1.5, 2, 1], 3, 7, ("electronic", [[0, 0, 0]], [3])),
+    # H2+ LCAO of tests/hydrogen_molecular_ion_lcao.rs:101-107 (ion_pos +-1.25, width 1, coefficients [[1], [1]])
+    "lcao_h2p": (psi_lcao(1, 2), [1.0, 1.0], [0, 1.0, -1.25, 0, 0, 1.25, 0, 0], 1, 2,
+                 ("electronic", [[-1.25, 0, 0], [1.25, 0, 0]], [1, 1])),
+    # He LCAO of tests/helium_lcao.rs:92-101 (width 1/1.69, two orbitals [[1]], n_up = 1)
+    "lcao_he": (psi_lcao(2, 1), [1.0, 1.0], [0, 1.69, 0, 0, 0, 0, 0, 0], 2, 2, ("electronic", [[0, 0, 0]], [2])),
+    # H2 molecular orbitals: singlet sigma_g(1) sigma_g'(2) with unequal coefficients, and the triplet determinant
+    "lcao_h2_singlet": (psi_lcao(2, 2), [1.0, 0.9, 0.8, 1.1], [0, 1.0 / 0.85, -0.7, 0, 0, 0.7, 0, 0], 2, 4,
+                        ("electronic", [[-0.7, 0, 0], [0.7, 0, 0]], [1, 1])),
+    "lcao_h2_triplet": (psi_lcao(2, 2), [1.0, 1.0, 1.0, -1.0], [1, 1.0 / 0.85, -0.7, 0.1, 0, 0.7, -0.1, 0.2], 2, 4,
+                        ("electronic", [[-0.7, 0.1, 0], [0.7, -0.1, 0.2]], [1, 1])),
 }
 
 
 def main():
-    rng = random.Random(20261017)
-    out = {}
+    import sys
+    only = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--only" else None
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "wf_golden.json")
+    rng_main = random.Random(20261017)
+    out = json.load(open(path)) if only else {}
     for name, (psi, p, g, ne, nopt, ham) in CASES.items():
+        if only and not name.startswith(only):
+            continue
+        # the LCAO cases were added later and draw from their own stream so that the earlier entries stay reproducible
+        rng = random.Random("mole-b200 " + name) if name.startswith("lcao") else rng_main
         entries = []
         ncfg = 3 if name.startswith("sj") else 6
         for c in range(ncfg):
@@ -162,7 +196,6 @@ def main():
                                 pgrad=[mp.nstr(t, 25) for t in pg[:nopt]], eloc=mp.nstr(eloc, 25), v=mp.nstr(v, 25)))
         out[name] = dict(params=p, geom=g, n_elec=ne, n_params=nopt, ham=list(ham), entries=entries)
         print(name, "done")
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "wf_golden.json")
     with open(path, "w") as fh:
         json.dump(out, fh, indent=1)
     print("wrote", path)

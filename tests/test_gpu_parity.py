@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-10
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wf_golden.json")))
-SMALL = ["h2", "he", "h2p", "gauss_sho", "gauss_h", "sto_h"]
+LCAO = ["lcao_h2p", "lcao_he", "lcao_h2_singlet", "lcao_h2_triplet"]
+SMALL = ["h2", "he", "h2p", "gauss_sho", "gauss_h", "sto_h"] + LCAO
 SJ = ["sj_ne", "sj_be", "sj_li"]
 ALL = SMALL + SJ
 
@@ -57,6 +58,43 @@ def test_pointwise_traits_match_mpmath_golden(mole, name):
         if g["n_params"]:
             assert rel_err(wf.parameter_gradient(cfg), [float(t) for t in e["pgrad"]]) < TOL
         assert abs(op.act_on(wf, cfg) / wf.value(cfg) - float(e["eloc"])) < TOL * max(1.0, abs(float(e["eloc"])))
+
+
+def test_lcao_helium_is_the_reference_helium(mole):
+    """tests/helium_lcao.rs:94-102: the commented-out SpinDeterminantProduct over a Hydrogen1sBasis of width 1/1.69 and
+    the HeliumAtomWaveFunction(1.69) the test runs in its place are the same function -> with one Philox stream the
+    two kinds take the same decisions and give the same energies (and the reference's criterion, :134)."""
+    c = cases()
+    he, op = c["he"]["make"](mole)
+    lc, _ = c["lcao_he"]["make"](mole)
+    out = []
+    for wf in (he, lc):
+        ens = mole.Ensemble(4096, 2, SEED0)
+        ens.init_uniform(-1.0, 1.0)
+        m = mole.MetropolisDiffuse(0.1, SEED0)                              # helium_lcao.rs:110
+        got = ens.sweep(wf, m, op, n_sweeps=300, n_discard=50, block_size=50, observables=mole.ffi.OBS_ENERGY,
+                        traces=("energy", "accept"))
+        e, err, _, _ = mole.acc_finalize(ens.acc_get())
+        out.append((got["accept"], got["energy"], ens.get_configs(), e, err))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert close(out[1][1], out[0][1], 1e-9) and close(out[1][2], out[0][2])
+    assert abs(out[1][3] - (-2.84765625)) < 5 * out[1][4] + 2e-3          # <E> of exp(-alpha(r1+r2)) at alpha = 1.69 is alpha^2 - 27 alpha / 8
+
+
+def test_lcao_descriptor_errors(mole):
+    b3 = [[0, 0, 0], [1, 0, 0], [2, 0, 0]]
+    with pytest.raises(mole.MoleError):
+        mole.Hydrogen1sBasis(b3, [1.0])                                     # closed set: one or two centres
+    with pytest.raises(mole.MoleError):
+        mole.Hydrogen1sBasis([[0, 0, 0]], [1.0, 2.0])                       # one width
+    b = mole.Hydrogen1sBasis([[0, 0, 0]], [1.0])
+    with pytest.raises(mole.MoleError):
+        mole.SingleDeterminant([mole.Orbital([[1.0]], b)])                  # (1 electron, 1 centre) is the STO kind
+    with pytest.raises(mole.MoleError):
+        mole.SpinDeterminantProduct([mole.Orbital([[1.0]], b)] * 2, 2)
+    bneg = mole.Hydrogen1sBasis([[0, 0, 0]], [-1.0])
+    with pytest.raises(mole.MoleError):
+        mole.SpinDeterminantProduct([mole.Orbital([[1.0]], bneg)] * 2, 1)   # width <= 0 is rejected by the library
 
 
 def test_init_draws_match_oracle(mole, orc):

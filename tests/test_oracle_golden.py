@@ -16,7 +16,8 @@ def _oracle_case(orc, name):
     g = GOLD[name]
     kind = {"h2": orc.WF_H2_HL_STO, "he": orc.WF_STO_PRODUCT, "h2p": orc.WF_H2P_PRODUCT, "gauss_sho": orc.WF_GAUSSIAN,
             "gauss_h": orc.WF_GAUSSIAN, "sto_h": orc.WF_STO_1S, "sj_ne": orc.WF_SLATER_JASTROW,
-            "sj_be": orc.WF_SLATER_JASTROW, "sj_li": orc.WF_SLATER_JASTROW}[name]
+            "sj_be": orc.WF_SLATER_JASTROW, "sj_li": orc.WF_SLATER_JASTROW, "lcao_h2p": orc.WF_LCAO_1E_2C,
+            "lcao_he": orc.WF_LCAO_2E_1C, "lcao_h2_singlet": orc.WF_LCAO_2E_2C, "lcao_h2_triplet": orc.WF_LCAO_2E_2C}[name]
     wf = orc.wf_desc(kind, g["params"], g["geom"], n_elec=g["n_elec"])
     wf.n_params = g["n_params"]
     if g["ham"][0] == "electronic":
@@ -117,6 +118,33 @@ def test_mpmath_golden(orc, name):
             pref = np.array([float(t) for t in e["pgrad"]])
             assert np.max(np.abs(orc.wf_parameter_gradient(wf, cfg) - pref)) < tol * max(1.0, np.max(np.abs(pref)))
         assert abs(orc.local_energy(ham, wf, cfg) - float(e["eloc"])) < tol * max(1.0, abs(float(e["eloc"])))
+
+
+def test_lcao_reduces_to_the_reference_closed_forms(orc):
+    # tests/helium_lcao.rs:94-101: the commented-out SpinDeterminantProduct of two 1s orbitals of width 1/1.69 IS the
+    # HeliumAtomWaveFunction the test runs instead (:102) -> same psi, grad, lap, E_L as the STO-product kind
+    he = orc.wf_desc(orc.WF_STO_PRODUCT, [1.69])
+    lc = orc.wf_desc(orc.WF_LCAO_2E_1C, [1.0, 1.0], [0, 1.69, 0, 0, 0, 0, 0, 0])
+    ham = orc.ham_desc(orc.HAM_ELECTRONIC, [[0, 0, 0]], [2])
+    # one orbital on one of two centres = the 1-electron STO of examples/dmc.rs:106-125 shifted to that centre
+    sto = orc.wf_desc(orc.WF_STO_1S, [0.8])
+    l1 = orc.wf_desc(orc.WF_LCAO_1E_2C, [0.0, 1.0], [0, 0.8, 5.0, 5.0, 5.0, 0.25, -0.5, 0.125])
+    for x in np.random.default_rng(3).normal(size=(10, 2, 3)):
+        assert rel_err(orc.wf_value(lc, x), orc.wf_value(he, x)) < 1e-14
+        assert rel_err(orc.wf_gradient(lc, x), orc.wf_gradient(he, x)) < 1e-13
+        assert rel_err(orc.wf_laplacian(lc, x), orc.wf_laplacian(he, x)) < 1e-13
+        assert rel_err(orc.local_energy(ham, lc, x), orc.local_energy(ham, he, x)) < 1e-13
+        y = x[:1]
+        ys = y - np.array([[0.25, -0.5, 0.125]])
+        assert rel_err(orc.wf_value(l1, y), orc.wf_value(sto, ys)) < 1e-14
+        assert rel_err(orc.wf_gradient(l1, y), orc.wf_gradient(sto, ys)) < 1e-13
+        assert rel_err(orc.wf_laplacian(l1, y), orc.wf_laplacian(sto, ys)) < 1e-13
+    # the triplet determinant is antisymmetric under exchange and vanishes at coincidence
+    g = GOLD["lcao_h2_triplet"]
+    tr = orc.wf_desc(orc.WF_LCAO_2E_2C, g["params"], g["geom"])
+    x = np.array([[0.3, -0.2, 0.5], [-0.6, 0.1, 0.25]])
+    assert rel_err(orc.wf_value(tr, x[::-1]), -orc.wf_value(tr, x)) < 1e-14
+    assert orc.wf_value(tr, np.array([x[0], x[0]])) == 0.0
 
 
 def test_analytic_checks(orc):
