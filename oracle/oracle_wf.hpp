@@ -10,7 +10,9 @@
 //
 // Parity status: the reference cannot be built here (Rust nightly + MKL, no toolchain,
 // SURVEY.md §8(c)); this file is pinned against the golden vectors of SURVEY.md §8(c)
-// and against 40-digit mpmath evaluations (tests/golden/make_golden.py).
+// and against 40-digit mpmath evaluations (tests/golden/make_golden.py).  The LCAO kinds (7-9) and the
+// Slater-Jastrow kind have no upstream implementation at all: they are pinned by the mpmath fixtures and,
+// for LCAO, by reduction to the reference's He and STO closed forms (tests/test_oracle_golden.py).
 #pragma once
 #include <cmath>
 #include <cstdint>

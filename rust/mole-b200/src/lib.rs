@@ -64,6 +64,22 @@ impl GpuWaveFunction {
         let p = [zeta[0], zeta[1], zeta[2], b[0], b[1], b[2], b[3]];
         Self::create(ctx, 5, (n_up + n_dn) as i32, &p, &[kappa, n_up as f64, n_dn as f64], true)
     }
+    /// LCAO determinants over a hydrogen-1s basis (kinds 7-9 of include/mole_b200.h): the `Hydrogen1sBasis` /
+    /// `Orbital` / `SingleDeterminant` / `SpinDeterminantProduct` API named at tests/helium_lcao.rs:94-101 and
+    /// tests/hydrogen_molecular_ion_lcao.rs:103-107.  `ion_pos` has one or two rows, `coefficients[k][c]` is
+    /// orbital k's weight on centre c, `determinant` selects the 2x2 determinant instead of the spin product.
+    pub fn lcao(ctx: &Context, ion_pos: &Array2<f64>, width: f64, coefficients: &Array2<f64>, determinant: bool) -> Result<Self> {
+        let (nc, ne) = (ion_pos.nrows(), coefficients.nrows());
+        let bad_shape = || Error::ShapeError(ndarray::ShapeError::from_kind(ndarray::ErrorKind::IncompatibleShape));
+        let kind = match (ne, nc) { (1, 2) => 7, (2, 1) => 8, (2, 2) => 9, _ => return Err(bad_shape()) };
+        if coefficients.ncols() != nc || ion_pos.ncols() != 3 { return Err(bad_shape()); }
+        let mut geom = [0.0f64; 8];
+        geom[0] = if determinant && ne == 2 { 1.0 } else { 0.0 };
+        geom[1] = 1.0 / width;
+        for (i, v) in ion_pos.iter().enumerate() { geom[2 + i] = *v; }
+        let p: Vec<f64> = coefficients.iter().cloned().collect();
+        Self::create(ctx, kind, ne as i32, &p, &geom, true)
+    }
     pub(crate) fn raw(&self) -> *mut sys::mole_wf_s { self.raw }
 }
 impl Drop for GpuWaveFunction { fn drop(&mut self) { unsafe { sys::mole_wf_destroy(self.raw); } } }

@@ -39,3 +39,10 @@ def test_dmc_example():
     assert "VMC Energy:" in out
     e = float(out.split("DMC Energy:")[1].split()[0])
     assert abs(e + 0.5) < 0.05
+
+
+def test_lcao_example():
+    out = _run("lcao.py", "--walkers", "2048")
+    e1 = float(out.split("H2+ LCAO   Energy:")[1].split()[0])
+    e2 = float(out.split("He LCAO    Energy:")[1].split()[0])
+    assert abs(e1 + 0.5648) < 2e-3 and abs(e2 + 2.8477) < 1e-2      # closed forms: LCAO integrals at R = 2.5; alpha^2 - 27 alpha / 8

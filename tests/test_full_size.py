@@ -122,6 +122,57 @@ def test_config3_h2plus_box_full_size(mole, orc):
     assert abs(e - ref.mean()) < 5 * np.hypot(ref.mean(axis=1).std() / np.sqrt(128), err)
 
 
+def test_config3_lcao_kinds_full_size(mole, orc):
+    """BASELINE configs[2] with the LCAO descriptors the reference's tests name (commented out upstream,
+    hydrogen_molecular_ion_lcao.rs:103-107, helium_lcao.rs:94-101) at 2^16 walkers and the tests' own run lengths:
+    H2+ sigma_g = 1s_A + 1s_B with MetropolisBox(1.0), 10 000 sweeps, block 100; He with MetropolisDiffuse(0.1)."""
+    c = cases()["lcao_h2p"]
+    wf, op = c["make"](mole)
+    W, steps, block = 1 << 16, 10000, 100
+    met = mole.MetropolisBox(1.0, SEED0)
+    ens = mole.Ensemble(W, 1, SEED0)
+    ens.init_uniform()
+    x0 = ens.get_configs().copy()
+    kw = dict(n_sweeps=steps, n_discard=block, block_size=block, observables=mole.ffi.OBS_ENERGY)
+    ens.sweep(wf, met, op, **kw)
+    acc, xf = ens.acc_get(), ens.get_configs()
+    assert acc.n_samples == W * (steps - block) and acc.n_moves == W * steps
+    _subsample_parity(mole, orc, c, x0, xf, W, (0, W - 4), orc.METROP_BOX, 1.0, steps, block)
+    _shards_add_up(mole, wf, op, met, W, 1, lambda h: h.init_uniform(), kw, xf, acc)
+    e, err, _, _ = mole.acc_finalize(acc)
+    # closed form of the LCAO energy (overlap, Coulomb and exchange integrals of two 1s functions at distance R):
+    # this is where the reference test's -0.565 (:139-140) comes from
+    R = 2.5
+    S = np.exp(-R) * (1 + R + R * R / 3)
+    J = -1 / R + np.exp(-2 * R) * (1 + 1 / R)
+    K = -np.exp(-R) * (1 + R)
+    exact = -0.5 + (J + K) / (1 + S) + 1 / R
+    assert abs(exact - (-0.565)) < 5e-4
+    assert abs(e - exact) < 5 * err and err < 1e-4
+
+    c = cases()["lcao_he"]
+    wf, op = c["make"](mole)
+    steps, block = 2500, 10
+    met = mole.MetropolisDiffuse(0.1, SEED0)
+    ens = mole.Ensemble(W, 2, SEED0)
+    ens.init_uniform()
+    x0 = ens.get_configs().copy()
+    obs = mole.ffi.OBS_ENERGY | mole.ffi.OBS_PGRAD | mole.ffi.OBS_WFVALUE
+    kw = dict(n_sweeps=steps, n_discard=block, block_size=block, observables=obs)
+    ens.sweep(wf, met, op, **kw)
+    acc, xf = ens.acc_get(), ens.get_configs()
+    _subsample_parity(mole, orc, c, x0, xf, W, (0, W - 4), orc.METROP_DIFFUSE, 0.1, steps, block)
+    _shards_add_up(mole, wf, op, met, W, 2, lambda h: h.init_uniform(), kw, xf, acc)
+    e, err, _, g = mole.acc_finalize(acc)
+    assert abs(e - (1.69 ** 2 - 27.0 / 8.0 * 1.69)) < 5 * err and err < 2e-4
+    # SR moments of the two coefficients: positive semi-definite 2 x 2 block
+    n = acc.n_samples
+    s00 = acc.oo(0, 0) / n - (acc.sum_o[0] / n) ** 2
+    s11 = acc.oo(1, 1) / n - (acc.sum_o[1] / n) ** 2
+    s01 = acc.oo(0, 1) / n - acc.sum_o[0] * acc.sum_o[1] / n ** 2
+    assert s00 >= -1e-12 and s11 >= -1e-12 and s00 * s11 - s01 * s01 >= -1e-12 and np.isfinite(g).all()
+
+
 def test_config5_ne_slater_jastrow_full_size(mole, orc):
     """Ne Slater-Jastrow, P = 7, Diffuse tau = 0.02, 2^17 walkers x 200 sweeps, block 10 (the bench workload)."""
     c = cases()["sj_ne"]

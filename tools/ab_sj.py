@@ -19,6 +19,11 @@ def one_small(kind, reps):
         wf, op, ne, tau = m.HydrogenMoleculeWaveFunction(1.4, [0.5]), m.ElectronicHamiltonian.from_ions([[-0.7, 0, 0], [0.7, 0, 0]], [1, 1]), 2, 0.25
     elif kind == "he":
         wf, op, ne, tau = m.HeliumAtomWaveFunction(1.69), m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [2]), 2, 0.1
+    elif kind.startswith("lcao"):                                  # the LCAO determinant kinds (tests/common.py cases)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from common import cases
+        c = cases()[kind]
+        (wf, op), ne, tau = c["make"](m), c["ne"], 0.1
     else:
         wf, op, ne, tau = m.GaussianWaveFunction(1.0), m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1]), 1, 0.025
     ens = m.Ensemble(W, ne, SEED); ens.init_uniform()
@@ -34,7 +39,7 @@ def one_small(kind, reps):
         ctx.synchronize()
         ts.append(1e3 * (time.perf_counter() - t0))
     e, de, acc, g = m.acc_finalize(ens.acc_get())
-    print("%-28s %-6s ms/launch %s  best %.2f  = %.3e walker-steps/s  E %.10f acc %.6f" % (
+    print("%-28s %-15s ms/launch %s  best %.2f  = %.3e walker-steps/s  E %.10f acc %.6f" % (
         os.path.basename(os.environ.get("MOLE_B200_LIB", "default")), kind, " ".join("%.2f" % t for t in ts), min(ts),
         W * NS / (min(ts) * 1e-3), e, acc), flush=True)
 
@@ -75,7 +80,7 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "--one-small":
         one_small(sys.argv[2], int(sys.argv[3]))
     elif len(sys.argv) > 1 and sys.argv[1] == "--small":          # python tools/ab_sj.py --small lib1.so lib2.so
-        for kind in ("h2", "he", "gauss"):
+        for kind in ("h2", "he", "gauss", "lcao_h2p", "lcao_he", "lcao_h2_singlet", "lcao_h2_triplet"):
             for lib in [a for a in sys.argv[2:] if a.endswith(".so")]:
                 env = dict(os.environ, MOLE_B200_LIB=os.path.abspath(lib))
                 subprocess.run([sys.executable, os.path.abspath(__file__), "--one-small", kind, "3"], env=env, timeout=300)
