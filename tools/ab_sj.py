@@ -80,7 +80,10 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "--one-small":
         one_small(sys.argv[2], int(sys.argv[3]))
     elif len(sys.argv) > 1 and sys.argv[1] == "--small":          # python tools/ab_sj.py --small lib1.so lib2.so
-        for kind in ("h2", "he", "gauss", "lcao_h2p", "lcao_he", "lcao_h2_singlet", "lcao_h2_triplet"):
+        kinds = ("h2", "he", "gauss", "lcao_h2p", "lcao_he", "lcao_h2_singlet", "lcao_h2_triplet")
+        if "--kinds" in sys.argv:                                  # --kinds lcao_h2p,lcao_he
+            kinds = sys.argv[sys.argv.index("--kinds") + 1].split(",")
+        for kind in kinds:
             for lib in [a for a in sys.argv[2:] if a.endswith(".so")]:
                 env = dict(os.environ, MOLE_B200_LIB=os.path.abspath(lib))
                 subprocess.run([sys.executable, os.path.abspath(__file__), "--one-small", kind, "3"], env=env, timeout=300)
