@@ -483,6 +483,43 @@ def test_dmc_step_slater_jastrow_matches_oracle(mole, orc):
         assert close(ens.get_configs(), x)
 
 
+@pytest.mark.parametrize("name", ["lcao_h2p", "lcao_h2_singlet", "lcao_h2_triplet"])
+def test_dmc_step_lcao_matches_oracle(mole, orc, name):
+    """One DMC time step (dmc.rs:87-130) with an LCAO guiding function, state re-synchronised on the oracle each step;
+    the triplet has a node, so the fixed-node rejection (metrop.rs:178-180) is exercised."""
+    c = cases()[name]
+    wf, op = c["make"](mole)
+    W, tau, seed, ne = 512, 0.02, bytes([5] * 32), c["ne"]
+    m = mole.MetropolisDiffuse.from_rng(tau, seed).fix_nodes().set_compat(mole.ffi.COMPAT_NAN_ACCEPT)
+    x = np.array([orc.init_normal(seed, w, ne, 0.9) for w in range(W)])
+    w = np.ones(W)
+    ens = mole.Ensemble(W, ne, seed)
+    e_ref = -0.6 if ne == 1 else -1.0
+    for t in range(3):
+        ens.set_configs(x); ens.set_weights(w); ens.step = t
+        e_o, tw_o, w2, x2 = orc.dmc_step(c["owf"], c["oham"], w, x, tau, tau, e_ref, seed, t)
+        swe, sw = ens.dmc_step(wf, m, op, tau, e_ref)
+        assert abs(swe / sw - e_o) < 1e-9 * abs(e_o) and abs(sw - tw_o) < 1e-10 * tw_o
+        assert close(ens.get_configs(), x2) and close(ens.get_weights(), w2, 1e-8)
+        ens.branch(mole.ffi.BRANCH_SR)
+        src = ens.branch_sources()
+        w, x = np.full(W, w2.mean()), x2[src]
+        assert close(ens.get_configs(), x)
+
+
+def test_dmc_lcao_h2plus_energy(mole):
+    """DMC of H2+ at R = 2.5 guided by the LCAO sigma_g of tests/hydrogen_molecular_ion_lcao.rs:101-107: the guide is
+    nodeless, so the run converges to the exact total energy -0.5938235 Ha (electronic -0.9938235 + 1/R), well below
+    the guide's own VMC energy -0.56483."""
+    c = cases()["lcao_h2p"]
+    wf, op = c["make"](mole)
+    m = mole.MetropolisDiffuse.from_rng(0.01, bytes([1] * 32)).fix_nodes()
+    dmc = mole.DmcRunner.new(wf, 8192, -0.565, op, m, mole.SRBrancher.new(), identical_start=False)
+    en, er = dmc.diffuse(0.01, 3000, 100, 10)
+    assert abs(en[-1] + 0.5938235) < max(6 * er[-1], 8e-3)     # the oracle's run of 4000 walkers: -0.5908 +/- 0.0023
+    assert en[-1] < -0.58
+
+
 def test_slater_jastrow_long_run_no_drift(mole, orc):
     """The kernel carries the inverse Slater matrices and grad ln D through Sherman-Morrison updates and
     rebuilds them from scratch only every SJ_REFRESH_EVERY (8) sweeps; the oracle rebuilds everything for

@@ -9,6 +9,16 @@ ens = m.Ensemble(300, 2, seed); ens.init_uniform()
 ens.sweep(wf, m.MetropolisDiffuse(0.25, seed), op, n_sweeps=12, block_size=5, observables=obs, traces=("energy","accept"), keep_series=True)
 ens.sweep(wf, m.MetropolisBox(1.0, seed), op, n_sweeps=30, block_size=5, observables=m.ffi.OBS_ENERGY, append_series=True)
 print("series", ens.series_analyze(block_sizes=[1,2,3], per_walker=True)["tcorr"])
+# LCAO determinant kinds (sweeps with SR moments, DMC step with the nodal triplet)
+bs = m.Hydrogen1sBasis([[-0.7, 0, 0], [0.7, 0, 0]], [0.85])
+tri = m.SingleDeterminant([m.Orbital([[1.0], [1.0]], bs), m.Orbital([[1.0], [-1.0]], bs)])
+el = m.Ensemble(333, 2, seed); el.init_uniform()
+el.sweep(tri, m.MetropolisDiffuse(0.1, seed), op, n_sweeps=12, block_size=5, observables=obs, traces=("pgrad",))
+el.dmc_step(tri, m.MetropolisDiffuse(0.02, seed), op, 0.02, -0.5); el.branch(m.ffi.BRANCH_SR)
+sg = m.SingleDeterminant([m.Orbital([[1.0], [1.0]], m.Hydrogen1sBasis([[-1.25, 0, 0], [1.25, 0, 0]], [1.0]))])
+e1 = m.Ensemble(77, 1, seed); e1.init_uniform()
+e1.sweep(sg, m.MetropolisBox(1.0, seed), op, n_sweeps=12, block_size=5, observables=obs)
+print("lcao acc", el.acc_get().sum_e, e1.acc_get().sum_e)
 # Slater-Jastrow
 sj = m.SlaterJastrow(5, 5, (9.64, 2.88, 2.88), (0.5, 1.0, 0.1, -0.05), 1.0); opn = m.ElectronicHamiltonian.from_ions([[0,0,0]],[10])
 e2 = m.Ensemble(50, 10, seed); e2.init_normal(0.5)
