@@ -75,6 +75,7 @@ int32_t mole_ctx_create(int32_t device, mole_ctx_t* out) {
 
 static void ctx_free(mole_ctx_s* ctx) {
   cudaSetDevice(ctx->device);
+  mole_comm_destroy(ctx);                       // communicator and its scratch, if mole_comm_init was called
   if (ctx->stream) cudaStreamDestroy(STREAM(ctx));
   delete ctx;
 }
@@ -335,6 +336,10 @@ static int32_t eval_device(mole_ctx_s* ctx, const WfParams& wp, const HamParams*
   // outputs are HOST pointers; stage through temporaries
   const int n = 3 * wp.ne, np = wp.np;
   double *d_psi = nullptr, *d_grad = nullptr, *d_lap = nullptr, *d_h = nullptr, *d_pg = nullptr;
+  struct Free {                                   // the CU() error returns below must not leak the temporaries
+    double **a, **b, **c, **d, **e;
+    ~Free() { cudaFree(*a); cudaFree(*b); cudaFree(*c); cudaFree(*d); cudaFree(*e); }
+  } guard{&d_psi, &d_grad, &d_lap, &d_h, &d_pg};
   if (psi) CU(ctx, cudaMalloc(&d_psi, W * sizeof(double)));
   if (grad) CU(ctx, cudaMalloc(&d_grad, (size_t)W * n * sizeof(double)));
   if (lap) CU(ctx, cudaMalloc(&d_lap, W * sizeof(double)));
@@ -360,7 +365,6 @@ static int32_t eval_device(mole_ctx_s* ctx, const WfParams& wp, const HamParams*
   if (d_h) CU(ctx, cudaMemcpyAsync(hpsi, d_h, W * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
   if (d_pg) CU(ctx, cudaMemcpyAsync(pgrad, d_pg, (size_t)W * np * sizeof(double), cudaMemcpyDeviceToHost, STREAM(ctx)));
   CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
-  cudaFree(d_psi); cudaFree(d_grad); cudaFree(d_lap); cudaFree(d_h); cudaFree(d_pg);
   return MOLE_OK;
 }
 

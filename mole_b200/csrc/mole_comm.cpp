@@ -27,9 +27,8 @@ struct NcclApi {
   bool ok = false;
 };
 
-NcclApi& api() {
-  static NcclApi a;
-  if (a.handle) return a;
+NcclApi load_api() {
+  NcclApi a;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
     a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -43,6 +42,13 @@ NcclApi& api() {
   a.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(a.handle, "ncclAllGather");
   a.GetErrorString = (const char* (*)(int))dlsym(a.handle, "ncclGetErrorString");
   a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather && a.GetErrorString;
+  return a;
+}
+
+// resolved once per process (the initialisation of a function-local static is thread-safe: contexts may be driven
+// from different threads)
+NcclApi& api() {
+  static NcclApi a = load_api();
   return a;
 }
 
