@@ -176,11 +176,23 @@ __global__ void sr_pick_gather_kernel(const unsigned long long* __restrict__ cum
 // (local_sum_ptr = sum of this rank's post-update weights; red_rows = one {sum w E, sum w, ..} row per
 // rank), exactly as the host does on the synchronous path, and the energy is written to *step_e_out
 // (dmc.rs:133).
+constexpr int PICK_SMEM_TILES = 1024;   // tile offsets of up to 2^20 walkers are searched in shared memory
 __global__ void sr_pick_gather_tiled_kernel(const unsigned long long* __restrict__ cum, const unsigned long long* tile_sums,
                                             int n_tiles, int64_t W, int n, uint64_t walker_offset, RngKey key, uint32_t step,
                                             const double* __restrict__ x, double* x2, const double* __restrict__ el,
                                             double* el2, double* w2, double new_weight, const double* local_sum_ptr,
                                             const double* red_rows, int n_rows, double* step_e_out, int32_t* src) {
+  // The step is bound by dependent-load latency, not bandwidth (measured: 10 us for this kernel at 4096 and at 32768
+  // walkers alike).  The tile offsets are staged in shared memory once per CTA, and the search inside the tile is 4-ary:
+  // three independent probes per round, 4 + 2 dependent L2 round trips instead of 10.  The picked index is the first
+  // one whose inclusive prefix sum exceeds the draw, which is unique, so the result is that of the binary search.
+  __shared__ unsigned long long s_tiles[PICK_SMEM_TILES + 1];
+  const bool staged = n_tiles <= PICK_SMEM_TILES;
+  if (staged) {
+    for (int i = threadIdx.x; i <= n_tiles; i += blockDim.x) s_tiles[i] = tile_sums[i];
+    __syncthreads();
+  }
+  const unsigned long long* ts = staged ? s_tiles : tile_sums;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0 && step_e_out) {                                     // ensemble energy over all ranks, rank order
     double swe = red_rows[0], sw = red_rows[1];
@@ -189,17 +201,25 @@ __global__ void sr_pick_gather_tiled_kernel(const unsigned long long* __restrict
   }
   if (j >= W) return;
   if (local_sum_ptr) new_weight = *local_sum_ptr / (double)W;     // branching.rs:21
-  const unsigned long long total = tile_sums[n_tiles];
+  const unsigned long long total = ts[n_tiles];
   const Philox4 p = mole_draw(key, walker_offset + (uint64_t)j, step, DOM_BRANCH, 0, 0);
   const unsigned long long u = __umul64hi(mole_u64(p), total);     // uniform integer in [0,total)
   // last tile whose exclusive offset is <= u, skipping empty tiles by construction (offset[t+1] > u)
   int tl = 0, th = n_tiles - 1;
   while (tl < th) {
     const int mid = (tl + th) >> 1;
-    if (tile_sums[mid + 1] > u) th = mid; else tl = mid + 1;
+    if (ts[mid + 1] > u) th = mid; else tl = mid + 1;
   }
-  const unsigned long long ul = u - tile_sums[tl];
+  const unsigned long long ul = u - ts[tl];
   int64_t lo = (int64_t)tl * SCAN_TILE, hi = min(lo + SCAN_TILE, W) - 1;
+  while (hi - lo >= 4) {
+    const int64_t q = (hi - lo) >> 2, m1 = lo + q, m2 = m1 + q, m3 = m2 + q;   // lo < m1 < m2 < m3 < hi
+    const unsigned long long c1 = cum[m1], c2 = cum[m2], c3 = cum[m3];
+    if (c1 > ul) hi = m1;
+    else if (c2 > ul) { lo = m1 + 1; hi = m2; }
+    else if (c3 > ul) { lo = m2 + 1; hi = m3; }
+    else lo = m3 + 1;
+  }
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
     if (cum[mid] > ul) hi = mid; else lo = mid + 1;
