@@ -147,6 +147,22 @@ def test_lcao_reduces_to_the_reference_closed_forms(orc):
     assert orc.wf_value(tr, np.array([x[0], x[0]])) == 0.0
 
 
+def test_lcao_h2plus_vmc_reproduces_the_closed_form_energy(orc):
+    # tests/hydrogen_molecular_ion_lcao.rs:101-140 with the LCAO function it names: MetropolisBox(1.0), block 100; the
+    # energy of 1s_A + 1s_B at R = 2.5 follows from the overlap, Coulomb and exchange integrals (-0.56483; the test's -0.565)
+    from common import SEED0, cases
+    c = cases()["lcao_h2p"]
+    W = 256
+    cfgs = np.array([orc.init_uniform(SEED0, w, 1) for w in range(W)])
+    r = orc.ensemble_run(c["owf"], c["oham"], orc.run_options(orc.METROP_BOX, 1.0, orc.OBS_ENERGY), cfgs, SEED0, 4000, 100,
+                         trace=False)["energy"]
+    R = 2.5
+    S, J, K = np.exp(-R) * (1 + R + R * R / 3), -1 / R + np.exp(-2 * R) * (1 + 1 / R), -np.exp(-R) * (1 + R)
+    exact = -0.5 + (J + K) / (1 + S) + 1 / R
+    err = r.mean(axis=1).std() / np.sqrt(W)
+    assert abs(r.mean() - exact) < 5 * err and err < 2e-3
+
+
 def test_analytic_checks(orc):
     # 1-electron STO alpha=1 on hydrogen: E_L == -0.5 everywhere
     sto = orc.wf_desc(orc.WF_STO_1S, [1.0])
