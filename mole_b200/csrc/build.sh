@@ -16,5 +16,5 @@ mkdir -p "$OBJ"
 "$NVCC" "${FLAGS[@]}" -c "$HERE/mole_api.cu" -o "$OBJ/mole_api.o" 2> "$OBJ/ptxas_mole_api.log" || { cat "$OBJ/ptxas_mole_api.log"; exit 1; }
 "$NVCC" "${FLAGS[@]}" -x cu -c "$HERE/mole_host.cpp" -o "$OBJ/mole_host.o"
 "$NVCC" "${FLAGS[@]}" -x cu -c "$HERE/mole_comm.cpp" -o "$OBJ/mole_comm.o"
-"$NVCC" -shared -ccbin "$HOSTCXX" -o "$OUT" "$OBJ/mole_api.o" "$OBJ/mole_host.o" "$OBJ/mole_comm.o" -lcudart_static -ldl -lrt -lpthread
+"$NVCC" -Wno-deprecated-gpu-targets -shared -ccbin "$HOSTCXX" -o "$OUT" "$OBJ/mole_api.o" "$OBJ/mole_host.o" "$OBJ/mole_comm.o" -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT"
