@@ -352,7 +352,6 @@ int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_
                          double* energies, double* errors, int32_t* n_out, double* step_energies) {
   if (!ens || !wf || !m || !op || !reference_energy || !energies || !errors || !n_out || block_size < 1)
     return MOLE_ERR_INVALID_ARG;
-  mole_ctx_s* ctx = ens->ctx;
   const int blocks = num_iterations / block_size;
   std::vector<double> en, vars;
   double e_ref = *reference_energy;
