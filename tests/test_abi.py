@@ -100,7 +100,7 @@ def test_finaliser_matches_reference_statistics(mole, orc):
     assert np.allclose(g, gref, rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize("P", [1, 3, 7])
+@pytest.mark.parametrize("P", [1, 3, 7, 8])   # 8 = MOLE_ACC_MAX_PARAMS
 def test_optimizers_match_oracle(mole, orc, P):
     rng = np.random.default_rng(10 + P)
     W, ns, bs = 4, 200, 10
@@ -152,3 +152,24 @@ def test_struct_sizes_of_series_and_log_records(mole):
     import ctypes as C
     assert C.sizeof(mole.ffi.SeriesStats) == 40 and C.sizeof(mole.ffi.BlockLog) == 56
     assert C.sizeof(mole.ffi.SweepArgs) == 24 + 5 * 8
+
+
+def test_hot_kernels_do_not_spill():
+    """Static check on the ptxas -v log of the build (tools/ptxas_report.py): the Slater-Jastrow sweep / DMC kernels
+    (the bench workload) and the DMC step kernels hold their state in registers -- a spill there is a silent 10-20 %
+    regression that parity tests cannot see.  The thread-per-walker LCAO SR variants are known to spill."""
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import ptxas_report
+    if not os.path.exists(ptxas_report.LOG):
+        pytest.skip("no ptxas log: library was not built by build.sh in this tree")
+    rows = ptxas_report.parse()
+    assert len(rows) >= 60 and all(r["regs"] for r in rows)
+    hot = [r for r in rows if r["demangled"].startswith(("void sj_sweep_kernel", "sj_dmc_kernel", "void dmc_step_kernel", "sj_eval_kernel"))]
+    assert len(hot) >= 10
+    for r in hot:
+        assert r["spill_st"] == 0 and r["spill_ld"] == 0 and r["stack"] == 0, r
+        assert r["regs"] <= 255
+    # two warps per scheduler at 255 registers is the SJ kernel's design point (DESIGN 7.1)
+    assert all(r["regs"] >= 169 for r in rows if r["demangled"].startswith("void sj_sweep_kernel"))
