@@ -4,6 +4,7 @@
 #pragma once
 #include "mole_internal.h"
 #include "mole_rng.cuh"
+#include "mole_search.h"
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
@@ -204,26 +205,7 @@ __global__ void sr_pick_gather_tiled_kernel(const unsigned long long* __restrict
   const unsigned long long total = ts[n_tiles];
   const Philox4 p = mole_draw(key, walker_offset + (uint64_t)j, step, DOM_BRANCH, 0, 0);
   const unsigned long long u = __umul64hi(mole_u64(p), total);     // uniform integer in [0,total)
-  // last tile whose exclusive offset is <= u, skipping empty tiles by construction (offset[t+1] > u)
-  int tl = 0, th = n_tiles - 1;
-  while (tl < th) {
-    const int mid = (tl + th) >> 1;
-    if (ts[mid + 1] > u) th = mid; else tl = mid + 1;
-  }
-  const unsigned long long ul = u - ts[tl];
-  int64_t lo = (int64_t)tl * SCAN_TILE, hi = min(lo + SCAN_TILE, W) - 1;
-  while (hi - lo >= 4) {
-    const int64_t q = (hi - lo) >> 2, m1 = lo + q, m2 = m1 + q, m3 = m2 + q;   // lo < m1 < m2 < m3 < hi
-    const unsigned long long c1 = cum[m1], c2 = cum[m2], c3 = cum[m3];
-    if (c1 > ul) hi = m1;
-    else if (c2 > ul) { lo = m1 + 1; hi = m2; }
-    else if (c3 > ul) { lo = m2 + 1; hi = m3; }
-    else lo = m3 + 1;
-  }
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (cum[mid] > ul) hi = mid; else lo = mid + 1;
-  }
+  const int64_t lo = mole_pick_tiled(cum, ts, n_tiles, W, SCAN_TILE, u);   // mole_search.h (host-tested)
   src[j] = (int32_t)lo;
   for (int c = 0; c < n; ++c) x2[(size_t)c * W + j] = x[(size_t)c * W + lo];
   el2[j] = el[lo];
