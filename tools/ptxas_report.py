@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Static resource table of every kernel in libmole_b200.so from the ptxas -v log that build.sh keeps
 (mole_b200/csrc/_obj/ptxas_mole_api.log): registers, stack frame, spill stores / loads, static shared memory.
-No GPU needed.  Usage: python tools/ptxas_report.py [> profiles/rNN_ptxas_resources.txt]"""
+No GPU needed.  Usage: python tools/ptxas_report.py [substring of the kernel name] [> profiles/rNN_ptxas_resources.txt]"""
 import os
 import re
 import subprocess
@@ -41,7 +41,7 @@ def parse(path=LOG):
 
 
 def main():
-    rows = parse()
+    rows = [r for r in parse() if len(sys.argv) < 2 or sys.argv[1] in r["demangled"]]
     print("# ptxas -v resources per kernel (sm_100a, flags of mole_b200/csrc/build.sh); %d kernels" % len(rows))
     print("%-5s %-6s %-8s %-8s %-7s %s" % ("regs", "stack", "spill_st", "spill_ld", "smem", "kernel"))
     for r in sorted(rows, key=lambda r: (-r["spill_st"], r["demangled"])):
