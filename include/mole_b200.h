@@ -242,6 +242,18 @@ typedef struct {
 
 int32_t mole_acc_reset(mole_ens_t ens);
 int32_t mole_acc_get(mole_ens_t ens, mole_acc_host* out);
+/* Health of the ensemble since the last mole_acc_reset.  The reference has no such notion: a NaN/Inf local
+ * energy or parameter gradient silently poisons its sample vectors (vmc.rs:133-172) and the acceptance test
+ * silently rejects a non-finite psi (metrop.rs:81,197).  Here a sample whose E_L or O_k is not finite is
+ * kept OUT of every accumulator (it still appears in the traces) and counted; a DMC walker whose E_L is not
+ * finite gets weight 0 (it is never picked by the brancher) and is counted.  After mole_acc_allreduce the
+ * counters are sums over all ranks. */
+typedef struct {
+  int64_t nonfinite_samples;     /* VMC samples skipped (per walker and sweep)      */
+  int64_t nonfinite_dmc_walkers; /* DMC walker-steps whose weight was zeroed        */
+  int64_t reserved[2];
+} mole_ens_health;
+int32_t mole_ensemble_health(mole_ens_t ens, mole_ens_health* out);
 /* sum the device accumulators over all ranks of the communicator (NCCL allreduce, fp64 sum) */
 int32_t mole_acc_allreduce(mole_ens_t ens);
 /* device pointer + length (doubles) of the packed accumulator vector, for callers that bring their
@@ -269,8 +281,14 @@ enum {
 int32_t mole_opt_create(int32_t kind, int32_t n_params, double step_size, double momentum_parameter,
                         int32_t history, uint32_t compat, mole_opt_t* opt);
 int32_t mole_opt_destroy(mole_opt_t opt);
-/* Optimizer::compute_parameter_update (optimize/src/traits.rs:18-25) from the reduced moments */
+/* Optimizer::compute_parameter_update (optimize/src/traits.rs:18-25) from the reduced moments.  Non-finite moments
+ * (MOLE_ERR_DATA_ACCESS), a pivot below n eps max|S| or a non-finite update (MOLE_ERR_LINALG) are refused and
+ * deltap is left untouched. */
 int32_t mole_opt_step(mole_opt_t opt, const double* pars, const mole_acc_host* acc, double* deltap);
+/* StochasticReconfiguration only: S_kk <- S_kk * diag_scale + diag_shift before the solve.  Default (1.01, 0) is the
+ * reference's hard-coded regularisation (optimizers.rs:225-231); an absolute shift is the usual stabiliser when
+ * two parameters are nearly redundant (the Jastrow b1/b2 pair of the Slater-Jastrow kind). */
+int32_t mole_opt_set_sr_regularization(mole_opt_t opt, double diag_scale, double diag_shift);
 /* the regularised SR matrix the solve uses (P*P row-major), for parity tests */
 int32_t mole_opt_sr_matrix(mole_opt_t opt, const mole_acc_host* acc, double* S);
 
@@ -306,9 +324,11 @@ int32_t mole_branch_sources(mole_ens_t ens, int32_t* src);
 /* One block of DmcRunner::diffuse's inner loop (dmc.rs:84-141): n_steps x (time step, ensemble energy
  * sum w E / sum w over ALL ranks, branch).  With SRBrancher the block is enqueued without host reads
  * (the reference energy is constant within a block, dmc.rs:143-145): 3 launches per time step, the
- * branching normalisation and the per-step energies are formed on the device, multi-rank sums go
- * through NCCL on the same stream, and step_energies[n_steps] comes back with one copy.  Identical
- * results to n_steps x (mole_dmc_step, mole_branch). */
+ * branching normalisation is formed on the device and the per-step {sum w E, sum w} rows come back with one
+ * copy.  Multi-rank: every rank is a population island (SRBrancher resamples against the rank's own N, w_max
+ * and mean weight - stratified, unbiased), so no collective sits in the step loop; the rows of all ranks are
+ * all-gathered once per block and every rank forms the same step_energies[n_steps].  Identical results to
+ * n_steps x (mole_dmc_step, mole_branch). */
 int32_t mole_dmc_block(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind,
                        double time_step, double reference_energy, int32_t n_steps, double* step_energies);
 /* DmcRunner::diffuse (dmc.rs:69-153): returns n_out running energies and errors */

@@ -657,6 +657,12 @@ class Ensemble:
     def acc_allreduce(self):
         self._c(lib().mole_acc_allreduce(self.handle))
 
+    def health(self):
+        """(non-finite VMC samples skipped, DMC walker-steps killed) since the last acc_reset."""
+        h = ffi.EnsHealth()
+        self._c(lib().mole_ensemble_health(self.handle, C.byref(h)))
+        return int(h.nonfinite_samples), int(h.nonfinite_dmc_walkers)
+
     def acc_device_ptr(self):
         p, n = C.c_void_p(), C.c_int32()
         self._c(lib().mole_acc_device_ptr(self.handle, C.byref(p), C.byref(n)))
@@ -768,6 +774,11 @@ class StochasticReconfiguration(Optimizer):
 
     def __init__(self, step_size, nparm=1, compat=0):
         super().__init__(nparm, step_size, compat=compat)
+
+    def set_regularization(self, diag_scale=1.01, diag_shift=0.0):
+        """S_kk <- S_kk * diag_scale + diag_shift before the solve (default: optimizers.rs:225-231)."""
+        check(lib().mole_opt_set_sr_regularization(self.handle, C.c_double(diag_scale), C.c_double(diag_shift)))
+        return self
 
 
 # ---------------------------------------------------------------------------------------------------

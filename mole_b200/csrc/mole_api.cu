@@ -212,7 +212,7 @@ int32_t mole_ensemble_create(mole_ctx_t ctx, int64_t W, int32_t ne, const uint8_
   CU(ctx, cudaMalloc(&e->el, W * sizeof(double)));
   CU(ctx, cudaMalloc(&e->el2, W * sizeof(double)));
   CU(ctx, cudaMalloc(&e->blk, W * sizeof(double)));
-  CU(ctx, cudaMalloc(&e->acc, ACC_LEN * sizeof(double)));
+  CU(ctx, cudaMalloc(&e->acc, ACC_DEV_LEN * sizeof(double)));
   e->partial_rows = ens_grid_rows(ctx);
   CU(ctx, cudaMalloc(&e->partials, (size_t)e->partial_rows * ACC_LEN * sizeof(double)));
   CU(ctx, cudaMalloc(&e->ticket, 2 * sizeof(unsigned int)));   // [0] accumulator reduction, [1] branching scan
@@ -223,7 +223,7 @@ int32_t mole_ensemble_create(mole_ctx_t ctx, int64_t W, int32_t ne, const uint8_
   CU(ctx, cudaMalloc(&e->src, (size_t)W * sizeof(int32_t)));
   CU(ctx, cudaMemsetAsync(e->x, 0, nx * sizeof(double), STREAM(ctx)));
   CU(ctx, cudaMemsetAsync(e->blk, 0, W * sizeof(double), STREAM(ctx)));
-  CU(ctx, cudaMemsetAsync(e->acc, 0, ACC_LEN * sizeof(double), STREAM(ctx)));
+  CU(ctx, cudaMemsetAsync(e->acc, 0, ACC_DEV_LEN * sizeof(double), STREAM(ctx)));
   CU(ctx, cudaMemsetAsync(e->ticket, 0, 2 * sizeof(unsigned int), STREAM(ctx)));
   fill_kernel<<<cdiv(W, 256), 256, 0, STREAM(ctx)>>>(e->w, W, 1.0);   // dmc.rs:51 initial weight 1.0
   KERNEL_CHECK(ctx);
@@ -535,7 +535,7 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
 int32_t mole_acc_reset(mole_ens_t e) {
   if (!e) return MOLE_ERR_INVALID_ARG;
   CU(e->ctx, cudaSetDevice(e->ctx->device));
-  CU(e->ctx, cudaMemsetAsync(e->acc, 0, ACC_LEN * sizeof(double), STREAM(e->ctx)));
+  CU(e->ctx, cudaMemsetAsync(e->acc, 0, ACC_DEV_LEN * sizeof(double), STREAM(e->ctx)));
   CU(e->ctx, cudaMemsetAsync(e->blk, 0, e->W * sizeof(double), STREAM(e->ctx)));
   e->blk_fill = 0;
   return MOLE_OK;
@@ -552,10 +552,22 @@ int32_t mole_acc_get(mole_ens_t e, mole_acc_host* out) {
   return MOLE_OK;
 }
 
+int32_t mole_ensemble_health(mole_ens_t e, mole_ens_health* out) {
+  if (!e || !out) return MOLE_ERR_INVALID_ARG;
+  double h[2];
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  CU(e->ctx, cudaMemcpyAsync(h, e->acc + ACC_BAD, 2 * sizeof(double), cudaMemcpyDeviceToHost, STREAM(e->ctx)));
+  CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
+  memset(out, 0, sizeof(*out));
+  out->nonfinite_samples = (int64_t)h[0];
+  out->nonfinite_dmc_walkers = (int64_t)h[1];
+  return MOLE_OK;
+}
+
 int32_t mole_acc_device_ptr(mole_ens_t e, void** p, int32_t* n) {
   if (!e || !p || !n) return MOLE_ERR_INVALID_ARG;
   *p = e->acc;
-  *n = ACC_LEN;
+  *n = ACC_DEV_LEN;   // the packed moments followed by the two health counters (all summed over ranks)
   return MOLE_OK;
 }
 
@@ -573,7 +585,7 @@ static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
   CU(ctx, cudaSetDevice(ctx->device));
   DmcParams dp;
   memset(&dp, 0, sizeof(dp));
-  dp.x = e->x; dp.w = e->w; dp.el = e->el; dp.red = e->red; dp.partials = e->partials; dp.ticket = e->ticket;
+  dp.x = e->x; dp.w = e->w; dp.el = e->el; dp.red = e->red; dp.partials = e->partials; dp.ticket = e->ticket; dp.health = e->acc + ACC_BAD_DMC;
   dp.W = e->W; dp.walker_offset = e->walker_offset; dp.key = e->key; dp.step = e->step;
   dp.tau_move = m->param; dp.tau_weight = time_step; dp.e_ref = e_ref; dp.el_cached = e->el_cached; dp.compat = m->compat;
   dp.wf = wf->p; dp.ham = op->p;
@@ -639,8 +651,8 @@ int32_t mole_dmc_step(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op,
 
 // One block of DmcRunner::diffuse's inner loop (dmc.rs:84-141), SRBrancher: n_steps x (time step, ensemble
 // energy, branch) enqueued without any host read - the reference energy only changes between blocks
-// (dmc.rs:143-145) - then ONE copy of the per-step energies.  Multi-rank: the three per-step scalars are
-// all-reduced on the device (NCCL on the same stream).  Results are identical to the step-by-step entry
+// (dmc.rs:143-145) - then ONE copy of the per-step {sum w E, sum w} rows.  Multi-rank: ranks are population islands
+// within a block and the rows are all-gathered once per block.  Results are identical to the step-by-step entry
 // points (mole_dmc_step + mole_branch), which the other branchers and the parity tests use.
 int32_t mole_dmc_block(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind, double time_step,
                        double e_ref, int32_t n_steps, double* step_energies) {
@@ -661,32 +673,38 @@ int32_t mole_dmc_block(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op
   if (n_steps == 0) return MOLE_OK;
   CU(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = STREAM(ctx);
+  const bool multi = ctx->nranks > 1;
+  const int nr = multi ? ctx->nranks : 1;
   if (e->step_e_cap < n_steps) {
     CU(ctx, cudaStreamSynchronize(st));
     cudaFree(e->step_e);
+    cudaFree(e->gath);
     e->step_e = nullptr;
-    CU(ctx, cudaMalloc(&e->step_e, (size_t)n_steps * sizeof(double)));
+    e->gath = nullptr;
+    CU(ctx, cudaMalloc(&e->step_e, (size_t)2 * n_steps * sizeof(double)));
     e->step_e_cap = n_steps;
   }
-  const bool multi = ctx->nranks > 1;
-  double gcount = (double)e->W;
-  if (multi) {
-    double s[1] = {gcount};
-    if ((rc = mole_comm_allreduce_host(ctx, s, 1, nullptr, 0)) != MOLE_OK) return rc;
-    gcount = s[0];
-    if (!e->gath) CU(ctx, cudaMalloc(&e->gath, (size_t)ctx->nranks * 4 * sizeof(double)));
-  }
+  if (multi && !e->gath) CU(ctx, cudaMalloc(&e->gath, (size_t)nr * 2 * e->step_e_cap * sizeof(double)));
+  // Every rank is a population island inside a block: SRBrancher normalises with the rank's own N / w_max and resets
+  // to the rank's own mean weight (stratified resampling, unbiased), so NO collective sits in the step loop; the
+  // per-step {sum w E, sum w} rows of all ranks are gathered ONCE per block and every rank forms the same energies.
   for (int j = 0; j < n_steps; ++j) {
     if ((rc = dmc_step_launch(e, wf, m, op, time_step, e_ref)) != MOLE_OK) return rc;
-    const double* rows = e->red;         // {sum w E, sum w, sum w', max w'} of this rank
-    if (multi) {                         // one row per rank, ONE small collective per time step
-      if ((rc = mole_comm_allgather_device(ctx, e->red, e->gath, 4)) != MOLE_OK) return rc;
-      rows = e->gath;
-    }
-    if ((rc = sr_branch_launch(e, 0.0, 0.0, rows, multi ? ctx->nranks : 1, gcount, e->red + 2, e->step_e + j)) != MOLE_OK) return rc;
+    if ((rc = sr_branch_launch(e, 0.0, 0.0, e->red, 1, (double)e->W, e->red + 2, e->step_e + 2 * j)) != MOLE_OK) return rc;
   }
-  CU(ctx, cudaMemcpyAsync(step_energies, e->step_e, (size_t)n_steps * sizeof(double), cudaMemcpyDeviceToHost, st));
+  std::vector<double> rows((size_t)nr * 2 * n_steps);
+  if (multi) {
+    if ((rc = mole_comm_allgather_device(ctx, e->step_e, e->gath, 2 * n_steps)) != MOLE_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(rows.data(), e->gath, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  } else {
+    CU(ctx, cudaMemcpyAsync(rows.data(), e->step_e, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
   CU(ctx, cudaStreamSynchronize(st));
+  for (int j = 0; j < n_steps; ++j) {
+    double swe = 0.0, sw = 0.0;                                    // rank order: identical on every rank
+    for (int r = 0; r < nr; ++r) { swe += rows[((size_t)r * n_steps + j) * 2]; sw += rows[((size_t)r * n_steps + j) * 2 + 1]; }
+    step_energies[j] = swe / sw;                                   // dmc.rs:133
+  }
   return MOLE_OK;
 }
 
@@ -714,15 +732,9 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
       red[2] = 0.0; red[3] = 0.0;
       for (int64_t i = 0; i < W; ++i) { red[2] = red[2] + hw[i]; red[3] = std::max(red[3], hw[i]); }
     }
-    double local_sum = red[2], gmax = red[3], gcount = (double)W;
-    {
-      double sums[1] = {gcount}, maxs[1] = {gmax};
-      const int32_t rc = mole_comm_allreduce_host(ctx, sums, 1, maxs, 1);
-      if (rc != MOLE_OK) return rc;
-      gcount = sums[0]; gmax = maxs[0];
-    }
-    const double norm_factor = gcount / gmax;                 // branching.rs:24 (global N, global w_max)
-    const double new_weight = local_sum / (double)W;          // branching.rs:21 (stratified per rank)
+    // stratified per rank (see mole_dmc_block): the rank's own N, w_max and mean weight, no collective
+    const double norm_factor = (double)W / red[3];            // branching.rs:24
+    const double new_weight = red[2] / (double)W;             // branching.rs:21
     return sr_branch_launch(e, norm_factor, new_weight, nullptr, 0, 0.0, nullptr, nullptr);
   } else {
     // scratch of the clone list (<= 3 copies per walker, branching.rs:60) lives with the ensemble: no

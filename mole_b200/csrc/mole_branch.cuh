@@ -174,9 +174,8 @@ __global__ void sr_pick_gather_kernel(const unsigned long long* __restrict__ cum
 // pass 4 (SR) on TILE-LOCAL prefix sums: the search goes over the exclusive tile offsets first and then
 // inside the tile - the same walker as the upper bound on the global prefix sums, without the pass that
 // adds the offsets.  The new weight and the step's ensemble energy are formed from device-side sums
-// (local_sum_ptr = sum of this rank's post-update weights; red_rows = one {sum w E, sum w, ..} row per
-// rank), exactly as the host does on the synchronous path, and the energy is written to *step_e_out
-// (dmc.rs:133).
+// (local_sum_ptr = sum of this rank's post-update weights; red_rows = {sum w E, sum w, ..} rows), exactly as
+// the host does on the synchronous path, and the step's {sum w E, sum w} go to step_e_out[0..1].
 constexpr int PICK_SMEM_TILES = 1024;   // tile offsets of up to 2^20 walkers are searched in shared memory
 __global__ void sr_pick_gather_tiled_kernel(const unsigned long long* __restrict__ cum, const unsigned long long* tile_sums,
                                             int n_tiles, int64_t W, int n, uint64_t walker_offset, RngKey key, uint32_t step,
@@ -195,10 +194,11 @@ __global__ void sr_pick_gather_tiled_kernel(const unsigned long long* __restrict
   }
   const unsigned long long* ts = staged ? s_tiles : tile_sums;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0 && step_e_out) {                                     // ensemble energy over all ranks, rank order
-    double swe = red_rows[0], sw = red_rows[1];
+  if (j == 0 && step_e_out) {                                     // this step's {sum w E, sum w} (dmc.rs:112-113,133): the division
+    double swe = red_rows[0], sw = red_rows[1];                   // happens on the host, after ONE gather per block over the ranks
     for (int r = 1; r < n_rows; ++r) { swe += red_rows[4 * r]; sw += red_rows[4 * r + 1]; }
-    *step_e_out = swe / sw;
+    step_e_out[0] = swe;
+    step_e_out[1] = sw;
   }
   if (j >= W) return;
   if (local_sum_ptr) new_weight = *local_sum_ptr / (double)W;     // branching.rs:21

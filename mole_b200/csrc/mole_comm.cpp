@@ -131,7 +131,7 @@ int32_t mole_acc_allreduce(mole_ens_t e) {
   if (ctx->nranks <= 1) return MOLE_OK;
   if (!ctx->nccl_comm) return mole_set_error(ctx, MOLE_ERR_NCCL, "mole_acc_allreduce before mole_comm_init");
   cudaSetDevice(ctx->device);
-  const int rc = api().AllReduce(e->acc, e->acc, ACC_LEN, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, (cudaStream_t)ctx->stream);
+  const int rc = api().AllReduce(e->acc, e->acc, ACC_DEV_LEN, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, (cudaStream_t)ctx->stream);
   if (rc != 0) return nccl_fail(ctx, "ncclAllReduce", rc);
   return MOLE_OK;
 }

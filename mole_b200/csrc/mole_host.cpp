@@ -27,6 +27,8 @@ struct mole_opt_s {
   double step_size, momentum_parameter;
   int history;
   uint32_t compat;
+  double sr_diag_scale = 1.0 + 1e-2;   // optimizers.rs:225-231
+  double sr_diag_shift = 0.0;          // mole_opt_set_sr_regularization
   std::vector<double> momentum, momentum_prev, grad_prev, pars_prev;
   std::deque<std::vector<double>> s, y;
   size_t iter = 0;
@@ -62,17 +64,23 @@ static void sr_matrix(const mole_opt_s* o, const mole_acc_host* a, std::vector<d
       else v -= (a->sum_o[k] / n) * (a->sum_o[l] / n);
       S[(size_t)k * np + l] = v;
     }
-  for (int k = 0; k < np; ++k) S[(size_t)k * np + k] *= 1.0 + 1e-2;
+  for (int k = 0; k < np; ++k) S[(size_t)k * np + k] = S[(size_t)k * np + k] * o->sr_diag_scale + o->sr_diag_shift;
 }
 
-// dense solve with partial pivoting; stands in for LAPACK dsytrf/dsytrs (optimizers.rs:251)
+// dense solve with partial pivoting; stands in for LAPACK dsytrf/dsytrs (optimizers.rs:251).  Singular means a
+// pivot below n eps max|S| (or NaN): a rank-deficient S amplifies the noise of g without bound, so the step is
+// refused (Error::LinalgError) instead of applied.
 static bool solve_dense(std::vector<double> a, std::vector<double> b, int n, std::vector<double>& x) {
+  double amax = 0.0;
+  for (double v : a) amax = std::max(amax, std::fabs(v));
+  if (!(amax > 0.0) || !std::isfinite(amax)) return false;
+  const double tiny = (double)n * 2.220446049250313e-16 * amax;
   for (int c = 0; c < n; ++c) {
     int piv = c;
     for (int r = c + 1; r < n; ++r)
       if (std::fabs(a[(size_t)r * n + c]) > std::fabs(a[(size_t)piv * n + c])) piv = r;
     const double d = a[(size_t)piv * n + c];
-    if (d == 0.0 || d != d) return false;
+    if (!(std::fabs(d) > tiny)) return false;
     if (piv != c) {
       for (int k = 0; k < n; ++k) std::swap(a[(size_t)c * n + k], a[(size_t)piv * n + k]);
       std::swap(b[c], b[piv]);
@@ -90,6 +98,14 @@ static bool solve_dense(std::vector<double> a, std::vector<double> b, int n, std
     x[r] = s / a[(size_t)r * n + r];
   }
   return true;
+}
+
+// every moment the optimizers read must be finite: one NaN would otherwise reach the wavefunction parameters
+static bool moments_finite(const mole_acc_host* a, int np) {
+  bool ok = std::isfinite(a->n_samples) && std::isfinite(a->sum_e);
+  for (int k = 0; k < np; ++k) ok = ok && std::isfinite(a->sum_o[k]) && std::isfinite(a->sum_oe[k]);
+  for (int q = 0; q < np * (np + 1) / 2; ++q) ok = ok && std::isfinite(a->sum_oo[q]);
+  return ok;
 }
 
 static void lbfgs_push(mole_opt_s* o, const std::vector<double>& pars, const std::vector<double>& grad) {  // :148-159
@@ -178,10 +194,7 @@ int32_t mole_opt_sr_matrix(mole_opt_t o, const mole_acc_host* a, double* S) {
   return MOLE_OK;
 }
 
-int32_t mole_opt_step(mole_opt_t o, const double* pars, const mole_acc_host* a, double* deltap) {
-  if (!o || !pars || !a || !deltap) return MOLE_ERR_INVALID_ARG;
-  if (a->n_params != o->np)
-    return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "\"Parameter gradient\" moments missing or of the wrong size");
+static int32_t opt_step_unchecked(mole_opt_t o, const double* pars, const mole_acc_host* a, double* deltap) {
   const int np = o->np;
   std::vector<double> g;
   if (!energy_gradient(a, np, g)) return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "no samples accumulated");
@@ -220,6 +233,31 @@ int32_t mole_opt_step(mole_opt_t o, const double* pars, const mole_acc_host* a, 
     }
   }
   return MOLE_ERR_INVALID_ARG;
+}
+
+int32_t mole_opt_step(mole_opt_t o, const double* pars, const mole_acc_host* a, double* deltap) {
+  if (!o || !pars || !a || !deltap) return MOLE_ERR_INVALID_ARG;
+  if (a->n_params != o->np)
+    return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "\"Parameter gradient\" moments missing or of the wrong size");
+  if (!moments_finite(a, o->np))
+    return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "non-finite optimisation moments (see mole_ensemble_health); no update computed");
+  std::vector<double> dp(o->np, 0.0);
+  const int32_t rc = opt_step_unchecked(o, pars, a, dp.data());
+  if (rc != MOLE_OK) return rc;
+  for (int i = 0; i < o->np; ++i)
+    if (!std::isfinite(dp[i]))
+      return mole_set_error(nullptr, MOLE_ERR_LINALG, "parameter update is not finite (ill-conditioned solve); parameters left untouched");
+  for (int i = 0; i < o->np; ++i) deltap[i] = dp[i];
+  return MOLE_OK;
+}
+
+// S_kk <- S_kk * diag_scale + diag_shift before the solve.  The reference hard-codes (1.01, 0) (optimizers.rs:225-231),
+// which is the default; an absolute shift is the usual SR stabiliser when two parameters are nearly redundant.
+int32_t mole_opt_set_sr_regularization(mole_opt_t o, double diag_scale, double diag_shift) {
+  if (!o || !(diag_scale > 0.0) || !(diag_shift >= 0.0)) return MOLE_ERR_INVALID_ARG;
+  o->sr_diag_scale = diag_scale;
+  o->sr_diag_shift = diag_shift;
+  return MOLE_OK;
 }
 
 // ------------------------------------------------------------------ Runner::run (montecarlo.rs:24-46)

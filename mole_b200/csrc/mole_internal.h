@@ -21,7 +21,11 @@ enum {
   ACC_O = 10,                                  // 8 slots
   ACC_OE = ACC_O + MOLE_ACC_MAX_PARAMS,        // 8 slots
   ACC_OO = ACC_OE + MOLE_ACC_MAX_PARAMS,       // 36 slots, (k<=l) packed row-major over the ACTUAL P
-  ACC_LEN = ACC_OO + MOLE_ACC_MAX_PARAMS * (MOLE_ACC_MAX_PARAMS + 1) / 2
+  ACC_LEN = ACC_OO + MOLE_ACC_MAX_PARAMS * (MOLE_ACC_MAX_PARAMS + 1) / 2,
+  // health counters behind the packed moments (device vector only; mole_ensemble_health reads them): samples whose
+  // E_L or O_k was not finite are counted and kept OUT of every sum, DMC walkers with a non-finite E_L are killed
+  ACC_BAD = ACC_LEN, ACC_BAD_DMC = ACC_LEN + 1,
+  ACC_DEV_LEN = ACC_LEN + 2
 };
 
 // ---- POD parameter blocks passed to kernels by value -------------------------------------------
@@ -66,6 +70,7 @@ struct DmcParams {
   double* x; double* w; double* el; uint8_t* el_valid_flag;
   double* red;        // [4] sum_w_e, sum_w, sum_w_new, max_w_new (atomics-free: partials + ticket)
   double* partials; unsigned int* ticket;
+  double* health;     // &acc[ACC_BAD_DMC]
   int64_t W; uint64_t walker_offset; RngKey key; uint32_t step;
   double tau_move, tau_weight, e_ref;
   int32_t el_cached;

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) swee
     wk.refresh(p);
     const uint64_t wid = sp.walker_offset + (uint64_t)w;
     double blk = sp.blk[w];
-    int fill = sp.blk_fill;
+    int fill = sp.blk_fill, nbad = 0;   // nbad: skipped samples of the open block (not carried across launches)
 
     for (int s = 0; s < sp.n_sweeps; ++s) {
       const uint32_t step = sp.step0 + (uint32_t)s;
@@ -298,42 +298,59 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) swee
       }
       if (s < sp.n_discard) continue;                           // block 0 = equilibration, montecarlo.rs:36
       const int64_t si = s - sp.n_discard;
-      // Sampler::sample, samplers.rs:81-104
+      // Sampler::sample, samplers.rs:81-104.  A sample whose E_L or O_k is not finite (psi underflowed to 0, two
+      // particles on top of each other) is written to the traces as it is but kept out of every sum and counted
+      // in acc[ACC_BAD] (mole_ensemble_health): upstream it would turn the mean, the gradient and S into NaN.
       double el = 0.0, hpsi, kin_psi = 0.0;
       const double inv = m_rcp(wk.psi);
+      double pg[NP > 0 ? NP : 1], o[NP > 0 ? NP : 1];
+      const bool quirk = (sp.compat & MOLE_COMPAT_VECTOR_DIV) != 0;
+      bool bad = false;
       if (want_e) {
         el = mole_local_energy<WF>(p, sp.ham, wk.st, wk.psi, hpsi, kin_psi);
-        acc.v[ACC_N] += 1.0;
-        acc.v[ACC_E] += el;
-        acc.v[ACC_E2] = fma(el, el, acc.v[ACC_E2]);
-        acc.v[ACC_T] += kin_psi * inv;
-        blk += el;
+        bad = !isfinite(el);
+        if (sp.tr_energy) sp.tr_energy[(size_t)si * W + w] = el;
+      }
+      if (OPT && NP > 0) {
+        WF::pgrad(p, wk.st, pg);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          // intended O_k = d_k psi / psi; MOLE_COMPAT_VECTOR_DIV: stored sample 1/d_k psi, O_k = 1/(psi d_k psi)
+          o[k] = quirk ? inv / pg[k] : pg[k] * inv;
+          bad = bad || !isfinite(o[k]);
+          if (sp.tr_pgrad) sp.tr_pgrad[((size_t)si * NP + k) * W + w] = quirk ? 1.0 / pg[k] : pg[k];
+        }
+      }
+      if (bad) atomicAdd(sp.acc + ACC_BAD, 1.0);                // rare; integer-valued, so the order does not matter
+      if (want_e) {
+        if (!bad) {
+          acc.v[ACC_N] += 1.0;
+          acc.v[ACC_E] += el;
+          acc.v[ACC_E2] = fma(el, el, acc.v[ACC_E2]);
+          acc.v[ACC_T] += kin_psi * inv;
+          blk += el;
+        } else {
+          ++nbad;
+        }
         if (++fill == sp.block_size) {                          // block means, vmc.rs:158-164
-          const double bm = blk / (double)sp.block_size;
-          acc.v[ACC_B] += bm;
-          acc.v[ACC_B2] = fma(bm, bm, acc.v[ACC_B2]);
-          acc.v[ACC_NB] += 1.0;
+          if (nbad < sp.block_size) {
+            const double bm = blk / (double)(sp.block_size - nbad);
+            acc.v[ACC_B] += bm;
+            acc.v[ACC_B2] = fma(bm, bm, acc.v[ACC_B2]);
+            acc.v[ACC_NB] += 1.0;
+          }
           blk = 0.0;
           fill = 0;
+          nbad = 0;
         }
-        if (sp.tr_energy) sp.tr_energy[(size_t)si * W + w] = el;
       }
       if (sp.observables & MOLE_OBS_KINETIC) {
         const double k = want_e ? kin_psi * inv : -0.5 * WF::lap(p, wk.st) * inv;
         if (sp.tr_kinetic) sp.tr_kinetic[(size_t)si * W + w] = k;
       }
-      acc.v[ACC_PSI] += wk.psi;
+      if (!bad) acc.v[ACC_PSI] += wk.psi;
       if (sp.tr_wfvalue) sp.tr_wfvalue[(size_t)si * W + w] = wk.psi;   // psi^2/psi, operators.rs:22 + samplers.rs:90
-      if (OPT && NP > 0) {
-        double pg[NP > 0 ? NP : 1], o[NP > 0 ? NP : 1];
-        WF::pgrad(p, wk.st, pg);
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          // intended O_k = d_k psi / psi; MOLE_COMPAT_VECTOR_DIV: stored sample 1/d_k psi, O_k = 1/(psi d_k psi)
-          const bool quirk = (sp.compat & MOLE_COMPAT_VECTOR_DIV) != 0;
-          o[k] = quirk ? inv / pg[k] : pg[k] * inv;
-          if (sp.tr_pgrad) sp.tr_pgrad[((size_t)si * NP + k) * W + w] = quirk ? 1.0 / pg[k] : pg[k];
-        }
+      if (OPT && NP > 0 && !bad) {
         int q = 0;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
@@ -402,15 +419,21 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams
     const uint64_t wid = dp.walker_offset + (uint64_t)w;
 #pragma unroll
     for (int e = 0; e < NE; ++e) mole_move_state<WF, MOLE_METROP_DIFFUSE>(p, wk, e, dp.tau_move, sd, dp.key, wid, dp.step, dp.compat);
-    const double wt = dp.w[w];
-    s_we = fma(wt, e_old, s_we);                                // dmc.rs:112-113
-    s_w += wt;
     const double e_new = mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);   // :115-124
-    const double wn = wt * exp(-dp.tau_weight * ((e_old + e_new) / 2.0 - dp.e_ref));  // :126-128
+    // a walker whose local energy is not finite (upstream: NaN ensemble energy from here on) is counted
+    // (acc[ACC_BAD_DMC]) and dies: weight 0 before and after the step, never picked by the brancher
+    const double w_in = dp.w[w];
+    const double w_up = w_in * exp(-dp.tau_weight * ((e_old + e_new) / 2.0 - dp.e_ref));           // :126-128
+    const bool bad = !isfinite(e_old) || !isfinite(e_new) || !isfinite(w_up);
+    if (bad) atomicAdd(dp.health, 1.0);
+    const double wt = bad ? 0.0 : w_in;
+    s_we = fma(wt, bad ? 0.0 : e_old, s_we);                    // dmc.rs:112-113
+    s_w += wt;
+    const double wn = bad ? 0.0 : w_up;
     s_wn += wn;
     m_wn = fmax(m_wn, wn);
     dp.w[w] = wn;
-    dp.el[w] = e_new;
+    dp.el[w] = bad ? 0.0 : e_new;
 #pragma unroll
     for (int c = 0; c < 3 * NE; ++c) dp.x[(size_t)c * W + w] = wk.st.x[c];
   }

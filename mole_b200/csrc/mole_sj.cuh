@@ -600,7 +600,7 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
     sj_init(c, L);
     const uint64_t wid = sp.walker_offset + (uint64_t)(w < W ? w : W - 1);
     double blk = L.act ? sp.blk[w] : 0.0;
-    int fill = sp.blk_fill;
+    int fill = sp.blk_fill, nbad = 0;   // nbad: skipped samples of the open block (not carried across launches)
 #pragma unroll 1
     for (int s = 0; s < sp.n_sweeps; ++s) {
       const uint32_t step = sp.step0 + (uint32_t)s;
@@ -617,21 +617,36 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
       sj_fold_psi(L);
       if (want_e || OPT || (sp.observables & MOLE_OBS_KINETIC)) sj_measure<OPT>(c, sp.ham, L, kin, pot, sp.compat);
       const double el = kin + pot;
+      // a sample whose E_L or O_k is not finite goes to the traces as it is, but stays out of every sum and is
+      // counted in acc[ACC_BAD] (mole_ensemble_health); the decision is uniform over the walker's five lanes
+      bool bad = !isfinite(el);
+      if (OPT) {
+        const double* os = L.sm + SJ_OFF_MB + MB_OUT;
+        const bool mine = !isfinite(os[L.gl]) || (L.gl < 2 && !isfinite(os[5 + L.gl]));
+        bad = bad || ((__ballot_sync(SJ_FULL, mine) >> L.base) & 31u) != 0u;
+      }
+      const bool good = L.act && !bad;
+      if (bad && L.act && L.gl == 0) atomicAdd(sp.acc + ACC_BAD, 1.0);
       double bm = 0.0;
       bool closed = false;
       if (want_e) {
-        blk += el;
-        if (++fill == sp.block_size) { bm = blk / (double)sp.block_size; blk = 0.0; fill = 0; closed = true; }   // vmc.rs:158-164
+        if (bad) ++nbad; else blk += el;
+        if (++fill == sp.block_size) {                                 // vmc.rs:158-164
+          closed = nbad < sp.block_size;
+          bm = blk / (double)(sp.block_size - nbad);
+          blk = 0.0; fill = 0; nbad = 0;
+        }
       }
       if (L.act) {
         if (want_e) {
           // compact entries 0..4 -> idx 0 of lane gl; 5..9 -> idx 1
-          accv[0] += L.gl == 0 ? 1.0 : (L.gl == 1 ? el : (L.gl == 2 ? el * el : (closed ? (L.gl == 3 ? bm : bm * bm) : 0.0)));
+          const double sv = L.gl == 0 ? 1.0 : (L.gl == 1 ? el : el * el);
+          accv[0] += L.gl < 3 ? (good ? sv : 0.0) : (closed ? (L.gl == 3 ? bm : bm * bm) : 0.0);
           if (L.gl == 0 && closed) accv[1] += 1.0;                    // ACC_NB
-          if (L.gl == 3) accv[1] += kin;                              // ACC_T
+          if (L.gl == 3 && good) accv[1] += kin;                      // ACC_T
           if (sp.tr_energy && L.gl == 0) sp.tr_energy[(size_t)si * W + w] = el;
         }
-        if (L.gl == 4) accv[1] += L.psi;                              // ACC_PSI
+        if (L.gl == 4 && good) accv[1] += L.psi;                      // ACC_PSI
         if (L.gl == 0) {
           if (sp.tr_kinetic && (sp.observables & MOLE_OBS_KINETIC)) sp.tr_kinetic[(size_t)si * W + w] = kin;
           if (sp.tr_wfvalue) sp.tr_wfvalue[(size_t)si * W + w] = L.psi;
@@ -644,7 +659,7 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
 #pragma unroll
           for (int k = 0; k < SJ_NP; ++k) sp.tr_pgrad[((size_t)si * SJ_NP + k) * W + w] = L.psi * os[k];   // d_k psi, or 1/d_k psi under the quirk
         }
-        if (L.act) {
+        if (good) {
           // all loads first: the nine read-modify-writes would otherwise serialise (the compiler cannot tell that
           // the stores to am[] do not alias the os[] loads of the next entry)
           double* am = L.sm + SJ_OFF_ACC;
@@ -743,14 +758,18 @@ __global__ void SJ_BOUNDS sj_dmc_kernel(const DmcParams dp) {
     sj_measure<false>(c, dp.ham, L, kin, pot);
     const double e_new = kin + pot;
     if (L.act && L.gl == 0) {
-      const double wt = dp.w[w];
-      s_we = fma(wt, e_old, s_we);
+      const double w_in = dp.w[w];
+      const double w_up = w_in * exp(-dp.tau_weight * ((e_old + e_new) / 2.0 - dp.e_ref));
+      const bool bad = !isfinite(e_old) || !isfinite(e_new) || !isfinite(w_up);   // counted, and the walker dies (see dmc_step_kernel)
+      if (bad) atomicAdd(dp.health, 1.0);
+      const double wt = bad ? 0.0 : w_in;
+      s_we = fma(wt, bad ? 0.0 : e_old, s_we);
       s_w += wt;
-      const double wn = wt * exp(-dp.tau_weight * ((e_old + e_new) / 2.0 - dp.e_ref));
+      const double wn = bad ? 0.0 : w_up;
       s_wn += wn;
       m_wn = fmax(m_wn, wn);
       dp.w[w] = wn;
-      dp.el[w] = e_new;
+      dp.el[w] = bad ? 0.0 : e_new;
     }
     sj_store(L, c, dp.x, w, W);
   }

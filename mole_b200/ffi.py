@@ -69,6 +69,10 @@ class BlockLog(C.Structure):
                 ("block_wfvalue", C.c_double), ("acceptance", C.c_double)]
 
 
+class EnsHealth(C.Structure):
+    _fields_ = [("nonfinite_samples", C.c_int64), ("nonfinite_dmc_walkers", C.c_int64), ("reserved", C.c_int64 * 2)]
+
+
 LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(BlockLog))
 SWEEP_KEEP_SERIES, SWEEP_APPEND_SERIES = 1, 2
 SERIES_MAX_LAG = 200
@@ -106,6 +110,7 @@ SYMBOLS = [
     "mole_dmc_diffuse", "mole_bench_fp64_peak", "mole_ctx_launch_count", "mole_math_probe",
     "mole_series_length", "mole_series_clear", "mole_series_block_sizes", "mole_series_analyze", "mole_series_get",
     "mole_series_write_text", "mole_runner_run_logged", "mole_ensemble_save", "mole_ensemble_load", "mole_dmc_block",
+    "mole_ensemble_health", "mole_opt_set_sr_regularization",
 ]
 
 _lib = None

@@ -33,6 +33,7 @@ def test_struct_layouts_match_header(mole):
     assert C.sizeof(mole.ffi.OpDesc) == 8 + 24 * 8 + 8 * 4 + 8
     assert C.sizeof(mole.ffi.AccHost) == 62 * 8 + 8
     assert C.sizeof(mole.ffi.SweepArgs) == 24 + 5 * 8
+    assert C.sizeof(mole.ffi.EnsHealth) == 32
 
 
 def test_no_cpu_fallback(mole):
@@ -139,6 +140,44 @@ def test_optimizer_errors(mole):
     with pytest.raises(mole.MoleError) as ei:
         opt.compute_parameter_update(np.zeros(2), acc)
     assert ei.value.code == mole.ffi.ERR_LINALG
+
+
+def test_optimizer_refuses_poisoned_or_rank_deficient_moments(mole):
+    """VERDICT r1 weak#1 / ADVICE: one non-finite moment, a numerically singular S or a non-finite update must
+    fail loudly (Error::DataAccessError / Error::LinalgError) and leave deltap alone -- never reach the parameters."""
+    rng = np.random.default_rng(3)
+    P, W, ns = 3, 4, 100
+    en = -1.0 + 0.1 * rng.normal(size=(W, ns))
+    o = rng.normal(size=(W, ns, P))
+    good = _acc_from_samples(mole, en, o, 10)
+    for opt in (mole.SteepestDescent(1e-2, P), mole.StochasticReconfiguration(0.1, P)):
+        assert np.all(np.isfinite(opt.compute_parameter_update(np.zeros(P), good)))
+        for field, idx in (("sum_oe", 1), ("sum_oo", 2), ("sum_o", 0), ("sum_e", None)):
+            acc = _acc_from_samples(mole, en, o, 10)
+            if idx is None:
+                setattr(acc, field, float("nan"))
+            else:
+                getattr(acc, field)[idx] = float("inf")
+            with pytest.raises(mole.MoleError) as ei:
+                opt.compute_parameter_update(np.zeros(P), acc)
+            assert ei.value.code == mole.ffi.ERR_DATA_ACCESS and "non-finite" in str(ei.value)
+    # two identical parameters: S is rank deficient to rounding; the reference's 1.01 diagonal keeps it solvable,
+    # scale 1.0 does not -> refused; an absolute shift makes it well conditioned again
+    o2 = np.concatenate([o[:, :, :1], o[:, :, :1], o[:, :, 1:2]], axis=2)
+    acc = _acc_from_samples(mole, en, o2, 10)
+    opt = mole.StochasticReconfiguration(0.1, P)
+    assert np.all(np.isfinite(opt.compute_parameter_update(np.zeros(P), acc)))
+    opt.set_regularization(1.0, 0.0)
+    with pytest.raises(mole.MoleError) as ei:
+        opt.compute_parameter_update(np.zeros(P), acc)
+    assert ei.value.code == mole.ffi.ERR_LINALG
+    opt.set_regularization(1.0, 1e-3)
+    dp = opt.compute_parameter_update(np.zeros(P), acc)
+    S = opt.sr_matrix(acc)
+    assert np.all(np.isfinite(dp)) and np.linalg.cond(S) < 1e5
+    assert abs(dp[0] - dp[1]) < 1e-9 * max(1.0, abs(dp[0]))   # the redundant pair moves together
+    with pytest.raises(mole.MoleError):
+        opt.set_regularization(0.0, 0.0)
 
 
 def test_series_block_sizes_match_statfor_schedule(mole, orc):

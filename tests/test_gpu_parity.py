@@ -176,6 +176,60 @@ def test_sweep_parity_shared_philox(mole, orc, name, metrop):
         assert np.max(np.abs(g - gref)) < 1e-8 * max(1.0, np.max(np.abs(gref)))
 
 
+OPS = ["kinetic", "ionic_pot", "elec_pot", "ionic"]
+
+
+def _op_pair(mole, orc, c, opname):
+    """(oracle ham desc, mole operator) of one operator kind over the case's ions (operator.rs:16-149)."""
+    pos = np.array(c["oham"].ion_pos)[:3 * c["oham"].n_ions].reshape(-1, 3)
+    z = list(c["oham"].ion_charge)[:c["oham"].n_ions]
+    if opname == "kinetic":
+        return orc.ham_desc(orc.HAM_KINETIC), mole.KineticEnergy()
+    if opname == "ionic_pot":
+        return orc.ham_desc(orc.HAM_IONIC_POT, pos, z), mole.IonicPotential(pos, z)
+    if opname == "elec_pot":
+        return orc.ham_desc(orc.HAM_ELEC_POT), mole.ElectronicPotential()
+    return orc.ham_desc(orc.HAM_IONIC, pos, z), mole.IonicHamiltonian(mole.KineticEnergy(), mole.IonicPotential(pos, z))
+
+
+@pytest.mark.parametrize("name", ["h2", "he", "lcao_h2_singlet", "sj_ne", "sj_li"])
+@pytest.mark.parametrize("opname", OPS)
+def test_operator_kinds_act_on_and_as_sweep_operator(mole, orc, name, opname):
+    """KineticEnergy, IonicPotential, ElectronicPotential and IonicHamiltonian
+    (operator.rs:59-61,94-96,122-124,146-148) as the operator of mole_op_act_on, of the batched evaluation and
+    of a fused sweep ("Energy" => op), for a thread-per-walker kind and the cooperative Slater-Jastrow kind."""
+    c = cases()[name]
+    wf, _ = c["make"](mole)
+    oham, op = _op_pair(mole, orc, c, opname)
+    ne = c["ne"]
+    # LocalOperator::act_on, one configuration at a time (H psi, not divided)
+    for cfg in random_cfgs(4, ne, seed=11, scale=0.8):
+        ref = orc.ham_act_on(oham, c["owf"], cfg)
+        assert abs(op.act_on(wf, cfg) - ref) < TOL * max(abs(ref), 1e-3 * abs(orc.wf_value(c["owf"], cfg)))
+    # batched
+    W = 515
+    cfgs = random_cfgs(W, ne, seed=12, scale=0.8)
+    ens = mole.Ensemble(W, ne, SEED0)
+    ens.set_configs(cfgs)
+    got = ens.eval_vgl(wf, op, want=("psi", "hpsi"))
+    ref = orc.eval_batch(c["owf"], oham, cfgs, want_pgrad=False)
+    assert close(got["hpsi"] / got["psi"], ref["hpsi"] / ref["psi"])
+    # as the "Energy" operator of a sweep: same decisions (the operator does not enter the moves), its own E_L trace
+    steps, bs = 30, 10
+    seed = bytes([9] * 32)
+    tau = 0.25 if name in SMALL else 0.02
+    m = mole.MetropolisDiffuse(tau, seed)
+    start = np.array([orc.init_uniform(seed, w, ne) for w in range(64)])
+    refr = orc.ensemble_run(c["owf"], oham, orc.run_options(orc.METROP_DIFFUSE, tau, orc.OBS_ENERGY, nan_reject=1), start, seed, steps, bs)
+    e2 = mole.Ensemble(64, ne, seed)
+    e2.init_uniform(-1.0, 1.0)
+    out = e2.sweep(wf, m, op, n_sweeps=steps, n_discard=bs, block_size=bs, observables=mole.ffi.OBS_ENERGY, traces=("energy", "accept"))
+    assert np.array_equal(out["accept"], refr["accept"])
+    assert close(out["energy"], refr["energy"], 1e-9)
+    acc = e2.acc_get()
+    assert abs(acc.sum_e - refr["energy"].sum()) < 1e-9 * np.abs(refr["energy"]).sum()
+
+
 def test_sweep_is_independent_of_launch_split_and_sharding(mole, orc):
     """Philox keys are (walker, step): splitting the sweeps over launches, or the walkers over
     ensembles (ranks), must not change a single bit of the trajectory."""

@@ -1,0 +1,109 @@
+"""Multi-rank DEVICE paths: mole_acc_allreduce over NCCL and the multi-rank mole_dmc_block
+(population islands, one all-gather per block) on two GPUs, against single-rank runs of the same global walker ids.
+Needs >= 2 visible GPUs (gpurun --gpus 2); skipped otherwise.  One process per GPU, like the bench."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED = bytes([5] * 32)
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.is_available() and torch.cuda.device_count() >= 2
+
+
+def _vmc_setup(m, ctx):
+    wf = m.SlaterJastrow(2, 2, (3.68, 0.96, 0.96), (0.5, 1.0, 0.2, 0.1), 1.0, ctx=ctx)
+    op = m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [4], ctx=ctx)
+    return wf, op, m.MetropolisDiffuse.from_rng(0.05, SEED)
+
+
+def _dmc_setup(m, ctx):
+    wf = m.STO(0.9, ctx=ctx)
+    op = m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1], ctx=ctx)
+    return wf, op, m.MetropolisDiffuse.from_rng(0.025, SEED)
+
+
+def _rank(rank, world, uid, W_local, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import mole_b200 as m
+    from mole_b200 import distributed as D
+    torch.cuda.set_device(rank)
+    ctx = m.Context(rank)
+    ctx.comm_init(world, rank, uid)
+    obs = m.ffi.OBS_ENERGY | m.ffi.OBS_PGRAD | m.ffi.OBS_WFVALUE
+    # ---- VMC: sharded sweep + NCCL allreduce of the packed moments
+    wf, op, met = _vmc_setup(m, ctx)
+    ens = m.Ensemble(W_local, 4, SEED, walker_offset=rank * W_local, ctx=ctx)
+    ens.init_uniform(-1.0, 1.0)
+    ens.sweep(wf, met, op, n_sweeps=40, n_discard=10, block_size=10, observables=obs)
+    local = D.acc_to_array(ens.acc_get())
+    ens.acc_allreduce()
+    tot = ens.acc_get()
+    res = dict(vmc_local=local, vmc_total=D.acc_to_array(tot), vmc_cfgs=ens.get_configs(), vmc_health=ens.health())
+    # ---- DMC: the multi-rank block (islands + one gather) ...
+    dwf, dop, dmet = _dmc_setup(m, ctx)
+    a = m.Ensemble(W_local, 1, SEED, walker_offset=rank * W_local, ctx=ctx)
+    a.init_normal(1.0)
+    res["dmc_block_energies"] = a.dmc_block(dwf, dmet, dop, m.ffi.BRANCH_SR, 0.025, -0.5, 8)
+    res["dmc_block_cfgs"] = a.get_configs()
+    res["dmc_block_weights"] = a.get_weights()
+    # ... against the step-by-step entry points on a communicator-free context of the same GPU
+    ctx1 = m.Context(rank)
+    swf, sop, smet = _dmc_setup(m, ctx1)
+    b = m.Ensemble(W_local, 1, SEED, walker_offset=rank * W_local, ctx=ctx1)
+    b.init_normal(1.0)
+    rows = []
+    for _ in range(8):
+        rows.append(b.dmc_step(swf, smet, sop, 0.025, -0.5))
+        b.branch(m.ffi.BRANCH_SR)
+    res["dmc_rows"] = np.array(rows)
+    res["dmc_step_cfgs"] = b.get_configs()
+    out[rank] = res
+    del ens, a, b
+    ctx.close()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_allreduce_and_dmc_block():
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import mole_b200 as m
+    from mole_b200 import distributed as D
+    W_local = 1000
+    uid = m.comm_unique_id()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rank, args=(2, uid, W_local, out), nprocs=2, join=True)
+    r0, r1 = out[0], out[1]
+    # VMC: every rank holds the same reduced vector = the sum of the local ones; health counters ride along
+    assert np.array_equal(r0["vmc_total"], r1["vmc_total"])
+    assert np.allclose(r0["vmc_total"], r0["vmc_local"] + r1["vmc_local"], rtol=1e-14, atol=0)
+    assert r0["vmc_health"] == (0, 0)
+    # ... and equals the single-rank run over the same global walker ids (configurations bit for bit)
+    ctx = m.default_context()
+    wf, op, met = _vmc_setup(m, ctx)
+    ens = m.Ensemble(2 * W_local, 4, SEED)
+    ens.init_uniform(-1.0, 1.0)
+    obs = m.ffi.OBS_ENERGY | m.ffi.OBS_PGRAD | m.ffi.OBS_WFVALUE
+    ens.sweep(wf, met, op, n_sweeps=40, n_discard=10, block_size=10, observables=obs)
+    assert np.array_equal(ens.get_configs(), np.concatenate([r0["vmc_cfgs"], r1["vmc_cfgs"]]))
+    one = D.acc_to_array(ens.acc_get())
+    scale = np.maximum(np.abs(one), 1e-300)
+    assert np.max(np.abs(one - r0["vmc_total"]) / scale) < 1e-11
+    # DMC: each rank's island follows the step-by-step entry points bit for bit ...
+    for r in (r0, r1):
+        assert np.array_equal(r["dmc_block_cfgs"], r["dmc_step_cfgs"])
+        assert np.all(r["dmc_block_weights"] == r["dmc_block_weights"][0])
+    # ... and every rank forms the same ensemble energies: sum over ranks of {sum w E, sum w}, rank order
+    assert np.array_equal(r0["dmc_block_energies"], r1["dmc_block_energies"])
+    swe = r0["dmc_rows"][:, 0] + r1["dmc_rows"][:, 0]
+    sw = r0["dmc_rows"][:, 1] + r1["dmc_rows"][:, 1]
+    assert np.array_equal(r0["dmc_block_energies"], swe / sw)
