@@ -42,8 +42,8 @@ SR_DIAG = (1.01, 1e-2)  # S_kk <- 1.01 S_kk + 1e-2 (reference: 1.01, 0)
 E_WINDOW = (-129.2, -127.0)   # Ne: exact -128.94; this trial function starts near -128.1
 SEED = bytes(32)
 FLOPS = json.load(open(os.path.join(ROOT, "bench_data", "flops.json")))
-# DMC (BASELINE.json configs[3], examples/dmc.rs:189-210): H atom, Gaussian guide at its VMC optimum a = 8/(9 pi)
-DMC_A = 8.0 / (9.0 * np.pi)
+# DMC (BASELINE.json configs[3], examples/dmc.rs:189-210): H atom, Gaussian guide at its VMC optimum 1/a^2 = 8/(9 pi)
+DMC_A = float(np.sqrt(9.0 * np.pi / 8.0))   # psi = exp(-(r/a)^2), examples/dmc.rs:44-57: optimum 1/a^2 = 8/(9 pi)
 DMC_TAU = 0.025
 DMC_EREF = -0.4244      # <E> of the optimal Gaussian: -4/(3 pi)
 DMC_SEED = bytes([1] * 32)
@@ -109,7 +109,7 @@ def dmc_config(args, world, walkers=None, steps=None, bounded=False):
     steps = args.dmc_steps if steps is None else steps
     cfg = {"workload": "h_atom_dmc_sr_brancher (BASELINE.json configs[3], examples/dmc.rs:189-210): H atom, %s guide, "
                        "MetropolisDiffuse tau=%.3g, SRBrancher, E_ref updated between blocks" % (
-                           "Gaussian a=8/(9 pi)" if args.dmc_guide == "gaussian" else "1s STO alpha=0.9", DMC_TAU),
+                           "Gaussian 1/a^2=8/(9 pi)" if args.dmc_guide == "gaussian" else "1s STO alpha=0.9", DMC_TAU),
            "walkers_per_gpu": walkers, "global_walkers": walkers * world, "time_steps_per_step": steps,
            "parallelism": "walkers sharded (population islands, one all-gather per block), dp%d" % world,
            "cache": "L2 flushed between timed steps (256 MiB write)"}

@@ -65,6 +65,10 @@ int32_t mole_ctx_create(int32_t device, mole_ctx_t* out) {
                           "device is not sm_100 (B200): this library ships sm_100a code only");
   cudaStream_t s;
   CU(nullptr, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  // opt-ins to more than 48 KB of dynamic shared memory are per device: set them when the context is made, not
+  // behind process-wide flags (a second context on another GPU, or on another thread, needs them too)
+  CU(nullptr, sj_set_kernel_attributes());
+  CU(nullptr, cudaFuncSetAttribute(simple_remove_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   mole_ctx_s* c = new mole_ctx_s();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
@@ -452,6 +456,7 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
   if (wf->p.kind == MOLE_WF_CONSTANT && m->kind == MOLE_METROP_DIFFUSE)
     return mole_set_error(ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
   if (a->n_sweeps == 0) return MOLE_OK;
+  MOLE_RANGE("mole_sweep");
   CU(ctx, cudaSetDevice(ctx->device));
 
   const int64_t W = e->W;
@@ -543,6 +548,7 @@ int32_t mole_acc_reset(mole_ens_t e) {
 
 int32_t mole_acc_get(mole_ens_t e, mole_acc_host* out) {
   if (!e || !out) return MOLE_ERR_INVALID_ARG;
+  MOLE_RANGE("mole_acc_get");
   static_assert(sizeof(mole_acc_host) == ACC_LEN * sizeof(double) + 2 * sizeof(int32_t), "acc layout");
   CU(e->ctx, cudaSetDevice(e->ctx->device));
   CU(e->ctx, cudaMemcpyAsync(out, e->acc, ACC_LEN * sizeof(double), cudaMemcpyDeviceToHost, STREAM(e->ctx)));
@@ -582,11 +588,16 @@ static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
   if (m->kind != MOLE_METROP_DIFFUSE) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "DmcRunner takes a MetropolisDiffuse (dmc.rs:28)");
   if (wf->p.ne != e->ne) return mole_set_error(ctx, MOLE_ERR_SHAPE, "wavefunction / ensemble electron count mismatch");
   if (wf->p.kind == MOLE_WF_CONSTANT) return mole_set_error(ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
+  MOLE_RANGE("mole_dmc_step");
   CU(ctx, cudaSetDevice(ctx->device));
   DmcParams dp;
   memset(&dp, 0, sizeof(dp));
   dp.x = e->x; dp.w = e->w; dp.el = e->el; dp.red = e->red; dp.partials = e->partials; dp.ticket = e->ticket; dp.health = e->acc + ACC_BAD_DMC;
   dp.W = e->W; dp.walker_offset = e->walker_offset; dp.key = e->key; dp.step = e->step;
+  // E_old is carried from the previous step (it equals that step's E_new) - only for the same trial function and operator
+  const uint64_t sig = mole_el_signature(wf->p, op->p);
+  if (e->el_sig != sig) e->el_cached = 0;
+  e->el_sig = sig;
   dp.tau_move = m->param; dp.tau_weight = time_step; dp.e_ref = e_ref; dp.el_cached = e->el_cached; dp.compat = m->compat;
   dp.wf = wf->p; dp.ham = op->p;
   if (wf->p.kind == K_SLATER_JASTROW) {
@@ -614,6 +625,7 @@ static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
 static int32_t sr_branch_launch(mole_ens_t e, double norm_factor, double new_weight, const double* red_rows, int n_rows,
                                 double gcount, const double* local_sum_ptr, double* step_e_out) {
   mole_ctx_s* ctx = e->ctx;
+  MOLE_RANGE("mole_branch_sr");
   const int64_t W = e->W;
   const int n = 3 * e->ne;
   const int tiles = e->n_scan_blocks;
@@ -671,6 +683,7 @@ int32_t mole_dmc_block(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op
     return MOLE_OK;
   }
   if (n_steps == 0) return MOLE_OK;
+  MOLE_RANGE("mole_dmc_block");
   CU(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = STREAM(ctx);
   const bool multi = ctx->nranks > 1;
@@ -758,11 +771,6 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
     // bitmask + Fenwick tree in shared memory when 3W/32 words fit (W <= ~2.6e5), else in the global scratch
     int smem_words = (int)(cap / 32 + 3);
     if ((size_t)smem_words * 8 > 200 * 1024) smem_words = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CU(ctx, cudaFuncSetAttribute(simple_remove_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
     simple_remove_kernel<<<1, 1024, (size_t)smem_words * 8, st>>>(list, e->blocksums, tiles, W, e->walker_offset, e->key, e->step,
                                                                  mask, fen, e->sb_draws, smem_words, e->src);
     KERNEL_CHECK(ctx);

@@ -80,6 +80,7 @@ int32_t mole_comm_allreduce_host(mole_ctx_s* ctx, double* sum_vals, int n_sum, d
 // consuming kernels fold the nranks rows themselves (sums in rank order, max)
 int32_t mole_comm_allgather_device(mole_ctx_s* ctx, const double* send_dev, double* recv_dev, int n) {
   if (!ctx || ctx->nranks <= 1 || !ctx->nccl_comm) return MOLE_OK;
+  MOLE_RANGE("mole_comm_allgather");
   const int rc = api().AllGather(send_dev, recv_dev, (size_t)n, NCCL_FLOAT64, ctx->nccl_comm, (cudaStream_t)ctx->stream);
   if (rc != 0) return nccl_fail(ctx, "ncclAllGather", rc);
   return MOLE_OK;
@@ -130,6 +131,7 @@ int32_t mole_acc_allreduce(mole_ens_t e) {
   mole_ctx_s* ctx = e->ctx;
   if (ctx->nranks <= 1) return MOLE_OK;
   if (!ctx->nccl_comm) return mole_set_error(ctx, MOLE_ERR_NCCL, "mole_acc_allreduce before mole_comm_init");
+  MOLE_RANGE("mole_acc_allreduce");
   cudaSetDevice(ctx->device);
   const int rc = api().AllReduce(e->acc, e->acc, ACC_DEV_LEN, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, (cudaStream_t)ctx->stream);
   if (rc != 0) return nccl_fail(ctx, "ncclAllReduce", rc);

@@ -21,6 +21,18 @@ RngKey mole_key_from_seed(const uint8_t seed[32]) {
 
 int mole_oo_index(int P, int k, int l) { return k * P - k * (k - 1) / 2 + (l - k); }
 
+uint64_t mole_el_signature(const WfParams& w, const HamParams& h) {
+  uint64_t x = 1469598103934665603ull;
+  auto eat = [&x](const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) { x ^= b[i]; x *= 1099511628211ull; }
+  };
+  eat(&w.kind, sizeof(w.kind)); eat(&w.ne, sizeof(w.ne)); eat(w.p, sizeof(w.p)); eat(w.geom, sizeof(w.geom));
+  eat(&h.kind, sizeof(h.kind)); eat(&h.n_ions, sizeof(h.n_ions)); eat(h.ion_pos, sizeof(h.ion_pos)); eat(h.ion_z, sizeof(h.ion_z));
+  eat(&h.frequency, sizeof(h.frequency));
+  return x ? x : 1;
+}
+
 // ------------------------------------------------------------------ optimizers
 struct mole_opt_s {
   int kind, np;
@@ -239,6 +251,7 @@ int32_t mole_opt_step(mole_opt_t o, const double* pars, const mole_acc_host* a, 
   if (!o || !pars || !a || !deltap) return MOLE_ERR_INVALID_ARG;
   if (a->n_params != o->np)
     return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "\"Parameter gradient\" moments missing or of the wrong size");
+  MOLE_RANGE("mole_opt_step");
   if (!moments_finite(a, o->np))
     return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "non-finite optimisation moments (see mole_ensemble_health); no update computed");
   std::vector<double> dp(o->np, 0.0);

@@ -13,6 +13,30 @@
 #define MOLE_HD inline
 #define MOLE_D inline
 #endif
+// dynamic shared memory of a kernel; MOLE_EMU = the host emulation of tests/native/cuda_emu.h (test infrastructure:
+// the kernels are compiled unchanged by g++ and run thread-per-lane against the oracle, no GPU needed)
+#if defined(MOLE_EMU)
+#define MOLE_DYN_SMEM(T, name) T* name = (T*)mole_emu_dyn_smem
+#define MOLE_DEVICE_CODE 1
+#else
+#define MOLE_DYN_SMEM(T, name) extern __shared__ T name[]
+#if defined(__CUDACC__)
+#define MOLE_DEVICE_CODE 1
+#endif
+#endif
+
+// NVTX ranges around the host entry points that enqueue device work (sweep, reduce, DMC step, branch, collectives),
+// so that nsys / ncu --nvtx captures are attributable; compiled in with -DMOLE_NVTX (build.sh: MOLE_NVCC_EXTRA)
+#if defined(MOLE_NVTX) && !defined(MOLE_EMU)
+#include <nvtx3/nvToolsExt.h>
+struct MoleRange {
+  explicit MoleRange(const char* name) { nvtxRangePushA(name); }
+  ~MoleRange() { nvtxRangePop(); }
+};
+#define MOLE_RANGE(name) MoleRange mole_range_guard_(name)
+#else
+#define MOLE_RANGE(name) do { } while (0)
+#endif
 
 // ---- packed accumulator layout (doubles); mirrors mole_acc_host field order -----------------
 enum {
@@ -94,6 +118,9 @@ struct mole_ctx_s {
   int live_ens = 0;
   bool closing = false;
 };
+// FNV-1a over the parameter blocks: the cached local energy of a DMC ensemble is only reused for the same
+// wavefunction parameters and operator (dmc.rs:89-96 recomputes it every step)
+uint64_t mole_el_signature(const WfParams& w, const HamParams& h);
 
 struct mole_wf_s { mole_ctx_s* ctx; WfParams p; };
 struct mole_op_s { mole_ctx_s* ctx; HamParams p; };
@@ -108,6 +135,7 @@ struct mole_ens_s {
   double* x0 = nullptr;     // snapshot (lazily allocated)
   double* w = nullptr; double* w2 = nullptr;
   double* el = nullptr; double* el2 = nullptr; int el_cached = 0;
+  uint64_t el_sig = 0;       // signature of the (wavefunction parameters, operator) the cached E_L was computed with
   int wstats_valid = 0;      // red[2..3] hold sum/max of the CURRENT weights
   double* blk = nullptr; int32_t blk_fill = 0; int32_t blk_size = 0;
   double* acc = nullptr;    // [ACC_LEN]

@@ -14,14 +14,35 @@
 constexpr int SWEEP_THREADS = 128;
 
 // ------------------------------------------------------------------ per-thread accumulators
-template <int NP>
+// The ten scalar sums always live in registers.  The 2 NP + NP (NP + 1) / 2 optimisation moments live in registers
+// too, except when SMEM is set (kinds with NP >= 4: the 18 moments of the two-centre LCAO kind next to its walker
+// state spilled, profiles/r01d): then each thread owns one column of a [moments][SWEEP_THREADS] shared-memory block
+// (thread index fastest: conflict-free), the way sj_sweep_kernel keeps its 42 moments.
+template <int NP, bool SMEM = false>
 struct Acc {
   static constexpr int NOO = NP * (NP + 1) / 2;
-  static constexpr int LEN = 10 + 2 * NP + NOO;
-  double v[LEN];
-  MOLE_D void zero() {
+  static constexpr int NMOM = 2 * NP + NOO;
+  static constexpr int LEN = 10 + NMOM;
+  double v[SMEM ? 10 : LEN];
+  double* col;   // SMEM: this thread's column
+  MOLE_D void zero(double* smem_block) {
 #pragma unroll
-    for (int i = 0; i < LEN; ++i) v[i] = 0.0;
+    for (int i = 0; i < (SMEM ? 10 : LEN); ++i) v[i] = 0.0;
+    col = smem_block + threadIdx.x;
+    if (SMEM)
+#pragma unroll
+      for (int i = 0; i < NMOM; ++i) col[i * SWEEP_THREADS] = 0.0;
+  }
+  // moment i (0 .. NMOM-1): sum O_k at k, sum O_k E at NP + k, sum O_k O_l packed at 2 NP + q
+  MOLE_D void add(int i, double a, double b) {
+    if (SMEM) col[i * SWEEP_THREADS] = fma(a, b, col[i * SWEEP_THREADS]);
+    else v[10 + i] = fma(a, b, v[10 + i]);
+  }
+  MOLE_D void gather(double* all) const {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) all[i] = v[i];
+#pragma unroll
+    for (int i = 0; i < NMOM; ++i) all[10 + i] = SMEM ? col[i * SWEEP_THREADS] : v[SMEM ? 0 : 10 + i];
   }
   // compact index -> slot in the packed ACC_* layout
   MOLE_D static int slot(int i) {
@@ -268,9 +289,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) swee
   using WF = WfDev<KIND>;
   constexpr int NE = WF::NE;
   constexpr int NP = OPT ? WF::NP : 0;
-  using A = Acc<NP>;
+  constexpr bool MOM_SMEM = NP >= 4;
+  using A = Acc<NP, MOM_SMEM>;
+  __shared__ double s_mom[MOM_SMEM ? A::NMOM * SWEEP_THREADS : 1];
   A acc;
-  acc.zero();
+  acc.zero(s_mom);
   const WfParams& p = sp.wf;
   const double sd = sqrt(sp.metrop_param);
   const bool want_e = (sp.observables & MOLE_OBS_ENERGY) != 0;
@@ -354,10 +377,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) swee
         int q = 0;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-          acc.v[10 + k] += o[k];
-          acc.v[10 + NP + k] = fma(o[k], el, acc.v[10 + NP + k]);
+          acc.add(k, o[k], 1.0);
+          acc.add(NP + k, o[k], el);
 #pragma unroll
-          for (int l = k; l < NP; ++l, ++q) acc.v[10 + 2 * NP + q] = fma(o[k], o[l], acc.v[10 + 2 * NP + q]);
+          for (int l = k; l < NP; ++l, ++q) acc.add(2 * NP + q, o[k], o[l]);
         }
       }
     }
@@ -365,7 +388,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) swee
     for (int c = 0; c < 3 * NE; ++c) sp.x[(size_t)c * W + w] = wk.st.x[c];
     sp.blk[w] = blk;
   }
-  mole_block_reduce_to_global<A::LEN>(acc.v, sp.partials, sp.acc, sp.ticket, [](int i) { return A::slot(i); });
+  double all[A::LEN];
+  acc.gather(all);
+  __syncthreads();
+  mole_block_reduce_to_global<A::LEN>(all, sp.partials, sp.acc, sp.ticket, [](int i) { return A::slot(i); });
 }
 
 // Last-CTA fold of the per-CTA DMC partial rows {sum w E, sum w, sum w', max w'} into red[0..3] by the

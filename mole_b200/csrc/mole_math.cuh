@@ -12,7 +12,16 @@
 #pragma once
 #include "mole_internal.h"
 
-#if defined(__CUDACC__)
+#if defined(MOLE_DEVICE_CODE)
+
+// MUFU seeds (20 mantissa bits)
+#if defined(MOLE_EMU)
+MOLE_D double m_seed_rcp(double x) { return mole_emu_rcp_seed(x); }
+MOLE_D double m_seed_rsqrt(double x) { return mole_emu_rsqrt_seed(x); }
+#else
+MOLE_D double m_seed_rcp(double x) { double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+MOLE_D double m_seed_rsqrt(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+#endif
 
 // 1/x for finite normal x != 0.  The MUFU.RCP64H seed carries 20 mantissa bits (the low word is zero), so
 // ONE cubic Newton step y (1 + e + e^2), e = 1 - x y exact in the fma, leaves a truncation error e^3 < 2^-57
@@ -21,7 +30,7 @@ template <int N>
 MOLE_D void m_rcp_n(const double (&x)[N], double (&y)[N]) {
   double e[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+  for (int i = 0; i < N; ++i) y[i] = m_seed_rcp(x[i]);
 #pragma unroll
   for (int i = 0; i < N; ++i) e[i] = fma(-x[i], y[i], 1.0);
 #pragma unroll
@@ -49,7 +58,7 @@ template <int N>
 MOLE_D void m_rsqrt_n(const double (&x)[N], double (&y)[N]) {
   double hx[N], e[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+  for (int i = 0; i < N; ++i) y[i] = m_seed_rsqrt(x[i]);
   // same step on d = 1 - x y^2 = 2e: y + (y d)(1/2 + 3/8 d), five FP64 instructions instead of six
 #pragma unroll
   for (int i = 0; i < N; ++i) hx[i] = x[i] * y[i];
@@ -316,4 +325,4 @@ MOLE_D void m_sincos_turn_n(const double (&a)[N], double (&sn)[N], double (&cs)[
   }
 }
 
-#endif  // __CUDACC__
+#endif  // MOLE_DEVICE_CODE

@@ -58,7 +58,7 @@ MOLE_HD MoveDraw mole_draw_uniform4(RngKey k, uint64_t walker, uint32_t step, ui
   return MoveDraw{mole_u53(p.a, p.b), mole_u53(p.c, p.d), mole_u53(q.a, q.b), mole_u53(q.c, q.d)};
 }
 
-#if defined(__CUDACC__) && !defined(MOLE_HOST_ONLY)
+#if defined(MOLE_DEVICE_CODE) && !defined(MOLE_HOST_ONLY)
 #include "mole_math.cuh"
 // three standard normals (Box-Muller) + one uniform: MetropolisDiffuse (metrop.rs:160,197), DmcRunner::new (dmc.rs:52-56)
 // r = sqrt(-2 ln u), angle = 2 pi (w / 2^32); the two logs, two square roots and two sin/cos go through

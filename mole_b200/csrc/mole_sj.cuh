@@ -5,21 +5,26 @@
 //
 // Layout: FIVE lanes cooperate on one walker, six walkers per warp (lanes 30/31 idle).  Lane gl
 // owns one electron of each spin.  Registers hold the positions, the radial cache (r, 1/r and the three
-// orbital exponentials) and grad f of the two own electrons; shared memory holds, per walker, the pair
-// cache (u, g/r, laplacian term, 1/r, R for the 45 pairs), both inverse Slater matrices, a copy of
-// the positions, a mailbox for the intra-walker exchanges and the 42 optimisation moments.  The spin being moved always sits in
+// orbital exponentials) and the DRIFT V = grad ln D + grad f of the two own electrons; shared memory holds, per
+// walker, the pair cache (u, g/r, 1/r, R for the 45 pairs), both inverse Slater matrices, a mailbox for the
+// intra-walker exchanges and the 42 optimisation moments.  The spin being moved always sits in
 // register slot 0 (the slots are swapped between the two halves of a sweep), so there is one copy of
 // the move code.  A single-electron move re-evaluates only what changed: one orbital row, a
 // Sherman-Morrison update of one 5x5 inverse (rebuilt from scratch every SJ_REFRESH_EVERY sweeps), nine
-// Jastrow pairs; grad ln D of the own electrons is carried in registers and updated on accepted moves.
+// Jastrow pairs; the drift of every electron is updated by DIFFERENCES (grad ln D_j changes by -(v_j/ratio) H_j,
+// grad f_j by one pair term), and the acceptance needs only sum_j (|V'_j|^2 - |V_j|^2) = sum_j dV_j . (V_j + V'_j),
+// so neither grad ln D nor grad f is carried and no norm is re-summed (mole_sj_move.cuh).
 // All reductions over the five lanes go through the mailbox in a fixed order (deterministic).
 // The per-walker shared-memory stride is 5 (mod 16) doubles, so the unit-stride-in-lane accesses of a
-// warp's 30 active lanes fall on distinct 8-byte banks.
+// warp's 30 active lanes fall on distinct 8-byte banks; the two idle lanes read at an offset of 14 doubles into
+// walker slot 0 (bank pairs 14, 15 of the second half-warp, the only free ones).
 // Metropolis semantics are the reference's (src/metropolis/src/metrop.rs:60-96,150-212), including
 // the Frobenius norm over ALL electrons' drift in t_high / t_low.
 #pragma once
-#include <cuda_runtime.h>
 #include "mole_internal.h"
+#if !defined(MOLE_EMU)
+#include <cuda_runtime.h>
+#endif
 #include "mole_rng.cuh"
 #include "mole_math.cuh"
 
@@ -42,7 +47,7 @@ constexpr int SJ_MIN_CTAS = MOLE_SJ_MIN_CTAS;   // CTAs per SM the register budg
 #define SJ_BOUNDS __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS)
 #endif
 constexpr int SJ_NPAIR = 45;
-constexpr int SJ_PCV = 5;                       // cached values per pair: u, g/r, lap term, 1/r, R
+constexpr int SJ_PCV = 4;                       // cached values per pair: u, g/r, 1/r, R
 // shared memory per walker (offsets in doubles)
 constexpr int SJ_OFF_PC = 0;                               // [SJ_PCV][45]
 constexpr int SJ_OFF_MINV = SJ_OFF_PC + SJ_PCV * SJ_NPAIR; // [2][5][5] inverse Slater matrices, (spin, k, j)
@@ -50,7 +55,7 @@ constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 56 double
 constexpr int SJ_MB = 56;
 constexpr int SJ_OFF_ACC = SJ_OFF_MB + SJ_MB;              // [42] sum O_k, sum O_k E_L, sum O_k O_l of this walker slot
 constexpr int SJ_NMOM = 42;
-constexpr int SJ_STRIDE = 373;                             // >= SJ_OFF_ACC + SJ_NMOM and == 5 (mod 16)
+constexpr int SJ_STRIDE = 341;                             // >= SJ_OFF_ACC + SJ_NMOM and == 5 (mod 16)
 static_assert(SJ_STRIDE >= SJ_OFF_ACC + SJ_NMOM && SJ_STRIDE % 16 == 5, "per-walker stride");
 #ifndef MOLE_SJ_REFRESH_EVERY
 #define MOLE_SJ_REFRESH_EVERY 16
@@ -58,9 +63,9 @@ static_assert(SJ_STRIDE >= SJ_OFF_ACC + SJ_NMOM && SJ_STRIDE % 16 == 5, "per-wal
 constexpr int SJ_REFRESH_EVERY = MOLE_SJ_REFRESH_EVERY;    // sweeps between from-scratch rebuilds of the inverses
 constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
 // mailbox slots
-constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] old position of the moved electron
+constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] displacement x' - x, [7] |d|^2 - 2 tau d.V_e
 constexpr int MB_E = 8;       // [3] orbital exponentials at the trial position
-constexpr int MB_RIN = 12;    // [6][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles)
+constexpr int MB_RIN = 12;    // [6][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles); [5][0] = d.(V_e + V'_e)
 // measurement (sj_measure): [9][5] per-lane partial sums at 0..44, results at MB_OUT
 constexpr int MB_OUT = 45;    // [0..6] O_k, [7] 1.0, [8] E_L, [9..10] spare: every moment is a product out[k] * out[l]
 constexpr int SJ_NP = 7;
@@ -78,8 +83,7 @@ struct SjConst {
 // because the index is lane-divergent (a divergent index into the constant bank serialises).
 __shared__ unsigned char s_sj_mom[48];
 __device__ __forceinline__ void sj_mom_table_init() {
-  const int j = threadIdx.x;
-  if (j < 48) {
+  for (int j = threadIdx.x; j < 48; j += SJ_THREADS) {
     int k = 7, l = 7;                                    // padding entries: 1.0 * 1.0, never accumulated
     if (j < SJ_NP) { k = j; l = 7; }
     else if (j < 2 * SJ_NP) { k = j - SJ_NP; l = 8; }
@@ -103,14 +107,15 @@ struct SjLane {
   int lane, gl, base;
   int ph;              // spin held in register slot 0 (slot t holds spin t ^ ph)
   bool act;            // this 5-lane group holds a real walker
-  bool wr;             // lanes 30/31 alias group 0's shared memory and must never store to it
+  bool wr;             // lanes 30/31 read a shifted window of walker slot 0 and must never store
   bool val[2];         // slot validity (lane index < number of electrons of that spin)
   double x[2][3];      // own electrons
   double orb[2][5];    // r, 1/r, exp(-z1 r), exp(-z2 r), exp(-z3 r) at own electrons
-  double gf[2][3];     // grad_i f
-  double G[2][3];      // grad_i ln D
+  double V[2][3];      // drift grad_i ln psi = grad_i ln D + grad_i f, updated by differences on accepted moves
   double psi, fj;      // psi = L.psi * exp(L.fj): accepted moves multiply psi by the determinant ratio and add the
                        // Jastrow change to fj; sj_fold_psi / sj_refresh bring fj back to 0.  Replicated over the group
+  double Q;            // sum_j |V_j|^2 over all electrons, carried (Q += dQ on accept) for the range guard of the accept
+                       // test only; re-summed exactly by sj_refresh and whenever the guarded branch is taken
   double* sm;          // this walker's shared-memory region
 };
 
@@ -135,9 +140,9 @@ MOLE_D double sj_gsum(double v, const SjLane& L) {
   return s;
 }
 
-struct SjPair { double u, gr, lt, ir, R; };
+struct SjPair { double u, gr, ir, R; };
 
-// pair function from the squared distance (theory/jastrow.tex:23-31,45-48,68-71,82-97)
+// pair function from the squared distance (theory/jastrow.tex:23-31,45-48,68-71)
 MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   SjPair o;
   const double r = m_sqrt_rsqrt(r2, o.ir);
@@ -146,13 +151,18 @@ MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   const double iden = m_rcp(fma(c.b2, o.R, 1.0));
   const double R2 = o.R * o.R;
   o.u = fma(R2, fma(c.b4, o.R, c.b3), (c.b1 * o.R) * iden);
-  const double id2 = iden * iden;
-  const double du = fma(c.b1, id2, fma(3.0 * c.b4, R2, 2.0 * c.b3 * o.R));
-  const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden, fma(6.0 * c.b4, o.R, 2.0 * c.b3));
-  const double g = E * du;
-  o.gr = g * o.ir;
-  o.lt = fma(2.0, o.gr, fma(E * E, d2u, -c.kappa * g));   // div(rhat g) = 2 g/r + dg/dr
+  const double du = fma(c.b1, iden * iden, fma(3.0 * c.b4, R2, 2.0 * c.b3 * o.R));
+  o.gr = (E * du) * o.ir;
   return o;
+}
+
+// div(rhat g) = 2 g/r + dg/dr of a pair from its cached g/r and R and 1/(1 + b2 R) (jastrow.tex:82-97 with the
+// erratum of SURVEY.md 8(c)): E = exp(-kappa r) = 1 - kappa R, g = E u'(R), dg/dr = E^2 u'' - kappa g
+MOLE_D double sj_pair_lap(const SjConst& c, double gr, double R, double iden) {
+  const double E = fma(-c.kappa, R, 1.0), id2 = iden * iden;
+  const double du = fma(c.b1, id2, fma(3.0 * c.b4, R * R, 2.0 * c.b3 * R));
+  const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden, fma(6.0 * c.b4, R, 2.0 * c.b3));
+  return fma(2.0, gr, fma(E * E, d2u, -c.kappa * (E * du)));
 }
 
 // orbital values from the radial cache; entries k >= n are zero (identity padding of the Slater matrix)
@@ -233,12 +243,28 @@ MOLE_D void sj_invert(double* M, double* out, double& det, const SjLane& L) {
   det = (inv & 1) ? -d : d;
 }
 
-// rebuild the inverse Slater matrix of register slot t from scratch; returns the determinant
-MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t) {
+// sum over the group of this lane's share of Q = sum_j |V_j|^2 (absent electrons contribute nothing)
+MOLE_D double sj_q_exact(const SjLane& L) {
+  const double q0 = fma(L.V[0][2], L.V[0][2], fma(L.V[0][1], L.V[0][1], L.V[0][0] * L.V[0][0]));
+  const double q1 = fma(L.V[1][2], L.V[1][2], fma(L.V[1][1], L.V[1][1], L.V[1][0] * L.V[1][0]));
+  return sj_gsum((L.val[0] ? q0 : 0.0) + (L.val[1] ? q1 : 0.0), L);
+}
+
+// rebuild the inverse Slater matrix of register slot t from scratch; returns the determinant.  The drift keeps its
+// Jastrow part: V += grad ln D (fresh inverse) - grad ln D (carried inverse); with_drift = false (sj_init): V holds
+// grad f only and receives the fresh grad ln D
+MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t, bool with_drift) {
   const int spin = t ^ L.ph;
   const int n = sj_spin_n(c, spin);
   double phi[5];
   sj_phi(L.x[t], L.orb[t], n, phi);
+  double Gold[3] = {0.0, 0.0, 0.0};
+  if (with_drift) {
+    double mo[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) mo[k] = L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl];
+    sj_gradlnD(c, L.x[t], L.orb[t], mo, Gold);
+  }
   double* tsc = L.sm + SJ_OFF_MB + MB_RIN;
 #pragma unroll
   for (int k = 0; k < 5; ++k)
@@ -252,20 +278,25 @@ MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t) {
 #pragma unroll
   for (int k = 0; k < 5; ++k)
     if (L.wr) L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl] = out[k];          // Minv[k][j = gl]
-  sj_gradlnD(c, L.x[t], L.orb[t], out, L.G[t]);
+  double G[3];
+  sj_gradlnD(c, L.x[t], L.orb[t], out, G);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) L.V[t][q] += G[q] - Gold[q];
   sj_sync();
   return det;
 }
 
-// once per sweep: both inverses from scratch (bounds the Sherman-Morrison round-off), psi re-derived
-MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
-  const double d0 = sj_refresh_slot(c, L, 0);
-  const double d1 = sj_refresh_slot(c, L, 1);
+// every SJ_REFRESH_EVERY sweeps: both inverses from scratch (bounds the Sherman-Morrison round-off), psi re-derived,
+// Q re-summed
+MOLE_D void sj_refresh(const SjConst& c, SjLane& L, bool with_drift = true) {
+  const double d0 = sj_refresh_slot(c, L, 0, with_drift);
+  const double d1 = sj_refresh_slot(c, L, 1, with_drift);
   double fl = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) fl += L.sm[SJ_OFF_PC + L.gl + 5 * i];   // cache slots of absent pairs hold zeros
   L.psi = d0 * d1 * m_exp(sj_gsum(fl, L));
   L.fj = 0.0;
+  L.Q = sj_q_exact(L);
 }
 
 // full initialisation of the cooperative state from the positions in L.x (slot t = spin t)
@@ -297,14 +328,14 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
         gx = fma(P.gr, dx, gx); gy = fma(P.gr, dy, gy); gz = fma(P.gr, dz, gz);
         if (a < b && L.wr) {
           double* pc = L.sm + SJ_OFF_PC + sj_pidx(a, b);
-          pc[0] = P.u; pc[SJ_NPAIR] = P.gr; pc[2 * SJ_NPAIR] = P.lt; pc[3 * SJ_NPAIR] = P.ir; pc[4 * SJ_NPAIR] = P.R;
+          pc[0] = P.u; pc[SJ_NPAIR] = P.gr; pc[2 * SJ_NPAIR] = P.ir; pc[3 * SJ_NPAIR] = P.R;
         }
       }
     }
-    L.gf[t][0] = gx; L.gf[t][1] = gy; L.gf[t][2] = gz;
+    L.V[t][0] = gx; L.V[t][1] = gy; L.V[t][2] = gz;            // grad f; sj_refresh adds grad ln D
   }
   sj_sync();
-  sj_refresh(c, L);
+  sj_refresh(c, L, false);
 }
 
 // psi of the current configuration from the carried determinant part and Jastrow change
@@ -318,8 +349,7 @@ MOLE_D void sj_swap_slots(SjLane& L) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     double t = L.x[0][q]; L.x[0][q] = L.x[1][q]; L.x[1][q] = t;
-    t = L.gf[0][q]; L.gf[0][q] = L.gf[1][q]; L.gf[1][q] = t;
-    t = L.G[0][q]; L.G[0][q] = L.G[1][q]; L.G[1][q] = t;
+    t = L.V[0][q]; L.V[0][q] = L.V[1][q]; L.V[1][q] = t;
   }
 #pragma unroll
   for (int q = 0; q < 5; ++q) { const double t = L.orb[0][q]; L.orb[0][q] = L.orb[1][q]; L.orb[1][q] = t; }
@@ -355,20 +385,21 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     const double* x = L.x[t];
     const double* o = L.orb[t];
     const double r = o[0], ir = o[1];
-    double m[5];
-    const double* G = L.G[t];
+    double m[5], G[3];
 #pragma unroll
     for (int k = 0; k < 5; ++k) m[k] = L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl];
+    sj_gradlnD(c, x, o, m, G);                                   // grad ln D is not carried: V = G + grad f is
     if (Gout) { Gout[t][0] = G[0]; Gout[t][1] = G[1]; Gout[t][2] = G[2]; }
     // lap phi_k
     const double cp = o[4] * (c.z3 * c.z3 - 4.0 * c.z3 * ir);
     double lapD = (0 < n ? c.z1 * o[2] * (c.z1 - 2.0 * ir) : 0.0) * m[0];
     lapD = fma(1 < n ? (c.z2 * c.z2 * r - 4.0 * c.z2 + 2.0 * ir) * o[3] : 0.0, m[1], lapD);
     const double lapP = fma(4 < n ? x[2] * cp : 0.0, m[4], fma(3 < n ? x[1] * cp : 0.0, m[3], (2 < n ? x[0] * cp : 0.0) * m[2]));
-    const double gg = G[0] * L.gf[t][0] + G[1] * L.gf[t][1] + G[2] * L.gf[t][2];
-    const double ff = L.gf[t][0] * L.gf[t][0] + L.gf[t][1] * L.gf[t][1] + L.gf[t][2] * L.gf[t][2];
+    // lap_i psi / psi = lap_i D / D + lap_i f + 2 G.grad f + |grad f|^2 = lap_i D / D + lap_i f + |V|^2 - |G|^2
+    const double* V = L.V[t];
+    const double vg = fma(V[2] - G[2], V[2] + G[2], fma(V[1] - G[1], V[1] + G[1], (V[0] - G[0]) * (V[0] + G[0])));
     const double mk = L.val[t] ? 1.0 : 0.0;
-    kl = fma(mk, (lapD + lapP) + (2.0 * gg + ff), kl);
+    kl = fma(mk, (lapD + lapP) + vg, kl);
     if (want_ion) {                                              // IonicPotential::value, operator.rs:25-36
       double p = 0.0;
       for (int i = 0; i < h.n_ions; ++i) {
@@ -387,24 +418,26 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     }
   }
   // pair sums: sum_i lap_i f = 2 sum_pairs div(rhat g), V_ee = sum 1/r (ElectronicPotential::value,
-  // operator.rs:80-90) and df/db (jastrow.tex:109-119)
+  // operator.rs:80-90) and df/db (jastrow.tex:109-119); div(rhat g) is formed here from the cached g/r and R
+  // (once per sweep) instead of with every pair evaluation of every move
   const double* pc = L.sm + SJ_OFF_PC + L.gl;
-  double lt[9], pir[9], R[9];
+  double pgr[9], pir[9], R[9], den[9], id[9], lt[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    lt[i] = pc[2 * SJ_NPAIR + 5 * i];
-    pir[i] = pc[3 * SJ_NPAIR + 5 * i];
-    R[i] = pc[4 * SJ_NPAIR + 5 * i];
+    pgr[i] = pc[SJ_NPAIR + 5 * i];
+    pir[i] = pc[2 * SJ_NPAIR + 5 * i];
+    R[i] = pc[3 * SJ_NPAIR + 5 * i];
+    den[i] = fma(c.b2, R[i], 1.0);
   }
+  m_rcp_n<9>(den, id);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) lt[i] = pir[i] != 0.0 ? sj_pair_lap(c, pgr[i], R[i], id[i]) : 0.0;   // absent pairs: all-zero slots
   const double lts = (((lt[0] + lt[1]) + (lt[2] + lt[3])) + ((lt[4] + lt[5]) + (lt[6] + lt[7]))) + lt[8];
   kl = fma(2.0, lts, kl);
   if (want_ee) vl += (((pir[0] + pir[1]) + (pir[2] + pir[3])) + ((pir[4] + pir[5]) + (pir[6] + pir[7]))) + pir[8];
   double db[4] = {0.0, 0.0, 0.0, 0.0};
   if (OPT) {
-    double den[9], id[9], a0[3] = {0.0, 0.0, 0.0}, a1[3] = {0.0, 0.0, 0.0}, a2[3] = {0.0, 0.0, 0.0}, a3[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int i = 0; i < 9; ++i) den[i] = fma(c.b2, R[i], 1.0);
-    m_rcp_n<9>(den, id);
+    double a0[3] = {0.0, 0.0, 0.0}, a1[3] = {0.0, 0.0, 0.0}, a2[3] = {0.0, 0.0, 0.0}, a3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < 9; ++i) {                                // three interleaved partial sums per quantity
       const double q = R[i] * id[i], R2 = R[i] * R[i];
@@ -474,8 +507,11 @@ MOLE_D void sj_lane_setup(SjLane& L, const SjConst& c, double* smem, int64_t w, 
   L.wr = g < SJ_WPW;
   L.val[0] = L.gl < c.nup;
   L.val[1] = L.gl < c.ndn;
-  const int slot = (threadIdx.x >> 5) * SJ_WPW + (g < SJ_WPW ? g : 0);   // idle lanes alias group 0 (loads only)
-  L.sm = smem + (size_t)slot * SJ_STRIDE;
+  // idle lanes (30, 31) only ever load: a window shifted by 14 doubles into walker slot 0 of this warp puts them on
+  // bank pairs 14 and 15 of the second half-warp, the two the active lanes 16..29 leave free (aliasing slot 0 itself
+  // cost one conflict wavefront on every unit-stride access: l1tex__data_bank_conflicts 2.2e9 per launch)
+  const int slot = (threadIdx.x >> 5) * SJ_WPW + (g < SJ_WPW ? g : 0);
+  L.sm = smem + (size_t)slot * SJ_STRIDE + (g < SJ_WPW ? 0 : 14);
 }
 
 // global <-> registers; slot t must hold spin t (L.ph == 0)
@@ -531,7 +567,7 @@ MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid,
 __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __restrict__ x, int64_t W, WfParams p, HamParams h,
                                                               int have_ham, double* psi, double* grad, double* lap,
                                                               double* hpsi, double* pgrad) {
-  extern __shared__ double sj_smem[];
+  MOLE_DYN_SMEM(double, sj_smem);
   mole_math_smem_init();
   const SjConst c = sj_const(p);
   const int g = (threadIdx.x & 31) / 5;
@@ -556,7 +592,7 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
       if (L.val[t]) {
         const int cfg_e = t == 0 ? L.gl : c.nup + L.gl;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) grad[((size_t)w * p.ne + cfg_e) * 3 + q] = L.psi * (G[t][q] + L.gf[t][q]);
+        for (int q = 0; q < 3; ++q) grad[((size_t)w * p.ne + cfg_e) * 3 + q] = L.psi * L.V[t][q];
       }
   if (L.gl == 0) {
     if (psi) psi[w] = L.psi;
@@ -571,7 +607,7 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
 // ------------------------------------------------------------------ fused sweep
 template <int METROP, bool OPT>
 __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
-  extern __shared__ double sj_smem[];
+  MOLE_DYN_SMEM(double, sj_smem);
   mole_math_smem_init();
   if (OPT) sj_mom_table_init();
   const SjConst c = sj_const(sp.wf);
@@ -707,14 +743,14 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
     if (i < 10 + 2 * SJ_NP) return (int)ACC_OE + (i - 10 - SJ_NP);
     return (int)ACC_OO + (i - 10 - 2 * SJ_NP);
   };
-  if (threadIdx.x < LEN) {
+  for (int i = threadIdx.x; i < LEN; i += SJ_THREADS) {                 // (a one-warp CTA has fewer threads than entries)
     double s = 0.0;
-    if (threadIdx.x < 10) {
-      for (int q = 0; q < SJ_WARPS; ++q) s += red[q * 16 + threadIdx.x];
+    if (i < 10) {
+      for (int q = 0; q < SJ_WARPS; ++q) s += red[q * 16 + i];
     } else {
-      for (int q = 0; q < SJ_WPB; ++q) s += sj_smem[(size_t)q * SJ_STRIDE + SJ_OFF_ACC + (threadIdx.x - 10)];
+      for (int q = 0; q < SJ_WPB; ++q) s += sj_smem[(size_t)q * SJ_STRIDE + SJ_OFF_ACC + (i - 10)];
     }
-    sp.partials[(size_t)blockIdx.x * ACC_LEN + slot(threadIdx.x)] = s;
+    sp.partials[(size_t)blockIdx.x * ACC_LEN + slot(i)] = s;
   }
   __threadfence();
   __syncthreads();
@@ -722,8 +758,8 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (threadIdx.x < LEN) {
-      const int sl = slot(threadIdx.x);
+    for (int i = threadIdx.x; i < LEN; i += SJ_THREADS) {
+      const int sl = slot(i);
       double s = 0.0;
       for (unsigned b = 0; b < gridDim.x; ++b) s += sp.partials[(size_t)b * ACC_LEN + sl];
       sp.acc[sl] += s;
@@ -733,7 +769,7 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
 
 // ------------------------------------------------------------------ DMC time step (dmc.rs:87-130)
 __global__ void SJ_BOUNDS sj_dmc_kernel(const DmcParams dp) {
-  extern __shared__ double sj_smem[];
+  MOLE_DYN_SMEM(double, sj_smem);
   mole_math_smem_init();
   const SjConst c = sj_const(dp.wf);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -800,12 +836,9 @@ __global__ void SJ_BOUNDS sj_dmc_kernel(const DmcParams dp) {
 }
 
 // ------------------------------------------------------------------ host launchers
-static inline cudaError_t sj_upload_tables() {
-  static bool done_dev[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  bool& done = done_dev[dev & 63];
-  if (done) return cudaSuccess;
+#if !defined(MOLE_EMU)
+// dynamic shared-memory opt-in of every SJ kernel on the CURRENT device (mole_ctx_create)
+static inline cudaError_t sj_set_kernel_attributes() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(sj_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SJ_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sj_dmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SJ_SMEM_BYTES)) != cudaSuccess) return e;
@@ -813,7 +846,6 @@ static inline cudaError_t sj_upload_tables() {
   if ((e = cudaFuncSetAttribute(sj_sweep_kernel<M, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SJ_SMEM_BYTES)) != cudaSuccess) return e;
   SJ_ATTR(MOLE_METROP_BOX, false) SJ_ATTR(MOLE_METROP_BOX, true) SJ_ATTR(MOLE_METROP_DIFFUSE, false) SJ_ATTR(MOLE_METROP_DIFFUSE, true)
 #undef SJ_ATTR
-  done = true;
   return cudaSuccess;
 }
 
@@ -825,16 +857,13 @@ static inline int sj_grid(mole_ctx_s* ctx, int64_t W, int rows) {
 
 static inline cudaError_t sj_eval_launch(cudaStream_t st, const double* x, int64_t W, const WfParams& wp, const HamParams& h,
                                          int have_ham, double* psi, double* grad, double* lap, double* hpsi, double* pgrad) {
-  cudaError_t e = sj_upload_tables();
-  if (e != cudaSuccess) return e;
   const int blocks = (int)((W + SJ_WPB - 1) / SJ_WPB);
   sj_eval_kernel<<<blocks, SJ_THREADS, SJ_SMEM_BYTES, st>>>(x, W, wp, h, have_ham, psi, grad, lap, hpsi, pgrad);
   return cudaSuccess;
 }
 
 static inline int32_t sj_sweep_launch(mole_ctx_s* ctx, mole_ens_s* e, const SweepParams& sp, int metrop, bool opt) {
-  cudaError_t ce = sj_upload_tables();
-  if (ce != cudaSuccess) return mole_set_error(ctx, MOLE_ERR_CUDA, std::string("sj tables: ") + cudaGetErrorString(ce));
+  // launch errors are picked up by the caller's KERNEL_CHECK (cudaGetLastError) right after this returns
   const int blocks = sj_grid(ctx, e->W, e->partial_rows);
   cudaStream_t st = (cudaStream_t)ctx->stream;
   if (metrop == MOLE_METROP_BOX) {
@@ -848,9 +877,8 @@ static inline int32_t sj_sweep_launch(mole_ctx_s* ctx, mole_ens_s* e, const Swee
 }
 
 static inline int32_t sj_dmc_launch(mole_ctx_s* ctx, mole_ens_s* e, const DmcParams& dp) {
-  cudaError_t ce = sj_upload_tables();
-  if (ce != cudaSuccess) return mole_set_error(ctx, MOLE_ERR_CUDA, std::string("sj tables: ") + cudaGetErrorString(ce));
   const int blocks = sj_grid(ctx, e->W, e->partial_rows);
   sj_dmc_kernel<<<blocks, SJ_THREADS, SJ_SMEM_BYTES, (cudaStream_t)ctx->stream>>>(dp);
   return MOLE_OK;
 }
+#endif  // !MOLE_EMU
