@@ -15,6 +15,9 @@
 #endif
 // dynamic shared memory of a kernel; MOLE_EMU = the host emulation of tests/native/cuda_emu.h (test infrastructure:
 // the kernels are compiled unchanged by g++ and run thread-per-lane against the oracle, no GPU needed)
+#if !defined(MOLE_CALLER_LINE)
+#define MOLE_CALLER_LINE 0
+#endif
 #if defined(MOLE_EMU)
 #define MOLE_DYN_SMEM(T, name) T* name = (T*)mole_emu_dyn_smem
 #define MOLE_DEVICE_CODE 1

@@ -121,7 +121,11 @@ struct SjLane {
 
 MOLE_D int sj_spin_n(const SjConst& c, int spin) { return spin == 0 ? c.nup : c.ndn; }
 MOLE_D bool sj_slot_valid(const SjConst& c, int sid) { return sid < 5 ? sid < c.nup : (sid - 5) < c.ndn; }
+#if defined(MOLE_EMU)
+MOLE_D void sj_sync(int line = MOLE_CALLER_LINE) { __syncwarp(0xffffffffu, line); }   // the watchdog reports the caller
+#else
 MOLE_D void sj_sync() { __syncwarp(); }
+#endif
 
 // acceptance.min(1.0) with the NaN policy of include/mole_b200.h (MOLE_COMPAT_NAN_ACCEPT)
 MOLE_D double sj_clamp_acceptance(double a, uint32_t compat) {
@@ -659,7 +663,8 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
       if (OPT) {
         const double* os = L.sm + SJ_OFF_MB + MB_OUT;
         const bool mine = !isfinite(os[L.gl]) || (L.gl < 2 && !isfinite(os[5 + L.gl]));
-        bad = bad || ((__ballot_sync(SJ_FULL, mine) >> L.base) & 31u) != 0u;
+        const unsigned votes = __ballot_sync(SJ_FULL, mine);        // unconditionally: every lane of the warp must vote
+        bad = bad || ((votes >> L.base) & 31u) != 0u;
       }
       const bool good = L.act && !bad;
       if (bad && L.act && L.gl == 0) atomicAdd(sp.acc + ACC_BAD, 1.0);

@@ -15,7 +15,11 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #define __device__
@@ -60,8 +64,22 @@ static thread_local emu::dim3 threadIdx, blockIdx;
 static emu::dim3 blockDim, gridDim;
 static void* mole_emu_dyn_smem = nullptr;
 
-inline void __syncthreads() { emu::blk().block_bar.wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::blk().warp_bar[threadIdx.x >> 5].wait(); }
+// last synchronisation site of every emulated thread (source line of the caller), for the deadlock watchdog
+static int emu_site[1024];
+static int emu_hist[1024][12];
+static int emu_nsync[1024];
+inline void emu_note(int line) {
+  const unsigned t = threadIdx.x;
+  emu_site[t] = line;
+  emu_hist[t][emu_nsync[t] % 12] = line;
+  ++emu_nsync[t];
+}
+#define MOLE_CALLER_LINE __builtin_LINE()
+inline void __syncthreads(int line = __builtin_LINE()) { emu_note(-line); emu::blk().block_bar.wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu, int line = __builtin_LINE()) {
+  emu_note(line);
+  emu::blk().warp_bar[threadIdx.x >> 5].wait();
+}
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 template <class T>
@@ -143,6 +161,22 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_smem, const std::fu
     for (int w = 0; w < nwarp; ++w) b.warp_bar[w].reset((int)std::min<unsigned>(32u, block - 32u * w));
     std::vector<std::thread> th;
     th.reserve(block);
+    std::atomic<bool> done{false};
+    std::thread dog([&] {   // deadlock watchdog: MOLE_EMU_WATCHDOG seconds (default 60), then the threads' last sync sites
+      const char* w = getenv("MOLE_EMU_WATCHDOG");
+      const int limit = w ? atoi(w) : 60;
+      for (int t = 0; t < limit * 10 && !done.load(); ++t) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+      if (done.load()) return;
+      fprintf(stderr, "cuda_emu: block %u did not finish in %d s; last sync site (source line, <0: __syncthreads) per thread:\n", bx, limit);
+      for (unsigned t = 0; t < block; ++t) fprintf(stderr, "%s%d", t % 16 ? " " : "\n  ", emu_site[t]);
+      fprintf(stderr, "\nsync counts and the last 12 sites of threads 0 and %u:\n", block / 2);
+      for (unsigned t : {0u, block / 2}) {
+        fprintf(stderr, "  thread %u: %d syncs:", t, emu_nsync[t]);
+        for (int i = 0; i < 12; ++i) fprintf(stderr, " %d", emu_hist[t][(emu_nsync[t] + i) % 12]);
+        fprintf(stderr, "\n");
+      }
+      _exit(3);
+    });
     for (unsigned t = 0; t < block; ++t)
       th.emplace_back([&, t, bx] {
         ::threadIdx.x = t;
@@ -150,6 +184,8 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_smem, const std::fu
         body();
       });
     for (auto& x : th) x.join();
+    done.store(true);
+    dog.join();
   }
 }
 }  // namespace emu

@@ -214,3 +214,30 @@ def test_hot_kernels_do_not_spill():
     assert all(r["spill_st"] == 0 and r["spill_ld"] == 0 for r in rows), [r["demangled"] for r in rows if r["spill_st"]]
     # two warps per scheduler at 255 registers is the SJ kernel's design point
     assert all(r["regs"] >= 169 for r in rows if r["demangled"].startswith("void sj_sweep_kernel"))
+
+
+def test_last_error_string_is_per_thread(mole):
+    """errors raised without a context (NULL handles, host-only entry points) are kept per thread: two threads that
+    fail differently at the same time each read back their own message (include/mole_b200.h threading contract)."""
+    import threading
+    lib = mole.ffi.lib()
+    msgs, barrier = {}, threading.Barrier(2)
+
+    def fail(which):
+        opt = mole.StochasticReconfiguration(1.0, 2)
+        acc = mole.ffi.AccHost()
+        acc.n_params = 1 if which == 0 else 2
+        acc.n_samples = 10.0
+        for _ in range(200):
+            barrier.wait()
+            try:
+                opt.compute_parameter_update(np.zeros(2), acc)
+            except mole.MoleError as ex:
+                msgs.setdefault(which, set()).add(str(ex))
+    ths = [threading.Thread(target=fail, args=(i,)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert len(msgs[0]) == 1 and "wrong size" in next(iter(msgs[0]))
+    assert len(msgs[1]) == 1 and "singular" in next(iter(msgs[1]))

@@ -104,3 +104,23 @@ def test_emulated_sj_kernels_match_oracle(orc, sj_emu, tmp_path, name, metrop):
             s = (o[:, :, k] * o[:, :, l]).sum()
             assert abs(acc[26 + q] - s) < 1e-9 * np.abs(o[:, :, k] * o[:, :, l]).sum() + 1e-300
             q += 1
+
+
+@pytest.mark.parametrize("metrop", ["box", "diffuse"])
+def test_emulated_sj_kernel_with_nonfinite_walkers(orc, sj_emu, tmp_path, metrop):
+    """Walkers whose psi / E_L are NaN (an electron ON the nucleus) next to healthy ones in the same warp: every
+    warp-wide vote and mailbox reduction must still be reached by all lanes (a short-circuited __ballot_sync hung the
+    GPU in round 2's first run - the emulator's watchdog reports the diverging synchronisation sites), the NaN samples
+    are counted and skipped, the healthy walkers' sums are untouched."""
+    c = cases()["sj_be"]
+    W, steps, bs = 14, 20, 10
+    cfgs = np.random.default_rng(2).normal(0.0, 0.8, size=(W, 4, 3))
+    cfgs[:3, 0, :] = 0.0
+    os.environ["MOLE_EMU_WATCHDOG"] = "60"
+    kind, param = (orc.METROP_BOX, 1e-200) if metrop == "box" else (orc.METROP_DIFFUSE, 0.02)
+    got = run_emu(sj_emu, str(tmp_path), c, cfgs, kind, param, steps, 0, bs, bytes(32))
+    en, acc = got["energy"], got["acc"]
+    assert not np.isfinite(en[:3]).any() and np.isfinite(en[3:]).all()
+    assert acc[0] == (W - 3) * steps and acc[62] == 3 * steps and acc[5] == (W - 3) * steps // bs
+    assert abs(acc[1] - en[3:].sum()) < 1e-9 * np.abs(en[3:]).sum()
+    assert np.isfinite(acc[:62]).all()

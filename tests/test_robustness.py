@@ -129,3 +129,42 @@ def test_config5_sr_loop_stays_bounded_at_the_bench_settings(mole, orc, capsys):
     sub_mean = ref["energy"].mean()
     sub_err = ref["energy"].mean(axis=1).std(ddof=1) / np.sqrt(sub)
     assert abs(sub_mean - es[0]) < 5 * np.hypot(sub_err, errs[0])
+
+
+def test_two_contexts_driven_from_two_threads(mole, orc):
+    """include/mole_b200.h: "different ctxs may be driven from different threads".  Two contexts on the same GPU, each
+    with its own stream, ensemble and Slater-Jastrow / SimpleBranching work (the kernels whose shared-memory opt-ins used
+    to sit behind unsynchronised process-wide flags), run concurrently and reproduce the serial results bit for bit."""
+    import threading
+    c = cases()["sj_be"]
+    obs = mole.ffi.OBS_ENERGY | mole.ffi.OBS_PGRAD | mole.ffi.OBS_WFVALUE
+
+    def work(ctx, out, key):
+        wf = mole.SlaterJastrow(2, 2, (3.68, 0.96, 0.96), (0.5, 1.0, 0.2, 0.1), 1.0, ctx=ctx)
+        op = mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [4], ctx=ctx)
+        met = mole.MetropolisDiffuse.from_rng(0.05, SEED0)
+        ens = mole.Ensemble(3000, 4, SEED0, ctx=ctx)
+        ens.init_uniform(-1.0, 1.0)
+        for _ in range(5):
+            ens.sweep(wf, met, op, n_sweeps=20, n_discard=0, block_size=10, observables=obs)
+        acc = ens.acc_get()
+        g = mole.STO(0.9, ctx=ctx)
+        gop = mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1], ctx=ctx)
+        d = mole.Ensemble(70000, 1, SEED0, ctx=ctx)          # > 65k walkers: SimpleBranching needs the > 48 KB opt-in
+        d.init_normal(1.0)
+        d.dmc_step(g, mole.MetropolisDiffuse.from_rng(0.025, SEED0), gop, 0.025, -0.5)
+        d.branch(mole.ffi.BRANCH_SIMPLE)
+        out[key] = (ens.get_configs(), acc.sum_e, acc.oo(2, 5), d.get_configs())
+
+    serial, par = {}, {}
+    work(mole.Context(0), serial, "a")
+    ctxs = [mole.Context(0), mole.Context(0)]
+    ths = [threading.Thread(target=work, args=(ctxs[i], par, i)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert set(par) == {0, 1}
+    for i in range(2):
+        for a, b in zip(par[i], serial["a"]):
+            assert np.array_equal(np.asarray(a), np.asarray(b))

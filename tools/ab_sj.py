@@ -92,5 +92,5 @@ if __name__ == "__main__":
         nums = [int(a) for a in sys.argv[1:] if a.isdigit()]
         W, NS, reps = (nums + [1 << 17, 200, 3][len(nums):])[:3]
         for lib in libs:
-            env = dict(os.environ, MOLE_B200_LIB=os.path.abspath(lib))
+            env = dict(os.environ, MOLE_B200_LIB=os.path.abspath(lib), MOLE_B200_AB_OLD_LIB="1")
             subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(W), str(NS), str(reps)], env=env, timeout=300)
