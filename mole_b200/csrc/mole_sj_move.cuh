@@ -12,7 +12,8 @@
 //   other spin:          V'_j = V_j + d(grad f_j)
 //   j = e:               V'_e = grad f_e(x') + H_e(x') / ratio
 // (Sherman-Morrison: Minv'[.][j] = Minv[.][j] - Minv[.][e] v_j / ratio, v_j = phi(x') . Minv[.][j]).  No norm is
-// re-summed and neither grad ln D nor grad f is stored.  Q is carried only for the range guard below.
+// re-summed and neither grad ln D nor grad f is stored (the measurement re-forms both).  Q is carried only for the
+// range guard below.
 //
 // The three independent transcendental chains of a move (orbital radial part and the two Jastrow pairs
 // of each lane) go through the batched, stage-major math of mole_math.cuh and every lane sums the
@@ -40,9 +41,15 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   // ---- A: the owner proposes, everybody reads the trial point and the displacement
   if (isown && L.wr) {
     double dv[3];
+#if MOLE_SJ_PARK_DRAW
+    const double* const pk = L.sm + SJ_OFF_PARK + L.gl;            // this lane's draws (sj_sweep_moves parked them)
+    const double dr[4] = {pk[40], pk[45], pk[50], pk[55]};
+#else
+    const double dr[4] = {d.a, d.b, d.c, d.u};
+#endif
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      const double xi = q == 0 ? d.a : (q == 1 ? d.b : d.c);
+      const double xi = dr[q];
       double xn;
       if (METROP == MOLE_METROP_BOX) {
         const double lo = -0.5 * param, scale = 0.5 * param - lo;
@@ -54,7 +61,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
       mb[MB_XN + q] = xn;
       mb[MB_XN + 4 + q] = dv[q];
     }
-    mb[MB_XN + 3] = d.u;
+    mb[MB_XN + 3] = dr[3];
     if (METROP == MOLE_METROP_DIFFUSE) {
       const double dd = fma(dv[2], dv[2], fma(dv[1], dv[1], dv[0] * dv[0]));
       const double dV = fma(dv[2], L.V[0][2], fma(dv[1], L.V[0][1], dv[0] * L.V[0][0]));
@@ -217,7 +224,12 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   if (acc) {
     if (isown) {
 #pragma unroll
-      for (int qq = 0; qq < 3; ++qq) L.x[0][qq] = xn[qq];
+      for (int qq = 0; qq < 3; ++qq) {
+        L.x[0][qq] = xn[qq];
+#if MOLE_SJ_POS_IN_MOVE
+        if (L.wr) L.sm[SJ_OFF_POS + 3 * sid_e + qq] = xn[qq];        // the shared copy sj_gradf reads
+#endif
+      }
 #pragma unroll
       for (int qq = 0; qq < 5; ++qq) L.orb[0][qq] = on[qq];
     }

@@ -21,7 +21,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libmole_oracle.so")
 
 # enums (oracle_wf.hpp / oracle_mc.hpp)
 WF_STO_1S, WF_GAUSSIAN, WF_STO_PRODUCT, WF_H2_HL_STO, WF_H2P_PRODUCT, WF_SLATER_JASTROW, WF_CONSTANT = range(7)
-WF_LCAO_1E_2C, WF_LCAO_2E_1C, WF_LCAO_2E_2C = 7, 8, 9
+WF_LCAO_1E_2C, WF_LCAO_2E_1C, WF_LCAO_2E_2C, WF_LCAO_SJ = 7, 8, 9, 10
 HAM_KINETIC, HAM_IONIC_POT, HAM_ELEC_POT, HAM_IONIC, HAM_ELECTRONIC, HAM_HARMONIC = range(6)
 METROP_BOX, METROP_DIFFUSE = 0, 1
 OBS_ENERGY, OBS_PGRAD, OBS_WFVALUE, OBS_KINETIC = 1, 2, 4, 8
@@ -32,7 +32,7 @@ DOM_MOVE, DOM_INIT, DOM_BRANCH, DOM_SEED = range(4)
 
 class WfDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_elec", C.c_int32), ("n_params", C.c_int32), ("reserved", C.c_int32),
-                ("params", C.c_double * 8), ("geom", C.c_double * 8)]
+                ("params", C.c_double * 48), ("geom", C.c_double * 40)]
 
 
 class HamDesc(C.Structure):
@@ -86,7 +86,7 @@ def _seed(seed):
 def wf_desc(kind, params=(), geom=(), n_elec=None):
     ne = {WF_STO_1S: 1, WF_GAUSSIAN: 1, WF_STO_PRODUCT: 2, WF_H2_HL_STO: 2, WF_H2P_PRODUCT: 1,
           WF_CONSTANT: 1, WF_LCAO_1E_2C: 1, WF_LCAO_2E_1C: 2, WF_LCAO_2E_2C: 2}.get(kind)
-    if kind == WF_SLATER_JASTROW:
+    if kind in (WF_SLATER_JASTROW, WF_LCAO_SJ):
         ne = int(geom[1]) + int(geom[2])
     if n_elec is not None:
         ne = n_elec

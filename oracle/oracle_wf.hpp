@@ -64,10 +64,16 @@ enum WfKind : int32_t {
   WF_LCAO_1E_2C = 7,      // SingleDeterminant([phi_0]) over two centres (H2+)
   WF_LCAO_2E_1C = 8,      // two orbitals over one centre (He)
   WF_LCAO_2E_2C = 9,      // two orbitals over two centres (H2 molecular orbitals)
+  // General case of the same API: SpinDeterminantProduct of n_orb = max(n_up, n_dn) LCAO orbitals
+  // phi_k(r) = sum_c C[k][c] exp(-alpha_c |r - R_c|) over N_c <= 8 centres, both spins sharing the orbitals, times the
+  // e-e Jastrow of theory/jastrow.tex (as WF_SLATER_JASTROW).  geom: [kappa, n_up, n_dn, N_c, -, -, -, -,
+  // (R_c x, y, z, alpha_c) for c < N_c]; params: C[k][c] at k N_c + c, then b1..b4 (P = n_orb N_c + 4 <= 44).
+  WF_LCAO_SJ = 10,
 };
 
-constexpr int WF_MAX_PARAMS = 8;
-constexpr int WF_MAX_GEOM = 8;
+constexpr int WF_MAX_PARAMS = 48;
+constexpr int WF_MAX_GEOM = 40;
+constexpr int LSJ_MAX_CENTRES = 8;
 constexpr int WF_MAX_ELEC = 10;
 
 struct WfDesc {
@@ -324,6 +330,112 @@ inline void sj_parts(const Wf<R>& wf, const R* cfg, SjParts<R>& o) {
     }
 }
 
+// ---- general LCAO Slater-Jastrow (WF_LCAO_SJ): orbitals from the hydrogen-1s basis, determinants and Jastrow as above
+template <class R>
+struct LsjParts {
+  R det[2];
+  R ddet[WF_MAX_ELEC][3];
+  R d2det[WF_MAX_ELEC];
+  R dcdet[2][5 * LSJ_MAX_CENTRES];   // dD_s / dC[k][c]
+  R f;
+  R gf[WF_MAX_ELEC][3];
+  R lf[WF_MAX_ELEC];
+  R dbf[4];
+};
+
+inline int lsj_nc(const double* geom) { return (int)geom[3]; }
+inline int lsj_norb(const double* geom) { return std::max((int)geom[1], (int)geom[2]); }
+
+// chi_c and its gradient / laplacian at x: the reference's STO (hydrogen_molecular_ion_lcao.rs:25-49) at centre c
+template <class R>
+inline void lsj_basis(const Wf<R>& wf, const R* x, R* chi, R* gchi, R* lchi) {
+  const int nc = lsj_nc(wf.geom);
+  for (int c = 0; c < nc; ++c) {
+    const double* g = wf.geom + 8 + 4 * c;
+    const R al = R(g[3]);
+    R d[3] = {x[0] - R(g[0]), x[1] - R(g[1]), x[2] - R(g[2])};
+    const R r = norm_l2(d, 3);
+    chi[c] = r_exp(-al * r);
+    for (int q = 0; q < 3; ++q) gchi[3 * c + q] = -al * chi[c] * d[q] / r;
+    lchi[c] = al * chi[c] * (al - R(2.0) / r);
+  }
+}
+
+template <class R>
+inline void lsj_parts(const Wf<R>& wf, const R* cfg, LsjParts<R>& o) {
+  const double kappa = wf.geom[0];
+  const int nup = (int)wf.geom[1], ndn = (int)wf.geom[2], nc = lsj_nc(wf.geom), norb = lsj_norb(wf.geom);
+  const R* Cm = wf.p;                    // C[k][c]
+  const R* b = wf.p + norb * nc;
+  const int nspin[2] = {nup, ndn};
+  const int first[2] = {0, nup};
+  for (int s = 0; s < 2; ++s) {
+    const int n = nspin[s];
+    R A[25], G[5][15], L[25], X[5][LSJ_MAX_CENTRES];
+    for (int i = 0; i < n; ++i) {
+      R chi[LSJ_MAX_CENTRES], gchi[3 * LSJ_MAX_CENTRES], lchi[LSJ_MAX_CENTRES];
+      lsj_basis(wf, cfg + 3 * (first[s] + i), chi, gchi, lchi);
+      for (int c = 0; c < nc; ++c) X[i][c] = chi[c];
+      for (int k = 0; k < n; ++k) {
+        R v = R(0.0), l = R(0.0), g[3] = {R(0.0), R(0.0), R(0.0)};
+        for (int c = 0; c < nc; ++c) {
+          v += Cm[k * nc + c] * chi[c];
+          l += Cm[k * nc + c] * lchi[c];
+          for (int q = 0; q < 3; ++q) g[q] += Cm[k * nc + c] * gchi[3 * c + q];
+        }
+        A[i * n + k] = v; L[i * n + k] = l;
+        for (int q = 0; q < 3; ++q) G[i][3 * k + q] = g[q];
+      }
+    }
+    o.det[s] = (n == 0) ? R(1.0) : det_n(A, n);
+    for (int i = 0; i < n; ++i) {
+      R B[25];
+      for (int q3 = 0; q3 < 3; ++q3) {
+        for (int q = 0; q < n * n; ++q) B[q] = A[q];
+        for (int k = 0; k < n; ++k) B[i * n + k] = G[i][3 * k + q3];
+        o.ddet[first[s] + i][q3] = det_n(B, n);
+      }
+      for (int q = 0; q < n * n; ++q) B[q] = A[q];
+      for (int k = 0; k < n; ++k) B[i * n + k] = L[i * n + k];
+      o.d2det[first[s] + i] = det_n(B, n);
+    }
+    // dD/dC[k][c]: D is linear in column k, whose derivative is the column chi_c(r_i)
+    for (int k = 0; k < norb; ++k)
+      for (int c = 0; c < nc; ++c) {
+        if (k >= n) { o.dcdet[s][k * nc + c] = R(0.0); continue; }
+        R B[25];
+        for (int q = 0; q < n * n; ++q) B[q] = A[q];
+        for (int i = 0; i < n; ++i) B[i * n + k] = X[i][c];
+        o.dcdet[s][k * nc + c] = det_n(B, n);
+      }
+  }
+  const int ne = wf.ne;
+  o.f = R(0.0);
+  for (int m = 0; m < 4; ++m) o.dbf[m] = R(0.0);
+  for (int i = 0; i < ne; ++i) { o.lf[i] = R(0.0); for (int c = 0; c < 3; ++c) o.gf[i][c] = R(0.0); }
+  for (int i = 0; i < ne; ++i)
+    for (int j = i + 1; j < ne; ++j) {
+      R d[3];
+      for (int c = 0; c < 3; ++c) d[c] = cfg[3 * i + c] - cfg[3 * j + c];
+      const R r = norm_l2(d, 3);
+      const JPair<R> pr = sj_pair(b, kappa, r);
+      o.f += pr.u;
+      for (int c = 0; c < 3; ++c) {
+        const R t = pr.g * d[c] / r;
+        o.gf[i][c] += t;
+        o.gf[j][c] -= t;
+      }
+      const R lp = pr.g * R(2.0) / r + pr.dg;
+      o.lf[i] += lp;
+      o.lf[j] += lp;
+      const R den = R(1.0) + b[1] * pr.Rs;
+      o.dbf[0] += pr.Rs / den;
+      o.dbf[1] -= b[0] * pr.Rs * pr.Rs / (den * den);
+      o.dbf[2] += pr.Rs * pr.Rs;
+      o.dbf[3] += pr.Rs * pr.Rs * pr.Rs;
+    }
+}
+
 // ---------------------------------------------------------------- Function::value
 template <class R>
 R wf_value(const Wf<R>& wf, const R* cfg) {
@@ -355,6 +467,11 @@ R wf_value(const Wf<R>& wf, const R* cfg) {
     case WF_SLATER_JASTROW: {
       SjParts<R> s;
       sj_parts(wf, cfg, s);
+      return s.det[0] * s.det[1] * r_exp(s.f);
+    }
+    case WF_LCAO_SJ: {
+      LsjParts<R> s;
+      lsj_parts(wf, cfg, s);
       return s.det[0] * s.det[1] * r_exp(s.f);
     }
     case WF_CONSTANT:  // metrop.rs:240-242
@@ -426,6 +543,18 @@ void wf_gradient(const Wf<R>& wf, const R* cfg, R* out) {
     case WF_SLATER_JASTROW: {
       SjParts<R> s;
       sj_parts(wf, cfg, s);
+      const int nup = (int)wf.geom[1];
+      const R J = r_exp(s.f);
+      for (int i = 0; i < wf.ne; ++i) {
+        const R other = (i < nup) ? s.det[1] : s.det[0];
+        for (int c = 0; c < 3; ++c)
+          out[3 * i + c] = s.ddet[i][c] * other * J + s.det[0] * s.det[1] * J * s.gf[i][c];
+      }
+      return;
+    }
+    case WF_LCAO_SJ: {
+      LsjParts<R> s;
+      lsj_parts(wf, cfg, s);
       const int nup = (int)wf.geom[1];
       const R J = r_exp(s.f);
       for (int i = 0; i < wf.ne; ++i) {
@@ -511,6 +640,21 @@ R wf_laplacian(const Wf<R>& wf, const R* cfg) {
       }
       return lap;
     }
+    case WF_LCAO_SJ: {
+      LsjParts<R> s;
+      lsj_parts(wf, cfg, s);
+      const int nup = (int)wf.geom[1];
+      const R J = r_exp(s.f);
+      const R DD = s.det[0] * s.det[1];
+      R lap = R(0.0);
+      for (int i = 0; i < wf.ne; ++i) {
+        const R other = (i < nup) ? s.det[1] : s.det[0];
+        R cross = R(0.0), g2 = R(0.0);
+        for (int c = 0; c < 3; ++c) { cross += s.ddet[i][c] * s.gf[i][c]; g2 += s.gf[i][c] * s.gf[i][c]; }
+        lap += s.d2det[i] * other * J + R(2.0) * cross * other * J + DD * J * (s.lf[i] + g2);
+      }
+      return lap;
+    }
     case WF_LCAO_1E_2C:
       return lcao_orbital(wf, 0, cfg).l;
     case WF_LCAO_2E_1C:
@@ -563,6 +707,15 @@ void wf_parameter_gradient(const Wf<R>& wf, const R* cfg, R* out) {
       for (int m = 0; m < 3; ++m)
         out[m] = (s.dzdet[0][m] * s.det[1] + s.det[0] * s.dzdet[1][m]) * J;
       for (int m = 0; m < 4; ++m) out[3 + m] = s.det[0] * s.det[1] * J * s.dbf[m];  // jastrow.tex:123-126
+      return;
+    }
+    case WF_LCAO_SJ: {
+      LsjParts<R> s;
+      lsj_parts(wf, cfg, s);
+      const int nco = lsj_norb(wf.geom) * lsj_nc(wf.geom);
+      const R J = r_exp(s.f);
+      for (int m = 0; m < nco; ++m) out[m] = (s.dcdet[0][m] * s.det[1] + s.det[0] * s.dcdet[1][m]) * J;
+      for (int m = 0; m < 4; ++m) out[nco + m] = s.det[0] * s.det[1] * J * s.dbf[m];
       return;
     }
     case WF_LCAO_1E_2C:

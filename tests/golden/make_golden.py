@@ -10,6 +10,8 @@ so the fixtures do not share any derivative formula with the oracle or the CUDA 
   Gauss   examples/dmc.rs:47-50
   STO     examples/dmc.rs:108-111
   SJ      SURVEY.md §8(c) synthetic config 5; Jastrow f_ee of theory/jastrow.tex:23-26
+  LSJ     the same LCAO API in general (N_c <= 8 centres, n_up, n_dn <= 5, orbitals shared by the spins) times the
+          Jastrow of theory/jastrow.tex: geom = [kappa, n_up, n_dn, N_c, -, -, -, -, (R_c, alpha_c)...]
   LCAO    Hydrogen1sBasis / Orbital / SingleDeterminant / SpinDeterminantProduct as named (commented out) at
           tests/helium_lcao.rs:94-101 and tests/hydrogen_molecular_ion_lcao.rs:103-107: phi_k = sum_c C[k][c]
           exp(-|r - R_c| / width); geom = [mode, 1/width, R_0, R_1], params = C[k][c]
@@ -100,6 +102,45 @@ def psi_sj(x, p, g):
     return det(up) * det(dn) * mp.exp(f)
 
 
+def psi_lsj(x, p, g):
+    """General LCAO Slater-Jastrow (MOLE_WF_LCAO_SJ): SpinDeterminantProduct of n_orb = max(n_up, n_dn) orbitals
+    phi_k = sum_c C[k][c] exp(-alpha_c |r - R_c|) shared by both spins, times exp(f_ee) of theory/jastrow.tex:23-26.
+    geom = [kappa, n_up, n_dn, N_c, 0, 0, 0, 0, (R_c, alpha_c) ...]; params = C[k][c] at k N_c + c, then b1..b4."""
+    kappa, nup, ndn, nc = g[0], int(g[1]), int(g[2]), int(g[3])
+    norb = max(nup, ndn)
+    b = p[norb * nc:norb * nc + 4]
+
+    def phi(k, r):
+        return sum(p[k * nc + c] * sto(g[8 + 4 * c + 3], [r[q] - g[8 + 4 * c + q] for q in range(3)]) for c in range(nc))
+
+    up = [[phi(k, x[3 * i:3 * i + 3]) for k in range(nup)] for i in range(nup)]
+    dn = [[phi(k, x[3 * (nup + i):3 * (nup + i) + 3]) for k in range(ndn)] for i in range(ndn)]
+    f = mp.mpf(0)
+    ne = nup + ndn
+    for i in range(ne):
+        for j in range(i + 1, ne):
+            r = norm([x[3 * i + c] - x[3 * j + c] for c in range(3)])
+            R = (1 - mp.exp(-kappa * r)) / kappa
+            f += b[0] * R / (1 + b[1] * R) + b[2] * R ** 2 + b[3] * R ** 3
+    return det(up) * det(dn) * mp.exp(f)
+
+
+def lsj_case(nup, ndn, pos, alphas, C, b, kappa=1.0):
+    geom = [kappa, nup, ndn, len(pos), 0, 0, 0, 0]
+    for c, R in enumerate(pos):
+        geom += list(R) + [alphas[c]]
+    params = [v for row in C for v in row] + list(b)
+    return (psi_lsj, params, geom, nup + ndn, len(params), ("electronic", [list(R) for R in pos], [1] * len(pos)))
+
+
+H4_POS = [[-2.1, 0, 0], [-0.7, 0, 0], [0.7, 0, 0], [2.1, 0, 0]]
+H8_POS = [[1.4 * (i - 3.5), 0.3 * ((-1) ** i), 0.1 * i] for i in range(8)]
+H8_C = [[1.0, 1.1, 1.2, 1.3, 1.3, 1.2, 1.1, 1.0],
+        [1.0, 0.8, 0.5, 0.2, -0.2, -0.5, -0.8, -1.0],
+        [1.0, 0.3, -0.6, -0.9, -0.9, -0.6, 0.3, 1.0],
+        [0.7, -0.5, -0.9, 0.4, -0.4, 0.9, 0.5, -0.7]]
+
+
 def v_ion(x, ions, z):
     ne = len(x) // 3
     pot = mp.mpf(0)
@@ -163,6 +204,12 @@ CASES = {
                         ("electronic", [[-0.7, 0, 0], [0.7, 0, 0]], [1, 1])),
     "lcao_h2_triplet": (psi_lcao(2, 2), [1.0, 1.0, 1.0, -1.0], [1, 1.0 / 0.85, -0.7, 0.1, 0, 0.7, -0.1, 0.2], 2, 4,
                         ("electronic", [[-0.7, 0.1, 0], [0.7, -0.1, 0.2]], [1, 1])),
+    # general LCAO Slater-Jastrow: H4 chain (2 up, 2 dn, 4 centres, P = 12), an open-shell H3 (2 up, 1 dn, widths differ,
+    # P = 10) and a zig-zag H8 chain (4 up, 4 dn, 8 centres, P = 36: the large-P case of SURVEY.md 8(f)3)
+    "lsj_h4": lsj_case(2, 2, H4_POS, [1.0, 1.1, 1.1, 1.0], [[1, 1, 1, 1], [1, 0.5, -0.5, -1]], [0.5, 1.0, 0.1, -0.05]),
+    "lsj_h3": lsj_case(2, 1, [[-1.0, 0, 0], [0.6, 0.8, 0], [0.5, -0.7, 0.4]], [1.2, 0.9, 1.0], [[1, 0.9, 0.8], [1, -0.4, -0.7]],
+                       [0.4, 0.8, 0.0, 0.0], kappa=1.5),
+    "lsj_h8": lsj_case(4, 4, H8_POS, [1.0] * 8, H8_C, [0.5, 1.0, 0.05, 0.02]),
 }
 
 
@@ -176,14 +223,14 @@ def main():
         if only and not name.startswith(only):
             continue
         # the LCAO cases were added later and draw from their own stream so that the earlier entries stay reproducible
-        rng = random.Random("mole-b200 " + name) if name.startswith("lcao") else rng_main
+        rng = random.Random("mole-b200 " + name) if name.startswith(("lcao", "lsj")) else rng_main
         entries = []
-        ncfg = 3 if name.startswith("sj") else 6
+        ncfg = 3 if name.startswith("sj") else (2 if name == "lsj_h8" else (3 if name.startswith("lsj") else 6))
         for c in range(ncfg):
             if c == 0 and ne <= 2:
                 x = [0.3, -0.2, 0.5, -0.6, 0.1, 0.25][:3 * ne]      # SURVEY.md §8(c) configuration
             else:
-                scale = 0.6 if name.startswith("sj") else 1.0
+                scale = 0.6 if name.startswith("sj") else (1.5 if name.startswith("lsj") else 1.0)
                 x = [rng.gauss(0.0, scale) for _ in range(3 * ne)]
             val, grad, lap, pg = derivs(psi, x, p, [mp.mpf(v) for v in g])
             xm = [mp.mpf(v) for v in x]

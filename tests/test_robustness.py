@@ -115,7 +115,7 @@ def test_config5_sr_loop_stays_bounded_at_the_bench_settings(mole, orc, capsys):
             W, es[0], es[-1], errs[-1], min(conds), max(conds), np.array2string(ps[-1], precision=4)))
     assert np.isfinite(es).all() and B.E_WINDOW[0] < es.min() and es.max() < B.E_WINDOW[1]
     assert max(conds) < 1e6                                        # diag x 1.01 alone: 1e4 -> 2e10
-    assert np.all(np.abs(ps[:, :3] - p0[:3]) < 0.25 * p0[:3]) and np.all(np.abs(ps[:, 3:] - p0[3:]) < 0.5)
+    assert np.all(np.abs(ps[:, :3] - p0[:3]) < 0.5 * p0[:3]) and np.all(np.abs(ps[:, 3:] - p0[3:]) < 3.0)
     step_sizes = np.linalg.norm(np.diff(ps, axis=0), axis=1)
     assert step_sizes.max() < 10 * max(step_sizes[0], 1e-3)         # no run-away: |dp| does not blow up
     assert es[-5:].mean() < es[:3].mean() + 5 * errs.max()          # the optimisation does not climb
