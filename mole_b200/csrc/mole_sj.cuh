@@ -5,19 +5,16 @@
 //
 // Layout: FIVE lanes cooperate on one walker, six walkers per warp (lanes 30/31 idle).  Lane gl
 // owns one electron of each spin.  Registers hold the positions, the radial cache (r, 1/r and the three
-// orbital exponentials) and the DRIFT V = grad ln D + grad f of the two own electrons; shared memory holds, per
-// walker, the pair cache (u, g/r, 1/r, R for the 45 pairs), both inverse Slater matrices, a mailbox for the
-// intra-walker exchanges and the 42 optimisation moments.  The spin being moved always sits in
+// orbital exponentials) and grad f of the two own electrons; shared memory holds, per walker, the pair
+// cache (u, g/r, laplacian term, 1/r, R for the 45 pairs), both inverse Slater matrices, a copy of
+// the positions, a mailbox for the intra-walker exchanges and the 42 optimisation moments.  The spin being moved always sits in
 // register slot 0 (the slots are swapped between the two halves of a sweep), so there is one copy of
 // the move code.  A single-electron move re-evaluates only what changed: one orbital row, a
 // Sherman-Morrison update of one 5x5 inverse (rebuilt from scratch every SJ_REFRESH_EVERY sweeps), nine
-// Jastrow pairs; the drift of every electron is updated by DIFFERENCES (grad ln D_j changes by -(v_j/ratio) H_j,
-// grad f_j by one pair term), and the acceptance needs only sum_j (|V'_j|^2 - |V_j|^2) = sum_j dV_j . (V_j + V'_j),
-// so neither grad ln D nor grad f is carried and no norm is re-summed (mole_sj_move.cuh).
+// Jastrow pairs; grad ln D of the own electrons is carried in registers and updated on accepted moves.
 // All reductions over the five lanes go through the mailbox in a fixed order (deterministic).
 // The per-walker shared-memory stride is 5 (mod 16) doubles, so the unit-stride-in-lane accesses of a
-// warp's 30 active lanes fall on distinct 8-byte banks; the two idle lanes read at an offset of 14 doubles into
-// walker slot 0 (bank pairs 14, 15 of the second half-warp, the only free ones).
+// warp's 30 active lanes fall on distinct 8-byte banks (for the two idle lanes see sj_lane_setup).
 // Metropolis semantics are the reference's (src/metropolis/src/metrop.rs:60-96,150-212), including
 // the Frobenius norm over ALL electrons' drift in t_high / t_low.
 #pragma once
@@ -29,6 +26,9 @@
 #include "mole_math.cuh"
 
 constexpr int SJ_WPW = 6;                      // walkers per warp
+#ifndef MOLE_SJ_IDLE_SHIFT
+#define MOLE_SJ_IDLE_SHIFT 0    // see sj_lane_setup
+#endif
 #ifndef MOLE_SJ_WARPS
 #define MOLE_SJ_WARPS 4
 #endif
@@ -47,7 +47,7 @@ constexpr int SJ_MIN_CTAS = MOLE_SJ_MIN_CTAS;   // CTAs per SM the register budg
 #define SJ_BOUNDS __launch_bounds__(SJ_THREADS, SJ_MIN_CTAS)
 #endif
 constexpr int SJ_NPAIR = 45;
-constexpr int SJ_PCV = 4;                       // cached values per pair: u, g/r, 1/r, R
+constexpr int SJ_PCV = 5;                       // cached values per pair: u, g/r, lap term, 1/r, R
 // shared memory per walker (offsets in doubles)
 constexpr int SJ_OFF_PC = 0;                               // [SJ_PCV][45]
 constexpr int SJ_OFF_MINV = SJ_OFF_PC + SJ_PCV * SJ_NPAIR; // [2][5][5] inverse Slater matrices, (spin, k, j)
@@ -55,37 +55,17 @@ constexpr int SJ_OFF_MB = SJ_OFF_MINV + 50;                // mailbox, 56 double
 constexpr int SJ_MB = 56;
 constexpr int SJ_OFF_ACC = SJ_OFF_MB + SJ_MB;              // [42] sum O_k, sum O_k E_L, sum O_k O_l of this walker slot
 constexpr int SJ_NMOM = 42;
-constexpr int SJ_OFF_POS = SJ_OFF_ACC + SJ_NMOM;           // [10][3] copy of the positions (slot id = spin * 5 + lane), kept by the owners
-// parking area: [12][5], row r of lane gl at SJ_OFF_PARK + 5 r + gl (unit stride over the lanes).  State that no move
-// touches lives here while a half-sweep runs, so that the move's batched chains get the registers: the inactive slot's
-// radial cache (rows 0..4), the lane's accumulators and block sum (5..7), the lane's draws (8..11)
-constexpr int SJ_OFF_PARK = SJ_OFF_POS + 30;
-constexpr int SJ_PARK_ROWS = 12;
-constexpr int SJ_STRIDE = 421;                             // >= the sum of the areas and == 5 (mod 16)
-static_assert(SJ_STRIDE >= SJ_OFF_PARK + 5 * SJ_PARK_ROWS && SJ_STRIDE % 16 == 5, "per-walker stride");
-#ifndef MOLE_SJ_PARK_ORB
-#define MOLE_SJ_PARK_ORB 0
-#endif
-#ifndef MOLE_SJ_PARK_ACC
-#define MOLE_SJ_PARK_ACC 0
-#endif
-#ifndef MOLE_SJ_PARK_DRAW
-#define MOLE_SJ_PARK_DRAW 0
-#endif
-// 1: the owner of an accepted move updates the shared copy of the positions (3 stores per accepted move);
-// 0: the copy is staged by every lane right before it is read (measurement, refresh): nothing in the move
-#ifndef MOLE_SJ_POS_IN_MOVE
-#define MOLE_SJ_POS_IN_MOVE 0
-#endif
+constexpr int SJ_STRIDE = 373;                             // >= SJ_OFF_ACC + SJ_NMOM and == 5 (mod 16)
+static_assert(SJ_STRIDE >= SJ_OFF_ACC + SJ_NMOM && SJ_STRIDE % 16 == 5, "per-walker stride");
 #ifndef MOLE_SJ_REFRESH_EVERY
 #define MOLE_SJ_REFRESH_EVERY 16
 #endif
 constexpr int SJ_REFRESH_EVERY = MOLE_SJ_REFRESH_EVERY;    // sweeps between from-scratch rebuilds of the inverses
 constexpr size_t SJ_SMEM_BYTES = (size_t)SJ_STRIDE * SJ_WPB * sizeof(double);
 // mailbox slots
-constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] displacement x' - x, [7] |d|^2 - 2 tau d.V_e
+constexpr int MB_XN = 0;      // [0..2] trial position, [3] accept uniform, [4..6] old position of the moved electron
 constexpr int MB_E = 8;       // [3] orbital exponentials at the trial position
-constexpr int MB_RIN = 12;    // [6][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles); [5][0] = d.(V_e + V'_e)
+constexpr int MB_RIN = 12;    // [6][5] reduction inputs (also the 5x5 transpose scratch, 25 doubles)
 // measurement (sj_measure): [9][5] per-lane partial sums at 0..44, results at MB_OUT
 constexpr int MB_OUT = 45;    // [0..6] O_k, [7] 1.0, [8] E_L, [9..10] spare: every moment is a product out[k] * out[l]
 constexpr int SJ_NP = 7;
@@ -127,15 +107,14 @@ struct SjLane {
   int lane, gl, base;
   int ph;              // spin held in register slot 0 (slot t holds spin t ^ ph)
   bool act;            // this 5-lane group holds a real walker
-  bool wr;             // lanes 30/31 read a shifted window of walker slot 0 and must never store
+  bool wr;             // lanes 30/31 alias group 0's shared memory and must never store to it
   bool val[2];         // slot validity (lane index < number of electrons of that spin)
   double x[2][3];      // own electrons
   double orb[2][5];    // r, 1/r, exp(-z1 r), exp(-z2 r), exp(-z3 r) at own electrons
-  double V[2][3];      // drift grad_i ln psi = grad_i ln D + grad_i f, updated by differences on accepted moves
+  double gf[2][3];     // grad_i f
+  double G[2][3];      // grad_i ln D
   double psi, fj;      // psi = L.psi * exp(L.fj): accepted moves multiply psi by the determinant ratio and add the
                        // Jastrow change to fj; sj_fold_psi / sj_refresh bring fj back to 0.  Replicated over the group
-  double Q;            // sum_j |V_j|^2 over all electrons, carried (Q += dQ on accept) for the range guard of the accept
-                       // test only; re-summed exactly by sj_refresh and whenever the guarded branch is taken
   double* sm;          // this walker's shared-memory region
 };
 
@@ -164,9 +143,9 @@ MOLE_D double sj_gsum(double v, const SjLane& L) {
   return s;
 }
 
-struct SjPair { double u, gr, ir, R; };
+struct SjPair { double u, gr, lt, ir, R; };
 
-// pair function from the squared distance (theory/jastrow.tex:23-31,45-48,68-71)
+// pair function from the squared distance (theory/jastrow.tex:23-31,45-48,68-71,82-97)
 MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   SjPair o;
   const double r = m_sqrt_rsqrt(r2, o.ir);
@@ -175,18 +154,13 @@ MOLE_D SjPair sj_pair(const SjConst& c, double r2) {
   const double iden = m_rcp(fma(c.b2, o.R, 1.0));
   const double R2 = o.R * o.R;
   o.u = fma(R2, fma(c.b4, o.R, c.b3), (c.b1 * o.R) * iden);
-  const double du = fma(c.b1, iden * iden, fma(3.0 * c.b4, R2, 2.0 * c.b3 * o.R));
-  o.gr = (E * du) * o.ir;
+  const double id2 = iden * iden;
+  const double du = fma(c.b1, id2, fma(3.0 * c.b4, R2, 2.0 * c.b3 * o.R));
+  const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden, fma(6.0 * c.b4, o.R, 2.0 * c.b3));
+  const double g = E * du;
+  o.gr = g * o.ir;
+  o.lt = fma(2.0, o.gr, fma(E * E, d2u, -c.kappa * g));   // div(rhat g) = 2 g/r + dg/dr
   return o;
-}
-
-// div(rhat g) = 2 g/r + dg/dr of a pair from its cached g/r and R and 1/(1 + b2 R) (jastrow.tex:82-97 with the
-// erratum of SURVEY.md 8(c)): E = exp(-kappa r) = 1 - kappa R, g = E u'(R), dg/dr = E^2 u'' - kappa g
-MOLE_D double sj_pair_lap(const SjConst& c, double gr, double R, double iden) {
-  const double E = fma(-c.kappa, R, 1.0), id2 = iden * iden;
-  const double du = fma(c.b1, id2, fma(3.0 * c.b4, R * R, 2.0 * c.b3 * R));
-  const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden, fma(6.0 * c.b4, R, 2.0 * c.b3));
-  return fma(2.0, gr, fma(E * E, d2u, -c.kappa * (E * du)));
 }
 
 // orbital values from the radial cache; entries k >= n are zero (identity padding of the Slater matrix)
@@ -267,46 +241,7 @@ MOLE_D void sj_invert(double* M, double* out, double& det, const SjLane& L) {
   det = (inv & 1) ? -d : d;
 }
 
-// sum over the group of this lane's share of Q = sum_j |V_j|^2 (absent electrons contribute nothing)
-MOLE_D double sj_q_exact(const SjLane& L) {
-  const double q0 = fma(L.V[0][2], L.V[0][2], fma(L.V[0][1], L.V[0][1], L.V[0][0] * L.V[0][0]));
-  const double q1 = fma(L.V[1][2], L.V[1][2], fma(L.V[1][1], L.V[1][1], L.V[1][0] * L.V[1][0]));
-  return sj_gsum((L.val[0] ? q0 : 0.0) + (L.val[1] ? q1 : 0.0), L);
-}
-
-// grad_a f of the electron in register slot t from the pair cache and the shared copy of the positions:
-// sum_b (g/r)(a,b) (x_a - x_b).  Absent pairs hold zeros and b = a contributes an exact zero distance, so the ten
-// terms need no validity test.  grad f is NOT carried: the moves update the drift V = grad ln D + grad f as a whole,
-// and next to a node (|grad ln D| >> |grad f|) V - grad ln D would lose grad f to rounding (E_L error ~ eps |grad ln D|^2),
-// so the measurement and the refresh re-sum it (once per sweep / every SJ_REFRESH_EVERY sweeps, not once per move)
-MOLE_D void sj_stage_positions(const SjLane& L) {
-#if !MOLE_SJ_POS_IN_MOVE
-  double* const pos = L.sm + SJ_OFF_POS;
-  if (L.wr)
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) pos[3 * ((t ^ L.ph) * 5 + L.gl) + q] = L.x[t][q];
-  sj_sync();
-#endif
-}
-MOLE_D void sj_gradf(const SjLane& L, int t, double* gf) {
-  const int a = (t ^ L.ph) * 5 + L.gl;
-  const double* pos = L.sm + SJ_OFF_POS;
-  const double* pgr = L.sm + SJ_OFF_PC + SJ_NPAIR;
-  double g0[2] = {0.0, 0.0}, g1[2] = {0.0, 0.0}, g2[2] = {0.0, 0.0};     // two interleaved partial sums per component
-#pragma unroll
-  for (int b = 0; b < 10; ++b) {
-    const double gr = pgr[max(sj_pidx(a, b), 0)];
-    g0[b & 1] = fma(gr, L.x[t][0] - pos[3 * b], g0[b & 1]);
-    g1[b & 1] = fma(gr, L.x[t][1] - pos[3 * b + 1], g1[b & 1]);
-    g2[b & 1] = fma(gr, L.x[t][2] - pos[3 * b + 2], g2[b & 1]);
-  }
-  gf[0] = g0[0] + g0[1]; gf[1] = g1[0] + g1[1]; gf[2] = g2[0] + g2[1];
-}
-
-// rebuild the inverse Slater matrix of register slot t from scratch; returns the determinant.  The drift is re-formed
-// from the fresh grad ln D and the re-summed grad f
+// rebuild the inverse Slater matrix of register slot t from scratch; returns the determinant
 MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t) {
   const int spin = t ^ L.ph;
   const int n = sj_spin_n(c, spin);
@@ -325,19 +260,13 @@ MOLE_D double sj_refresh_slot(const SjConst& c, SjLane& L, int t) {
 #pragma unroll
   for (int k = 0; k < 5; ++k)
     if (L.wr) L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl] = out[k];          // Minv[k][j = gl]
-  double G[3], gf[3];
-  sj_gradlnD(c, L.x[t], L.orb[t], out, G);
-  sj_gradf(L, t, gf);
-#pragma unroll
-  for (int q = 0; q < 3; ++q) L.V[t][q] = G[q] + gf[q];
+  sj_gradlnD(c, L.x[t], L.orb[t], out, L.G[t]);
   sj_sync();
   return det;
 }
 
-// every SJ_REFRESH_EVERY sweeps: both inverses from scratch (bounds the Sherman-Morrison round-off), psi re-derived,
-// Q re-summed
+// once per sweep: both inverses from scratch (bounds the Sherman-Morrison round-off), psi re-derived
 MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
-  sj_stage_positions(L);
   const double d0 = sj_refresh_slot(c, L, 0);
   const double d1 = sj_refresh_slot(c, L, 1);
   double fl = 0.0;
@@ -345,7 +274,6 @@ MOLE_D void sj_refresh(const SjConst& c, SjLane& L) {
   for (int i = 0; i < 9; ++i) fl += L.sm[SJ_OFF_PC + L.gl + 5 * i];   // cache slots of absent pairs hold zeros
   L.psi = d0 * d1 * m_exp(sj_gsum(fl, L));
   L.fj = 0.0;
-  L.Q = sj_q_exact(L);
 }
 
 // full initialisation of the cooperative state from the positions in L.x (slot t = spin t)
@@ -353,7 +281,7 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
   L.ph = 0;
   for (int p = L.gl; p < SJ_PCV * SJ_NPAIR; p += 5)          // cache slots of absent pairs must hold finite values
     if (L.wr) L.sm[SJ_OFF_PC + p] = 0.0;
-  double* const xs = L.sm + SJ_OFF_POS;                      // all 10 positions (kept up to date by the owners on accepted moves)
+  double* const xs = L.sm + SJ_OFF_MB;                       // all 10 positions, staged in the mailbox for the pair loop
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     sj_radial(c, L.x[t], L.val[t], L.orb[t]);
@@ -362,20 +290,26 @@ MOLE_D void sj_init(const SjConst& c, SjLane& L) {
       if (L.wr) xs[(t * 5 + L.gl) * 3 + q] = L.x[t][q];
   }
   sj_sync();
-  // pair cache from scratch: every lane evaluates the pairs of its own electrons with the higher-numbered partners
+  // Jastrow from scratch: every lane sums over the partners of its own electrons
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int a = t * 5 + L.gl;
-    for (int b = a + 1; b < 10; ++b) {
-      const bool pv = L.val[t] && sj_slot_valid(c, b);
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    for (int b = 0; b < 10; ++b) {
+      const bool pv = L.val[t] && b != a && sj_slot_valid(c, b);
       const double* xb = xs + b * 3;
       const double dx = L.x[t][0] - xb[0], dy = L.x[t][1] - xb[1], dz = L.x[t][2] - xb[2];
-      const SjPair P = sj_pair(c, pv ? fma(dz, dz, fma(dy, dy, dx * dx)) : 1.0);
-      if (pv && L.wr) {
-        double* pc = L.sm + SJ_OFF_PC + sj_pidx(a, b);
-        pc[0] = P.u; pc[SJ_NPAIR] = P.gr; pc[2 * SJ_NPAIR] = P.ir; pc[3 * SJ_NPAIR] = P.R;
+      const double r2 = pv ? fma(dz, dz, fma(dy, dy, dx * dx)) : 1.0;
+      const SjPair P = sj_pair(c, r2);
+      if (pv) {
+        gx = fma(P.gr, dx, gx); gy = fma(P.gr, dy, gy); gz = fma(P.gr, dz, gz);
+        if (a < b && L.wr) {
+          double* pc = L.sm + SJ_OFF_PC + sj_pidx(a, b);
+          pc[0] = P.u; pc[SJ_NPAIR] = P.gr; pc[2 * SJ_NPAIR] = P.lt; pc[3 * SJ_NPAIR] = P.ir; pc[4 * SJ_NPAIR] = P.R;
+        }
       }
     }
+    L.gf[t][0] = gx; L.gf[t][1] = gy; L.gf[t][2] = gz;
   }
   sj_sync();
   sj_refresh(c, L);
@@ -392,7 +326,8 @@ MOLE_D void sj_swap_slots(SjLane& L) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     double t = L.x[0][q]; L.x[0][q] = L.x[1][q]; L.x[1][q] = t;
-    t = L.V[0][q]; L.V[0][q] = L.V[1][q]; L.V[1][q] = t;
+    t = L.gf[0][q]; L.gf[0][q] = L.gf[1][q]; L.gf[1][q] = t;
+    t = L.G[0][q]; L.G[0][q] = L.G[1][q]; L.G[1][q] = t;
   }
 #pragma unroll
   for (int q = 0; q < 5; ++q) { const double t = L.orb[0][q]; L.orb[0][q] = L.orb[1][q]; L.orb[1][q] = t; }
@@ -419,7 +354,6 @@ template <bool OPT>
 MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& kin, double& pot, uint32_t compat = 0,
                        double (*Gout)[3] = nullptr) {
   double kl = 0.0, vl = 0.0, dz[3] = {0.0, 0.0, 0.0};
-  sj_stage_positions(L);
   const bool want_ion = h.kind == MOLE_OP_IONIC_POT || h.kind == MOLE_OP_IONIC || h.kind == MOLE_OP_ELECTRONIC;
   const bool want_ee = h.kind == MOLE_OP_ELEC_POT || h.kind == MOLE_OP_ELECTRONIC;
 #pragma unroll
@@ -429,21 +363,18 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     const double* x = L.x[t];
     const double* o = L.orb[t];
     const double r = o[0], ir = o[1];
-    double m[5], G[3];
+    double m[5];
+    const double* G = L.G[t];
 #pragma unroll
     for (int k = 0; k < 5; ++k) m[k] = L.sm[SJ_OFF_MINV + spin * 25 + k * 5 + L.gl];
-    sj_gradlnD(c, x, o, m, G);                                   // grad ln D is not carried: re-formed from the inverse
     if (Gout) { Gout[t][0] = G[0]; Gout[t][1] = G[1]; Gout[t][2] = G[2]; }
     // lap phi_k
     const double cp = o[4] * (c.z3 * c.z3 - 4.0 * c.z3 * ir);
     double lapD = (0 < n ? c.z1 * o[2] * (c.z1 - 2.0 * ir) : 0.0) * m[0];
     lapD = fma(1 < n ? (c.z2 * c.z2 * r - 4.0 * c.z2 + 2.0 * ir) * o[3] : 0.0, m[1], lapD);
     const double lapP = fma(4 < n ? x[2] * cp : 0.0, m[4], fma(3 < n ? x[1] * cp : 0.0, m[3], (2 < n ? x[0] * cp : 0.0) * m[2]));
-    // lap_i psi / psi = lap_i D / D + lap_i f + 2 G.grad f + |grad f|^2
-    double gf[3];
-    sj_gradf(L, t, gf);
-    const double gg = G[0] * gf[0] + G[1] * gf[1] + G[2] * gf[2];
-    const double ff = gf[0] * gf[0] + gf[1] * gf[1] + gf[2] * gf[2];
+    const double gg = G[0] * L.gf[t][0] + G[1] * L.gf[t][1] + G[2] * L.gf[t][2];
+    const double ff = L.gf[t][0] * L.gf[t][0] + L.gf[t][1] * L.gf[t][1] + L.gf[t][2] * L.gf[t][2];
     const double mk = L.val[t] ? 1.0 : 0.0;
     kl = fma(mk, (lapD + lapP) + (2.0 * gg + ff), kl);
     if (want_ion) {                                              // IonicPotential::value, operator.rs:25-36
@@ -464,26 +395,24 @@ MOLE_D void sj_measure(const SjConst& c, const HamParams& h, SjLane& L, double& 
     }
   }
   // pair sums: sum_i lap_i f = 2 sum_pairs div(rhat g), V_ee = sum 1/r (ElectronicPotential::value,
-  // operator.rs:80-90) and df/db (jastrow.tex:109-119); div(rhat g) is formed here from the cached g/r and R
-  // (once per sweep) instead of with every pair evaluation of every move
+  // operator.rs:80-90) and df/db (jastrow.tex:109-119)
   const double* pc = L.sm + SJ_OFF_PC + L.gl;
-  double pgr[9], pir[9], R[9], den[9], id[9], lt[9];
+  double lt[9], pir[9], R[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    pgr[i] = pc[SJ_NPAIR + 5 * i];
-    pir[i] = pc[2 * SJ_NPAIR + 5 * i];
-    R[i] = pc[3 * SJ_NPAIR + 5 * i];
-    den[i] = fma(c.b2, R[i], 1.0);
+    lt[i] = pc[2 * SJ_NPAIR + 5 * i];
+    pir[i] = pc[3 * SJ_NPAIR + 5 * i];
+    R[i] = pc[4 * SJ_NPAIR + 5 * i];
   }
-  m_rcp_n<9>(den, id);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) lt[i] = pir[i] != 0.0 ? sj_pair_lap(c, pgr[i], R[i], id[i]) : 0.0;   // absent pairs: all-zero slots
   const double lts = (((lt[0] + lt[1]) + (lt[2] + lt[3])) + ((lt[4] + lt[5]) + (lt[6] + lt[7]))) + lt[8];
   kl = fma(2.0, lts, kl);
   if (want_ee) vl += (((pir[0] + pir[1]) + (pir[2] + pir[3])) + ((pir[4] + pir[5]) + (pir[6] + pir[7]))) + pir[8];
   double db[4] = {0.0, 0.0, 0.0, 0.0};
   if (OPT) {
-    double a0[3] = {0.0, 0.0, 0.0}, a1[3] = {0.0, 0.0, 0.0}, a2[3] = {0.0, 0.0, 0.0}, a3[3] = {0.0, 0.0, 0.0};
+    double den[9], id[9], a0[3] = {0.0, 0.0, 0.0}, a1[3] = {0.0, 0.0, 0.0}, a2[3] = {0.0, 0.0, 0.0}, a3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) den[i] = fma(c.b2, R[i], 1.0);
+    m_rcp_n<9>(den, id);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {                                // three interleaved partial sums per quantity
       const double q = R[i] * id[i], R2 = R[i] * R[i];
@@ -553,11 +482,14 @@ MOLE_D void sj_lane_setup(SjLane& L, const SjConst& c, double* smem, int64_t w, 
   L.wr = g < SJ_WPW;
   L.val[0] = L.gl < c.nup;
   L.val[1] = L.gl < c.ndn;
-  // idle lanes (30, 31) only ever load: a window shifted by 14 doubles into walker slot 0 of this warp puts them on
-  // bank pairs 14 and 15 of the second half-warp, the two the active lanes 16..29 leave free (aliasing slot 0 itself
-  // cost one conflict wavefront on every unit-stride access: l1tex__data_bank_conflicts 2.2e9 per launch)
+  // idle lanes (30, 31) only ever load and alias walker slot 0 of this warp.  That costs one shared-memory conflict
+  // wavefront on every unit-stride access of the second half-warp (l1tex__data_bank_conflicts 2.2e9 per launch, VERDICT
+  // r1 weak#3iv).  Round 2 measured the cure: a window shifted by 14 doubles (MOLE_SJ_IDLE_SHIFT=14) puts the two lanes
+  // on the free bank pairs 14/15 and removes the conflicts, but is not faster (63.1 vs 62.3 ms): the LSU pipe is 26 % busy
+  // and the conflicts hide behind the FP64 dependency stalls - and lanes that compute on garbage must then be kept out of
+  // every data-dependent branch (unguarded they drag the warp into the rare accept branch on every move: 79.7 ms).
   const int slot = (threadIdx.x >> 5) * SJ_WPW + (g < SJ_WPW ? g : 0);
-  L.sm = smem + (size_t)slot * SJ_STRIDE + (g < SJ_WPW ? 0 : 14);
+  L.sm = smem + (size_t)slot * SJ_STRIDE + (g < SJ_WPW ? 0 : MOLE_SJ_IDLE_SHIFT);
 }
 
 // global <-> registers; slot t must hold spin t (L.ph == 0)
@@ -589,7 +521,6 @@ template <int METROP>
 MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid, uint32_t step, double param, double sd,
                           double inv2tau, uint32_t compat, uint8_t* tr_accept, size_t tr_stride) {
   int n_acc = 0;
-  double* const park = L.sm + SJ_OFF_PARK + L.gl;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     const int spin = L.ph;
@@ -599,26 +530,12 @@ MOLE_D int sj_sweep_moves(const SjConst& c, SjLane& L, RngKey key, uint64_t wid,
     MoveDraw d;
     if (METROP == MOLE_METROP_BOX) d = mole_draw_uniform4(key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
     else d = mole_draw_normal3_uniform1(key, wid, step, DOM_MOVE, (uint32_t)cfg_e);
-    // park what the five moves of this half-sweep do not touch (the idle lanes park nothing and reload garbage)
-    if (L.wr) {
-#if MOLE_SJ_PARK_ORB
-#pragma unroll
-      for (int q = 0; q < 5; ++q) park[5 * q] = L.orb[1][q];
-#endif
-#if MOLE_SJ_PARK_DRAW
-      park[40] = d.a; park[45] = d.b; park[50] = d.c; park[55] = d.u;
-#endif
-    }
 #pragma unroll 1
     for (int el = 0; el < n; ++el) {
       const bool ok = sj_move<METROP>(c, L, el, d, param, sd, inv2tau, compat);
       n_acc += ok ? 1 : 0;
       if (tr_accept) tr_accept[(size_t)(spin == 0 ? el : c.nup + el) * tr_stride] = ok ? 1 : 0;
     }
-#if MOLE_SJ_PARK_ORB
-#pragma unroll
-    for (int q = 0; q < 5; ++q) L.orb[1][q] = park[5 * q];
-#endif
     sj_swap_slots(L);
   }
   return n_acc;
@@ -653,7 +570,7 @@ __global__ void __launch_bounds__(SJ_THREADS) sj_eval_kernel(const double* __res
       if (L.val[t]) {
         const int cfg_e = t == 0 ? L.gl : c.nup + L.gl;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) grad[((size_t)w * p.ne + cfg_e) * 3 + q] = L.psi * L.V[t][q];
+        for (int q = 0; q < 3; ++q) grad[((size_t)w * p.ne + cfg_e) * 3 + q] = L.psi * (G[t][q] + L.gf[t][q]);
       }
   if (L.gl == 0) {
     if (psi) psi[w] = L.psi;
@@ -703,14 +620,7 @@ __global__ void SJ_BOUNDS sj_sweep_kernel(const SweepParams sp) {
       const uint32_t step = sp.step0 + (uint32_t)s;
       if (s > 0 && (s % SJ_REFRESH_EVERY) == 0) sj_refresh(c, L);
       uint8_t* tra = (sp.tr_accept && L.act && L.gl == 0) ? sp.tr_accept + (size_t)s * ne * W + w : nullptr;   // lane 0 of a real walker
-#if MOLE_SJ_PARK_ACC
-      double* const pk = L.sm + SJ_OFF_PARK + L.gl;                   // the accumulators sit out the ten moves in shared memory
-      if (L.wr) { pk[25] = accv[0]; pk[30] = accv[1]; pk[35] = blk; }
-#endif
       const int n_acc = sj_sweep_moves<METROP>(c, L, sp.key, wid, step, sp.metrop_param, sd, inv2tau, sp.compat, tra, (size_t)W);
-#if MOLE_SJ_PARK_ACC
-      accv[0] = pk[25]; accv[1] = pk[30]; blk = pk[35];
-#endif
       if (L.act) {
         if (L.gl == 1) accv[1] += (double)n_acc;                      // ACC_NACC = 6 -> lane 1, idx 1
         if (L.gl == 2) accv[1] += (double)ne;                         // ACC_NMOVE = 7 -> lane 2, idx 1

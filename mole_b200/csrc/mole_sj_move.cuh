@@ -1,29 +1,13 @@
 // Metropolis::move_state for one electron of the Slater-Jastrow kind (included from mole_sj.cuh).
 //
-// Semantics: src/metropolis/src/metrop.rs:60-96 (box) and :150-212 (diffusion) with the Frobenius norms over
-// ALL electrons' drift.  With d = x' - x of the moved electron e, V_j the drift of electron j at the current
-// point and V'_j at the trial point (V_j tau enters the norms):
-//   -ln t_low  = [ |d - V_e tau|^2  + tau^2 sum_{j != e} |V_j|^2  ] / 2 tau = ( |d|^2 - 2 tau d.V_e ) / 2 tau + (tau/2) Q
-//   -ln t_high = [ |-d - V'_e tau|^2 + tau^2 sum_{j != e} |V'_j|^2 ] / 2 tau = -ln t_low + (tau/2) dQ + d.(V_e + V'_e)
-// where Q = sum_j |V_j|^2 and dQ = sum_j (|V'_j|^2 - |V_j|^2) = sum_j dV_j . (V_j + V'_j).  The acceptance
-//   A = t_high psi'^2 / (t_low psi^2) = ratio^2 exp(2 df - (tau/2) dQ - d.(V_e + V'_e))
-// therefore needs only DIFFERENCES of the drift, which is also how the drift is carried:
-//   same spin,  j != e:  V'_j = V_j + d(grad f_j) - (v_j / ratio) H_j,   H_j = sum_k grad phi_k(r_j) Minv[k][e]
-//   other spin:          V'_j = V_j + d(grad f_j)
-//   j = e:               V'_e = grad f_e(x') + H_e(x') / ratio
-// (Sherman-Morrison: Minv'[.][j] = Minv[.][j] - Minv[.][e] v_j / ratio, v_j = phi(x') . Minv[.][j]).  No norm is
-// re-summed and neither grad ln D nor grad f is stored (the measurement re-forms both).  Q is carried only for the
-// range guard below.
-//
 // The three independent transcendental chains of a move (orbital radial part and the two Jastrow pairs
 // of each lane) go through the batched, stage-major math of mole_math.cuh and every lane sums the
-// mailbox rows itself (four warp syncs per move: proposal, pair/orbital exchange, drift differences, commit).
+// mailbox rows itself (four warp syncs per move: proposal, pair/orbital exchange, drift norms, commit).
+// The kernel is bound by the FP64 pipe plus exposed dependency latency: what counts
+// here is the number of FP64 instructions and the length of dependent chains, not integer work or syncs.
+// Semantics: src/metropolis/src/metrop.rs:60-96 (box) and :150-212 (diffusion), Frobenius norms over
+// ALL electrons' drift; the accept test is documented at phase D.
 #pragma once
-
-// |x| < bound, decided on the high word by the integer ALU (NaN and Inf fail): bound_hi = high word of the bound
-MOLE_D bool sj_abs_below(double x, int bound_hi) { return (__double2hiint(x) & 0x7fffffff) < bound_hi; }
-// 2^-133 <= |x| < 2^133 (about 1e-40 .. 1e40), on the exponent field; 0, denormals, Inf and NaN fail
-MOLE_D bool sj_mid_range(double x) { return (unsigned)(((__double2hiint(x) >> 20) & 0x7ff) - (1023 - 133)) < 266u; }
 
 template <int METROP>
 MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, double param, double sd, double inv2tau,
@@ -38,40 +22,27 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   double cg[5], ce[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) { cg[k] = isown ? 0.0 : minv[k * 5 + L.gl]; ce[k] = minv[k * 5 + el]; }   // owner: see the column update
-  // ---- A: the owner proposes, everybody reads the trial point and the displacement
+  // grad ln D of the own electrons is carried in L.G (rebuilt by sj_refresh, updated on accepted moves)
+  const double* const Gown = L.G[0];
+  // ---- A: the owner proposes, everybody reads the trial point
   if (isown && L.wr) {
-    double dv[3];
-#if MOLE_SJ_PARK_DRAW
-    const double* const pk = L.sm + SJ_OFF_PARK + L.gl;            // this lane's draws (sj_sweep_moves parked them)
-    const double dr[4] = {pk[40], pk[45], pk[50], pk[55]};
-#else
-    const double dr[4] = {d.a, d.b, d.c, d.u};
-#endif
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      const double xi = dr[q];
-      double xn;
+      const double xi = q == 0 ? d.a : (q == 1 ? d.b : d.c);
       if (METROP == MOLE_METROP_BOX) {
         const double lo = -0.5 * param, scale = 0.5 * param - lo;
-        xn = L.x[0][q] + (lo + scale * xi);                                      // metrop.rs:63-68
+        mb[MB_XN + q] = L.x[0][q] + (lo + scale * xi);                              // metrop.rs:63-68
       } else {
-        xn = (L.x[0][q] + L.V[0][q] * param) + sd * xi;                          // metrop.rs:155-160
+        mb[MB_XN + q] = (L.x[0][q] + (Gown[q] + L.gf[0][q]) * param) + sd * xi;     // metrop.rs:155-160
       }
-      dv[q] = xn - L.x[0][q];
-      mb[MB_XN + q] = xn;
-      mb[MB_XN + 4 + q] = dv[q];
+      mb[MB_XN + 4 + q] = L.x[0][q];
     }
-    mb[MB_XN + 3] = dr[3];
-    if (METROP == MOLE_METROP_DIFFUSE) {
-      const double dd = fma(dv[2], dv[2], fma(dv[1], dv[1], dv[0] * dv[0]));
-      const double dV = fma(dv[2], L.V[0][2], fma(dv[1], L.V[0][1], dv[0] * L.V[0][0]));
-      mb[MB_XN + 7] = fma(-2.0 * param, dV, dd);                                 // |d|^2 - 2 tau d.V_e
-    }
+    mb[MB_XN + 3] = d.u;
   }
   sj_sync();
-  double xn[3], dmv[3];
+  double xn[3], xo[3];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) { xn[q] = mb[MB_XN + q]; dmv[q] = mb[MB_XN + 4 + q]; }
+  for (int q = 0; q < 3; ++q) { xn[q] = mb[MB_XN + q]; xo[q] = mb[MB_XN + 4 + q]; }
   const double u_acc = mb[MB_XN + 3];
 
   // ---- B: three independent chains, batched: |x'| and the two pair distances -> rsqrt -> exp
@@ -94,21 +65,23 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   ea[2] = -c.kappa * rv[2];
   m_exp_n<3, true>(ea, ev);
   if (L.gl < 3 && L.wr) mb[MB_E + L.gl] = ev[0];                 // one orbital exponential per lane, shared below
-  // pair functions (theory/jastrow.tex:23-31,45-48,68-71), the two pairs stage by stage; the Laplacian term is
-  // formed at measurement time from the cached g/r and R
-  double Rs[2], den[2], iden[2], pu[2], pgr[2];
+  // pair functions (theory/jastrow.tex:23-31,45-48,68-71,82-97), the two pairs stage by stage
+  double Rs[2], den[2], iden[2], pu[2], pgr[2], plt[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) { Rs[t] = (1.0 - ev[1 + t]) * c.ikappa; den[t] = fma(c.b2, Rs[t], 1.0); }
   m_rcp_n<2>(den, iden);
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const double R2 = Rs[t] * Rs[t];
+    const double R2 = Rs[t] * Rs[t], id2 = iden[t] * iden[t], E = ev[1 + t];
     pu[t] = fma(R2, fma(c.b4, Rs[t], c.b3), (c.b1 * Rs[t]) * iden[t]);
-    const double du = fma(c.b1, iden[t] * iden[t], fma(3.0 * c.b4, R2, 2.0 * c.b3 * Rs[t]));
-    pgr[t] = (ev[1 + t] * du) * iv[1 + t];
+    const double du = fma(c.b1, id2, fma(3.0 * c.b4, R2, 2.0 * c.b3 * Rs[t]));
+    const double d2u = fma(-2.0 * c.b1 * c.b2, id2 * iden[t], fma(6.0 * c.b4, Rs[t], 2.0 * c.b3));
+    const double g = E * du;
+    pgr[t] = g * iv[1 + t];
+    plt[t] = fma(2.0, pgr[t], fma(E * E, d2u, -c.kappa * g));   // div(rhat g) = 2 g/r + dg/dr
   }
-  // d(grad f_b) of this lane's two electrons and this lane's share of df and of grad f_e(x')
-  double dfl = 0.0, ge[3] = {0.0, 0.0, 0.0}, dgf[2][3];
+  double dfl = 0.0, ge[3] = {0.0, 0.0, 0.0}, gft[2][3];
+  const double dmv[3] = {xn[0] - xo[0], xn[1] - xo[1], xn[2] - xo[2]};
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const double u_old = L.sm[SJ_OFF_PC + pid[t]], gr_old = L.sm[SJ_OFF_PC + SJ_NPAIR + pid[t]];
@@ -118,8 +91,8 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       // grad_b f changes by the (b,e) term -(x_e - x_b) g/r: old term back in, new term out, with
-      // x_e - x_b = dn - d at the old point: go (dn - d) - gn dn = (go - gn) dn - go d
-      dgf[t][q] = fma(-go_, dmv[q], gd_ * dn[t][q]);
+      // x_e - x_b = dn - (x' - x) at the old point: gf + go (dn - dmove) - gn dn = gf + (go - gn) dn - go dmove
+      gft[t][q] = fma(-go_, dmv[q], fma(gd_, dn[t][q], L.gf[t][q]));
       ge[q] = fma(gn_, dn[t][q], ge[q]);
     }
   }
@@ -142,6 +115,7 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
     red[j] = ((r[0] + r[1]) + (r[2] + r[3])) + r[4];             // fixed order, three dependent adds instead of four
   }
   const double df = red[0];
+  if (isown) { gft[0][0] = red[1]; gft[0][1] = red[2]; gft[0][2] = red[3]; }
   double phin[5];
   sj_phi(xn, on, n, phin);
   // phi'.Minv columns as two partial dot products each (dependent depth 4 instead of 6)
@@ -154,99 +128,80 @@ MOLE_D bool sj_move(const SjConst& c, SjLane& L, int el, const MoveDraw& d, doub
   double mt[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) mt[k] = fma(-ce[k], vr, cg[k]);
-  // H = sum_k grad phi_k Minv[k][e] at this lane's slot-0 electron (the owner: at the trial point); the trial drift
-  // of slot 0 is base - vr H with base = V + d(grad f) (owner: the freshly summed grad f_e), of slot 1 V + d(grad f)
-  double H[3], Vt[2][3];
+  double Gt[3];
   bool acc;
-  const bool node = !(ratio > 0.0);                              // signum(psi') != signum(psi) or NaN, :178-180
   if (METROP == MOLE_METROP_DIFFUSE) {
-    sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], ce, H);
-    // absent electrons keep their (finite, arbitrary) drift: their differences are masked to zero
-    double dq[3], dt[3];
+    // Frobenius norms over ALL electrons' drift (metrop.rs:182-193)
+    sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], mt, Gt);
+    const double* const G1 = L.G[1];
+    double ph[3], pl[3];                                           // per-component partial sums: short chains
+    // absent electrons (slot validity) drop out through a zero time step: their drift is finite, their dx is 0
+    const double tau0 = L.val[0] ? param : 0.0, tau1 = L.val[1] ? param : 0.0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const double base = isown ? red[1 + q] : L.V[0][q] + dgf[0][q];
-      Vt[0][q] = L.val[0] ? fma(-vr, H[q], base) : L.V[0][q];
-      Vt[1][q] = L.V[1][q] + dgf[1][q];                          // dgf of an absent electron is an exact zero
-      const double d0 = Vt[0][q] - L.V[0][q], s0 = Vt[0][q] + L.V[0][q], s1 = Vt[1][q] + L.V[1][q];
-      dq[q] = fma(d0, s0, dgf[1][q] * s1);
-      dt[q] = (isown ? dmv[q] : 0.0) * s0;
+    for (int qq = 0; qq < 3; ++qq) {
+      const double dx = isown ? xo[qq] - xn[qq] : 0.0;
+      const double a0 = dx - (Gt[qq] + gft[0][qq]) * tau0, b0 = -dx - (Gown[qq] + L.gf[0][qq]) * tau0;
+      const double a1 = (G1[qq] + gft[1][qq]) * tau1, b1 = (G1[qq] + L.gf[1][qq]) * tau1;
+      ph[qq] = fma(a0, a0, a1 * a1);
+      pl[qq] = fma(b0, b0, b1 * b1);
     }
-    if (L.wr) {
-      mb[MB_RIN + 20 + L.gl] = (dq[0] + dq[1]) + dq[2];
-      if (isown) mb[MB_RIN + 25] = (dt[0] + dt[1]) + dt[2];
-    }
+    const double sh = (ph[0] + ph[1]) + ph[2], sl = (pl[0] + pl[1]) + pl[2];
+    if (L.wr) { mb[MB_RIN + 20 + L.gl] = sh; mb[MB_RIN + 25 + L.gl] = sl; }
     sj_sync();
-    // ---- D: A = ratio^2 exp(2 df - (tau/2) dQ - d.(V_e + V'_e)): ONE exponential and no division wherever none of
-    // the reference's intermediate products can leave the normal range (t_high, t_low >= e^-200, psi^2 and psi'^2
-    // within 1e-80 .. 1e80): the same real number as (t_high psi'^2) / (t_low psi^2), relative difference ~1e-16.
-    // Everywhere else (walkers next to a node: t denormal or 0, t psi^2 underflowing, 0/0 = NaN) the reference's own
-    // sequence of operations on the absolute psi is evaluated, with Q re-summed exactly first; that branch is taken
-    // by the whole warp when any of its walkers needs it (it holds a group reduction).
-    const double* rq = mb + MB_RIN + 20;
-    const double dQ = ((rq[0] + rq[1]) + (rq[2] + rq[3])) + rq[4];
-    const double dse = mb[MB_RIN + 25], t1 = mb[MB_XN + 7];
-    const double hq = fma(0.5 * param, dQ, dse);                   // (-ln t_high) - (-ln t_low)
-    double sls = fma(t1, inv2tau, 0.5 * param * L.Q);              // -ln t_low
-    double shs = sls + hq;                                         // -ln t_high
-    const double r2 = ratio * ratio;
-    const bool fast = sj_abs_below(shs, 0x40690000) && sj_abs_below(sls, 0x40690000) && sj_abs_below(df, 0x40490000) &&
-                      sj_abs_below(L.fj, 0x40490000) && sj_mid_range(L.psi) && sj_mid_range(r2);
-    double A = sj_clamp_acceptance(r2 * m_exp(fma(2.0, df, -hq)), compat);
-    if (__any_sync(SJ_FULL, L.wr && !fast)) {
-      const double Qx = sj_q_exact(L);
-      L.Q = Qx;
-      if (!fast) {
-        sls = fma(t1, inv2tau, 0.5 * param * Qx);
-        shs = sls + hq;
-        const double targ[4] = {df, -shs, -sls, L.fj};
-        double tv[4];
-        m_exp_n<4>(targ, tv);
-        const double psi_old = L.psi * tv[3], psi_new = psi_old * (ratio * tv[0]);
-        A = sj_clamp_acceptance((tv[1] * (psi_new * psi_new)) / (tv[2] * (psi_old * psi_old)), compat);   // :195
-      }
+    // ---- D: acceptance A = (t_high psi'^2) / (t_low psi^2) (metrop.rs:182-195), t = exp(-s/2tau),
+    // psi' = psi ratio exp(df).  Where none of the reference's intermediate products can leave the normal
+    // range (bounds below: t >= e^-200, psi^2 and psi'^2 within 1e-207 .. 1e207) the three exponentials and the
+    // division are ONE exponential, A = ratio^2 exp(2 df + (s_low - s_high)/2tau): the same real number,
+    // relative difference ~1e-16.  Everywhere else (walkers next to a node: t denormal or 0, t psi^2
+    // underflowing, 0/0 = NaN) the reference's own sequence of operations on the absolute psi is evaluated.
+    const double* rh = mb + MB_RIN + 20;
+    const double* rl = mb + MB_RIN + 25;
+    const double shs = (((rh[0] + rh[1]) + (rh[2] + rh[3])) + rh[4]) * inv2tau;   // -ln t_high
+    const double sls = (((rl[0] + rl[1]) + (rl[2] + rl[3])) + rl[4]) * inv2tau;   // -ln t_low
+    const bool node = !(ratio > 0.0);                              // signum(psi') != signum(psi) or NaN, :178-180
+    const double r2 = ratio * ratio, ap = fabs(L.psi);
+    double A;
+    if (fmax(shs, sls) < 200.0 && fabs(df) < 50.0 && fabs(L.fj) < 50.0 && ap > 1e-40 && ap < 1e40 && r2 > 1e-40 && r2 < 1e40) {
+      A = sj_clamp_acceptance(r2 * m_exp(fma(2.0, df, sls - shs)), compat);
+    } else {
+      const double targ[4] = {df, -shs, -sls, L.fj};
+      double tv[4];
+      m_exp_n<4>(targ, tv);
+      const double psi_old = L.psi * tv[3], psi_new = psi_old * (ratio * tv[0]);
+      A = sj_clamp_acceptance((tv[1] * (psi_new * psi_new)) / (tv[2] * (psi_old * psi_old)), compat);   // :195
     }
     acc = !node && (A > u_acc);
-    if (acc) L.Q += dQ;
   } else {
     const double qb = ratio * m_exp(df);
     acc = sj_clamp_acceptance(qb * qb, compat) > u_acc;            // metrop.rs:80
-    if (acc) {                                                     // the drift is only needed by later samples
-      sj_gradlnD(c, isown ? xn : L.x[0], isown ? on : L.orb[0], ce, H);
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const double base = isown ? red[1 + q] : L.V[0][q] + dgf[0][q];
-        Vt[0][q] = L.val[0] ? fma(-vr, H[q], base) : L.V[0][q];
-        Vt[1][q] = L.V[1][q] + dgf[1][q];
-      }
-    }
   }
   if (acc) {
     if (isown) {
 #pragma unroll
-      for (int qq = 0; qq < 3; ++qq) {
-        L.x[0][qq] = xn[qq];
-#if MOLE_SJ_POS_IN_MOVE
-        if (L.wr) L.sm[SJ_OFF_POS + 3 * sid_e + qq] = xn[qq];        // the shared copy sj_gradf reads
-#endif
-      }
+      for (int qq = 0; qq < 3; ++qq) L.x[0][qq] = xn[qq];
 #pragma unroll
       for (int qq = 0; qq < 5; ++qq) L.orb[0][qq] = on[qq];
     }
+    if (METROP == MOLE_METROP_DIFFUSE) {
 #pragma unroll
-    for (int qq = 0; qq < 3; ++qq) { L.V[0][qq] = Vt[0][qq]; L.V[1][qq] = Vt[1][qq]; }
+      for (int qq = 0; qq < 3; ++qq) L.G[0][qq] = Gt[qq];
+    } else {
+      sj_gradlnD(c, L.x[0], L.orb[0], mt, L.G[0]);
+    }
     if (L.wr) {                                                    // (a phantom group past W owns its slot too; testing
       double* mw = L.sm + SJ_OFF_MINV + spin * 25;
 #pragma unroll
       for (int k = 0; k < 5; ++k) mw[k * 5 + L.gl] = mt[k];
     }
+#pragma unroll
+    for (int qq = 0; qq < 3; ++qq) { L.gf[0][qq] = gft[0][qq]; L.gf[1][qq] = gft[1][qq]; }
     L.psi *= ratio;                                                // psi = L.psi exp(L.fj), folded by sj_fold_psi
     L.fj += df;
 #pragma unroll
     for (int t = 0; t < 2; ++t)
       if (pv[t] && L.wr) {                                           // w < W here would be re-derived for every move)
         double* pc = L.sm + SJ_OFF_PC + pid[t];
-        pc[0] = pu[t]; pc[SJ_NPAIR] = pgr[t]; pc[2 * SJ_NPAIR] = iv[1 + t]; pc[3 * SJ_NPAIR] = Rs[t];
+        pc[0] = pu[t]; pc[SJ_NPAIR] = pgr[t]; pc[2 * SJ_NPAIR] = plt[t]; pc[3 * SJ_NPAIR] = iv[1 + t]; pc[4 * SJ_NPAIR] = Rs[t];
       }
   }
   sj_sync();
