@@ -80,10 +80,16 @@ enum {
      phi_0(x_0) phi_1(x_1) (SpinDeterminantProduct, n_up = 1); mode 1: 2x2 determinant (SingleDeterminant). */
   MOLE_WF_LCAO_1E_2C = 7,     /* one electron, two centres (H2+):   psi = phi_0(x_0)             P=2 */
   MOLE_WF_LCAO_2E_1C = 8,     /* two electrons, one centre (He):    two orbitals                 P=2 */
-  MOLE_WF_LCAO_2E_2C = 9      /* two electrons, two centres (H2 MO): two orbitals                P=4 */
+  MOLE_WF_LCAO_2E_2C = 9,     /* two electrons, two centres (H2 MO): two orbitals                P=4 */
+  /* The same API in general: SpinDeterminantProduct of n_orb = max(n_up, n_dn) LCAO orbitals over
+     N_c <= 8 centres, n_up, n_dn <= 5, both spins sharing the orbitals, times the e-e Jastrow of theory/jastrow.tex
+     (b = 0 switches it off).  geom: [kappa, n_up, n_dn, N_c, 0, 0, 0, 0, (R_c x, y, z, alpha_c = 1/width_c) per centre];
+     params: C[k][c] at k N_c + c, then b1..b4: P = n_orb N_c + 4 <= 44.  With P > MOLE_ACC_MAX_PARAMS the optimisation
+     moments are the Gram matrix of the per-sample rows (mole_gram_*), not mole_acc_host. */
+  MOLE_WF_LCAO_SJ = 10
 };
-#define MOLE_WF_MAX_PARAMS 8
-#define MOLE_WF_MAX_GEOM 8
+#define MOLE_WF_MAX_PARAMS 48
+#define MOLE_WF_MAX_GEOM 40
 #define MOLE_WF_MAX_ELEC 10
 
 typedef struct {
@@ -264,6 +270,18 @@ int32_t mole_acc_device_ptr(mole_ens_t ens, void** ptr_dev, int32_t* n_doubles);
 int32_t mole_acc_finalize(const mole_acc_host* acc, double* energy, double* error, double* acceptance_per_sweep,
                           double* grad);
 
+/* ---- optimisation moments of a large-P kind (P > MOLE_ACC_MAX_PARAMS) -----------------
+ * A sweep with MOLE_OBS_PGRAD writes every sample's row v = (1, E_L, O_1 .. O_P) and contracts the rows into the
+ * Gram matrix G = sum v v^T on the device (fp64 SYRK on the tensor cores, mma.sync m8n8k4; mole_gram_select(ens, 1)
+ * runs the same contraction on the FP64 vector pipe).  G holds every moment the optimizers read: G[0][0] = n,
+ * G[0][1] = sum E, G[1][1] = sum E^2, G[0][2+k] = sum O_k, G[1][2+k] = sum O_k E, G[2+k][2+l] = sum O_k O_l
+ * (construct_sr_matrix optimizers.rs:191-233, compute_energy_gradient util.rs:6-46).  mole_acc_reset clears it. */
+int32_t mole_gram_get(mole_ens_t ens, int32_t* n_cols, double* gram /* (P+2)^2 row-major; NULL: query n_cols */);
+int32_t mole_gram_allreduce(mole_ens_t ens);
+int32_t mole_gram_device_ptr(mole_ens_t ens, void** ptr_dev, int32_t* n_doubles);
+int32_t mole_gram_select(mole_ens_t ens, int32_t impl /* 0: DMMA (default), 1: FP64 vector pipe */);
+int32_t mole_gram_finalize(int32_t n_cols, const double* gram, double* energy, double* grad /* P, nullable */);
+
 /* ---- NCCL communicator (walkers shard across the GPUs of one box) ------------------------------ */
 #define MOLE_NCCL_UNIQUE_ID_BYTES 128
 int32_t mole_comm_get_unique_id(uint8_t id[MOLE_NCCL_UNIQUE_ID_BYTES]);
@@ -289,6 +307,9 @@ int32_t mole_opt_step(mole_opt_t opt, const double* pars, const mole_acc_host* a
  * reference's hard-coded regularisation (optimizers.rs:225-231); an absolute shift is the usual stabiliser when
  * two parameters are nearly redundant (the Jastrow b1/b2 pair of the Slater-Jastrow kind). */
 int32_t mole_opt_set_sr_regularization(mole_opt_t opt, double diag_scale, double diag_shift);
+/* the same from the Gram matrix of a large-P kind (n_cols = P + 2) */
+int32_t mole_opt_step_gram(mole_opt_t opt, const double* pars, int32_t n_cols, const double* gram, double* deltap);
+int32_t mole_opt_sr_matrix_gram(mole_opt_t opt, int32_t n_cols, const double* gram, double* S);
 /* the regularised SR matrix the solve uses (P*P row-major), for parity tests */
 int32_t mole_opt_sr_matrix(mole_opt_t opt, const mole_acc_host* acc, double* S);
 

@@ -8,10 +8,10 @@ from . import ffi
 from .ffi import MoleError
 from .api import (Context, default_context, comm_unique_id, derive_seed, WaveFunction, STO, GaussianWaveFunction, Hydrogen1sBasis, Orbital, SingleDeterminant,
                   SpinDeterminantProduct,
-                  HeliumAtomWaveFunction, HydrogenMoleculeWaveFunction, H2WF, SlaterJastrow, WaveFunctionMock,
+                  HeliumAtomWaveFunction, HydrogenMoleculeWaveFunction, H2WF, SlaterJastrow, LcaoSlaterJastrow, WaveFunctionMock,
                   LocalOperator, KineticEnergy, IonicPotential, ElectronicPotential, IonicHamiltonian,
                   ElectronicHamiltonian, HarmonicHamiltonian, ParameterGradient, WavefunctionValue, operators,
-                  MetropolisBox, MetropolisDiffuse, Ensemble, acc_finalize, series_block_sizes, Optimizer, SteepestDescent, MomentumDescent,
+                  MetropolisBox, MetropolisDiffuse, Ensemble, acc_finalize, gram_finalize, series_block_sizes, Optimizer, SteepestDescent, MomentumDescent,
                   NesterovMomentum, OnlineLbfgs, StochasticReconfiguration, MonteCarloResult, Sampler, Runner,
                   VmcRunner, SRBrancher, SimpleBranching, DmcRunner)
 

@@ -240,10 +240,13 @@ class Hydrogen1sBasis:
     """Hydrogen1sBasis::new(ion_pos, widths): one function exp(-|r - R_c| / width) per centre.
     The device kinds take one width and one or two centres (closed set, like every other kind)."""
 
-    def __init__(self, ion_pos, widths):
+    def __init__(self, ion_pos, widths, general=False):
         self.ion_pos = np.asarray(ion_pos, dtype=np.float64).reshape(-1, 3)
         self.widths = [float(w) for w in widths]
-        if len(self.widths) != 1 or not 1 <= len(self.ion_pos) <= 2:
+        if general:                                              # for LcaoSlaterJastrow.from_orbitals: up to 8 centres
+            if not 1 <= len(self.ion_pos) <= 8 or len(self.widths) not in (1, len(self.ion_pos)):
+                raise MoleError(ffi.ERR_SHAPE, "general Hydrogen1sBasis: 1..8 centres, one width or one per centre")
+        elif len(self.widths) != 1 or not 1 <= len(self.ion_pos) <= 2:
             raise MoleError(ffi.ERR_SHAPE, "Hydrogen1sBasis on the device: one width, one or two centres")
 
     def clone(self):
@@ -302,6 +305,31 @@ class SlaterJastrow(WaveFunction):
 
     def __init__(self, n_up=5, n_dn=5, zeta=(9.64, 2.88, 2.88), b=(0.5, 1.0, 0.0, 0.0), kappa=1.0, ctx=None):
         super().__init__(list(zeta) + list(b), [kappa, n_up, n_dn], n_elec=n_up + n_dn, ctx=ctx)
+
+
+class LcaoSlaterJastrow(WaveFunction):
+    """SpinDeterminantProduct of LCAO orbitals over a Hydrogen1sBasis in general (tests/helium_lcao.rs:94-101: up to
+    5 + 5 electrons, up to 8 centres, both spins sharing the n_orb = max(n_up, n_dn) orbitals) times the e-e Jastrow
+    of theory/jastrow.tex.  coefficients[k][c] and b are the P = n_orb N_c + 4 variational parameters."""
+    KIND = ffi.WF_LCAO_SJ
+
+    def __init__(self, n_up, n_dn, ion_pos, widths, coefficients, b=(0.0, 1.0, 0.0, 0.0), kappa=1.0, ctx=None):
+        pos = np.asarray(ion_pos, dtype=np.float64).reshape(-1, 3)
+        nc, norb = len(pos), max(n_up, n_dn)
+        coef = np.asarray(coefficients, dtype=np.float64).reshape(norb, nc)
+        w = np.broadcast_to(np.asarray(widths, dtype=np.float64), (nc,))
+        if nc > 8 or norb > 5:
+            raise MoleError(ffi.ERR_SHAPE, "at most 8 centres and 5 orbitals per spin")
+        geom = [kappa, n_up, n_dn, nc, 0, 0, 0, 0]
+        for c in range(nc):
+            geom += list(pos[c]) + [1.0 / w[c]]
+        super().__init__(list(coef.reshape(-1)) + list(b), geom, n_elec=n_up + n_dn, ctx=ctx)
+
+    @classmethod
+    def from_orbitals(cls, orbitals, n_up, n_dn, b=(0.0, 1.0, 0.0, 0.0), kappa=1.0, ctx=None):
+        """SpinDeterminantProduct::new(orbitals, n_up) over Orbital::new(coefficients, basis) objects."""
+        basis = orbitals[0].basis
+        return cls(n_up, n_dn, basis.ion_pos, basis.widths, [o.coefficients.reshape(-1) for o in orbitals], b, kappa, ctx)
 
 
 class WaveFunctionMock(WaveFunction):
@@ -657,6 +685,21 @@ class Ensemble:
     def acc_allreduce(self):
         self._c(lib().mole_acc_allreduce(self.handle))
 
+    # ---- optimisation moments of a large-P kind: Gram matrix of the per-sample rows (1, E_L, O_k) ----
+    def gram_get(self):
+        n = C.c_int32()
+        self._c(lib().mole_gram_get(self.handle, C.byref(n), None))
+        g = np.empty((n.value, n.value))
+        self._c(lib().mole_gram_get(self.handle, C.byref(n), _dp(g)))
+        return g
+
+    def gram_allreduce(self):
+        self._c(lib().mole_gram_allreduce(self.handle))
+
+    def gram_select(self, impl):
+        """0: DMMA (tensor cores, default); 1: FP64 vector pipe."""
+        self._c(lib().mole_gram_select(self.handle, C.c_int32(impl)))
+
     def health(self):
         """(non-finite VMC samples skipped, DMC walker-steps killed) since the last acc_reset."""
         h = ffi.EnsHealth()
@@ -712,6 +755,15 @@ def acc_finalize(acc):
     return e.value, err.value, ac.value, g[:acc.n_params]
 
 
+def gram_finalize(gram):
+    """(mean energy, energy gradient) from the Gram matrix of a large-P kind (Ensemble.gram_get)."""
+    g = np.ascontiguousarray(gram, dtype=np.float64)
+    e = C.c_double()
+    grad = np.zeros(g.shape[0] - 2)
+    check(lib().mole_gram_finalize(C.c_int32(g.shape[0]), _dp(g), C.byref(e), _dp(grad)))
+    return e.value, grad
+
+
 # ---------------------------------------------------------------------------------------------------
 # Optimizers  (src/optimize/src/optimizers.rs)
 # ---------------------------------------------------------------------------------------------------
@@ -729,12 +781,20 @@ class Optimizer:
         """Optimizer::compute_parameter_update (optimize/src/traits.rs:18-25) from the reduced moments."""
         pars = np.ascontiguousarray(pars, dtype=np.float64)
         dp = np.empty(self.nparm)
-        check(lib().mole_opt_step(self.handle, _dp(pars), C.byref(acc), _dp(dp)))
+        if isinstance(acc, np.ndarray):                          # Gram matrix of a large-P kind (Ensemble.gram_get)
+            g = np.ascontiguousarray(acc, dtype=np.float64)
+            check(lib().mole_opt_step_gram(self.handle, _dp(pars), C.c_int32(g.shape[0]), _dp(g), _dp(dp)))
+        else:
+            check(lib().mole_opt_step(self.handle, _dp(pars), C.byref(acc), _dp(dp)))
         return dp
 
     def sr_matrix(self, acc):
         S = np.empty((self.nparm, self.nparm))
-        check(lib().mole_opt_sr_matrix(self.handle, C.byref(acc), _dp(S)))
+        if isinstance(acc, np.ndarray):
+            g = np.ascontiguousarray(acc, dtype=np.float64)
+            check(lib().mole_opt_sr_matrix_gram(self.handle, C.c_int32(g.shape[0]), _dp(g), _dp(S)))
+        else:
+            check(lib().mole_opt_sr_matrix(self.handle, C.byref(acc), _dp(S)))
         return S
 
     def __del__(self):

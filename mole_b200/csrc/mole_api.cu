@@ -11,6 +11,8 @@
 #include "mole_kernels.cuh"
 #include "mole_branch.cuh"
 #include "mole_sj.cuh"
+#include "mole_lsj.cuh"
+#include "mole_gram.cuh"
 #include "mole_stats.cuh"
 
 // errors raised without a context (NULL handles, mole_ctx_create); per thread, because different contexts may be
@@ -115,24 +117,26 @@ static int wf_kind_ne(const mole_wf_desc* d) {
   switch (d->kind) {
     case MOLE_WF_STO_1S: case MOLE_WF_GAUSSIAN: case MOLE_WF_H2P_PRODUCT: case MOLE_WF_CONSTANT: case MOLE_WF_LCAO_1E_2C: return 1;
     case MOLE_WF_STO_PRODUCT: case MOLE_WF_H2_HL_STO: case MOLE_WF_LCAO_2E_1C: case MOLE_WF_LCAO_2E_2C: return 2;
-    case MOLE_WF_SLATER_JASTROW: return (int)d->geom[1] + (int)d->geom[2];
+    case MOLE_WF_SLATER_JASTROW: case MOLE_WF_LCAO_SJ: return (int)d->geom[1] + (int)d->geom[2];
   }
   return -1;
 }
-static int wf_kind_np(int kind) {
+static int wf_kind_np(const mole_wf_desc* d) {
+  const int kind = d->kind;
   switch (kind) {
     case MOLE_WF_STO_1S: case MOLE_WF_GAUSSIAN: case MOLE_WF_STO_PRODUCT: case MOLE_WF_H2_HL_STO: return 1;
     case MOLE_WF_H2P_PRODUCT: case MOLE_WF_CONSTANT: return 0;
     case MOLE_WF_SLATER_JASTROW: return 7;
     case MOLE_WF_LCAO_1E_2C: case MOLE_WF_LCAO_2E_1C: return 2;   // coefficients C[k][c]
     case MOLE_WF_LCAO_2E_2C: return 4;
+    case MOLE_WF_LCAO_SJ: return std::max((int)d->geom[1], (int)d->geom[2]) * (int)d->geom[3] + 4;
   }
   return -1;
 }
 
 int32_t mole_wf_create(mole_ctx_t ctx, const mole_wf_desc* d, mole_wf_t* out) {
   if (!ctx || !d || !out) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "mole_wf_create: NULL argument");
-  const int ne = wf_kind_ne(d), np = wf_kind_np(d->kind);
+  const int ne = wf_kind_ne(d), np = wf_kind_np(d);
   if (ne < 0) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
   if (d->n_elec != ne) return mole_set_error(ctx, MOLE_ERR_SHAPE, "n_elec does not match the wavefunction kind");
   if (d->n_params != np) return mole_set_error(ctx, MOLE_ERR_SHAPE, "n_params does not match the wavefunction kind");
@@ -140,6 +144,12 @@ int32_t mole_wf_create(mole_ctx_t ctx, const mole_wf_desc* d, mole_wf_t* out) {
     const int nu = (int)d->geom[1], nd = (int)d->geom[2];
     if (nu < 0 || nd < 0 || nu > 5 || nd > 5 || nu + nd < 1 || !(d->geom[0] > 0.0))
       return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "Slater-Jastrow needs kappa>0 and 0<=n_up,n_dn<=5");
+  }
+  if (d->kind == MOLE_WF_LCAO_SJ) {
+    const int nu = (int)d->geom[1], nd = (int)d->geom[2], nc = (int)d->geom[3];
+    bool ok = nu >= 0 && nd >= 0 && nu <= 5 && nd <= 5 && nu + nd >= 1 && nc >= 1 && nc <= 8 && d->geom[0] > 0.0;
+    for (int c = 0; ok && c < nc; ++c) ok = d->geom[8 + 4 * c + 3] > 0.0;
+    if (!ok) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "LCAO Slater-Jastrow needs kappa>0, 0<=n_up,n_dn<=5, 1<=N_c<=8 and alpha_c = 1/width_c > 0");
   }
   if (d->kind >= MOLE_WF_LCAO_1E_2C && d->kind <= MOLE_WF_LCAO_2E_2C) {
     if (!(d->geom[1] > 0.0) || (d->geom[0] != 0.0 && d->geom[0] != 1.0))
@@ -245,6 +255,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
   cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath);
   cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen); cudaFree(e->sb_draws);
+  cudaFree(e->osamp); cudaFree(e->gram); cudaFree(e->gram_partials);
   mole_ctx_s* ctx = e->ctx;
   delete e;
   if (--ctx->live_ens == 0 && ctx->closing) ctx_free(ctx);
@@ -360,6 +371,9 @@ static int32_t eval_device(mole_ctx_s* ctx, const WfParams& wp, const HamParams*
     case K_SLATER_JASTROW:
       sj_eval_launch(STREAM(ctx), x_dev, W, wp, h, hp != nullptr, d_psi, d_grad, d_lap, d_h, d_pg);
       break;
+    case K_LCAO_SJ:
+      lsj_eval_kernel<<<cdiv(W, LSJ_THREADS), LSJ_THREADS, 0, STREAM(ctx)>>>(x_dev, W, wp, h, hp != nullptr, d_psi, d_grad, d_lap, d_h, d_pg);
+      break;
     default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
   }
   KERNEL_CHECK(ctx);
@@ -456,6 +470,33 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
   if (wf->p.kind == MOLE_WF_CONSTANT && m->kind == MOLE_METROP_DIFFUSE)
     return mole_set_error(ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
   if (a->n_sweeps == 0) return MOLE_OK;
+  const bool big_p = opt && wf->p.np > MOLE_ACC_MAX_PARAMS;     // moments = Gram matrix of the per-sample rows
+  if (big_p && wf->p.kind != K_LCAO_SJ) return mole_set_error(ctx, MOLE_ERR_SHAPE, "more than MOLE_ACC_MAX_PARAMS parameters");
+  if (big_p) {
+    // the rows of one launch must fit the sample buffer (<= 1 GiB): longer schedules run as several launches, which
+    // the counter-based streams make bit-identical to one
+    const int64_t ns_all = a->n_sweeps - a->n_discard;
+    const size_t row_bytes = (size_t)(wf->p.np + 2) * e->W * sizeof(double);
+    const int64_t cap = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / row_bytes));
+    if (ns_all > cap) {
+      if (a->energy_trace || a->wfvalue_trace || a->kinetic_trace || a->pgrad_trace || a->accept_trace)
+        return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "traces of a large-P sweep need a schedule that fits one launch");
+      mole_sweep_args part = *a;
+      int64_t left = a->n_sweeps;
+      bool first = true;
+      while (left > 0) {
+        const int64_t disc = first ? a->n_discard : 0;
+        const int64_t take = std::min<int64_t>(left, disc + cap);
+        part.n_sweeps = (int32_t)take; part.n_discard = (int32_t)std::min<int64_t>(disc, take);
+        if (!first && (a->flags & MOLE_SWEEP_KEEP_SERIES)) part.flags = (a->flags & ~MOLE_SWEEP_KEEP_SERIES) | MOLE_SWEEP_APPEND_SERIES;
+        const int32_t rc = mole_sweep(e, wf, m, op, &part);
+        if (rc != MOLE_OK) return rc;
+        left -= take;
+        first = false;
+      }
+      return MOLE_OK;
+    }
+  }
   MOLE_RANGE("mole_sweep");
   CU(ctx, cudaSetDevice(ctx->device));
 
@@ -507,6 +548,42 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
   if (wf->p.kind == K_SLATER_JASTROW) {
     const int32_t rc = sj_sweep_launch(ctx, e, sp, m->kind, opt);
     if (rc != MOLE_OK) return rc;
+  } else if (wf->p.kind == K_LCAO_SJ) {
+    const int cols = np + 2;
+    if (opt && nsamp > 0) {
+      const size_t need = (size_t)nsamp * cols * W;
+      if (need > e->osamp_cap) {
+        CU(ctx, cudaStreamSynchronize(STREAM(ctx)));
+        cudaFree(e->osamp);
+        e->osamp = nullptr; e->osamp_cap = 0;
+        CU(ctx, cudaMalloc(&e->osamp, need * sizeof(double)));
+        e->osamp_cap = need;
+      }
+      if (!e->gram) {
+        CU(ctx, cudaMalloc(&e->gram, GRAM_PAD * GRAM_PAD * sizeof(double)));
+        CU(ctx, cudaMemsetAsync(e->gram, 0, GRAM_PAD * GRAM_PAD * sizeof(double), STREAM(ctx)));
+        e->gram_rows = ctx->sm_count * 2;
+        CU(ctx, cudaMalloc(&e->gram_partials, (size_t)e->gram_rows * GRAM_PAD * GRAM_PAD * sizeof(double)));
+      }
+      sp.osamp = e->osamp;
+    }
+    const int blocks = std::min(cdiv(W, LSJ_THREADS), e->partial_rows);
+    if (m->kind == MOLE_METROP_BOX) {
+      if (opt) lsj_sweep_kernel<MOLE_METROP_BOX, true><<<blocks, LSJ_THREADS, 0, STREAM(ctx)>>>(sp);
+      else lsj_sweep_kernel<MOLE_METROP_BOX, false><<<blocks, LSJ_THREADS, 0, STREAM(ctx)>>>(sp);
+    } else {
+      if (opt) lsj_sweep_kernel<MOLE_METROP_DIFFUSE, true><<<blocks, LSJ_THREADS, 0, STREAM(ctx)>>>(sp);
+      else lsj_sweep_kernel<MOLE_METROP_DIFFUSE, false><<<blocks, LSJ_THREADS, 0, STREAM(ctx)>>>(sp);
+    }
+    if (sp.osamp) {                                          // S = O^T O (and every other moment): the Gram matrix of the rows
+      KERNEL_CHECK(ctx);
+      MOLE_RANGE("mole_gram");
+      if (e->gram_impl == 0) gram_dmma_kernel<<<e->gram_rows, GRAM_THREADS, 0, STREAM(ctx)>>>(e->osamp, W, nsamp, cols, e->gram_partials);
+      else gram_fma_kernel<<<e->gram_rows, GRAM_THREADS, 0, STREAM(ctx)>>>(e->osamp, W, nsamp, cols, e->gram_partials);
+      KERNEL_CHECK(ctx);
+      gram_fold_kernel<<<cdiv(GRAM_PAD * GRAM_PAD, 256), 256, 0, STREAM(ctx)>>>(e->gram_partials, e->gram_rows, e->gram);
+      e->gram_cols = cols;
+    }
   } else {
     const int blocks = std::min(cdiv(W, SWEEP_THREADS), e->partial_rows);
     switch (wf->p.kind) {
@@ -519,7 +596,7 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
   KERNEL_CHECK(ctx);
   e->step += (uint32_t)a->n_sweeps;
   if (a->observables & MOLE_OBS_ENERGY) e->blk_fill = (int32_t)((e->blk_fill + nsamp) % a->block_size);
-  if (opt) e->np_last = np;
+  if (opt && !big_p) e->np_last = np;
   e->el_cached = 0;
 
   const bool any_trace = (sp.tr_energy && a->energy_trace) || sp.tr_wfvalue || sp.tr_kinetic || sp.tr_pgrad || sp.tr_accept;
@@ -542,6 +619,7 @@ int32_t mole_acc_reset(mole_ens_t e) {
   CU(e->ctx, cudaSetDevice(e->ctx->device));
   CU(e->ctx, cudaMemsetAsync(e->acc, 0, ACC_DEV_LEN * sizeof(double), STREAM(e->ctx)));
   CU(e->ctx, cudaMemsetAsync(e->blk, 0, e->W * sizeof(double), STREAM(e->ctx)));
+  if (e->gram) CU(e->ctx, cudaMemsetAsync(e->gram, 0, GRAM_PAD * GRAM_PAD * sizeof(double), STREAM(e->ctx)));
   e->blk_fill = 0;
   return MOLE_OK;
 }
@@ -577,6 +655,35 @@ int32_t mole_acc_device_ptr(mole_ens_t e, void** p, int32_t* n) {
   return MOLE_OK;
 }
 
+// ------------------------------------------------------------------ Gram matrix of the per-sample rows (large-P kinds)
+int32_t mole_gram_get(mole_ens_t e, int32_t* n_cols, double* out) {
+  if (!e || !n_cols) return MOLE_ERR_INVALID_ARG;
+  *n_cols = e->gram_cols;
+  if (!out) return MOLE_OK;
+  if (!e->gram || e->gram_cols <= 0) return mole_set_error(e->ctx, MOLE_ERR_DATA_ACCESS, "no large-P \"Parameter gradient\" samples accumulated");
+  std::vector<double> h(GRAM_PAD * GRAM_PAD);
+  CU(e->ctx, cudaSetDevice(e->ctx->device));
+  CU(e->ctx, cudaMemcpyAsync(h.data(), e->gram, h.size() * sizeof(double), cudaMemcpyDeviceToHost, STREAM(e->ctx)));
+  CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
+  const int n = e->gram_cols;
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) out[a * n + b] = h[std::min(a, b) * GRAM_PAD + std::max(a, b)];   // symmetric from the upper triangle
+  return MOLE_OK;
+}
+
+int32_t mole_gram_device_ptr(mole_ens_t e, void** p, int32_t* n_doubles) {
+  if (!e || !p || !n_doubles) return MOLE_ERR_INVALID_ARG;
+  *p = e->gram;
+  *n_doubles = e->gram ? GRAM_PAD * GRAM_PAD : 0;
+  return MOLE_OK;
+}
+
+int32_t mole_gram_select(mole_ens_t e, int32_t impl) {
+  if (!e || (impl != 0 && impl != 1)) return MOLE_ERR_INVALID_ARG;
+  e->gram_impl = impl;
+  return MOLE_OK;
+}
+
 // ------------------------------------------------------------------ DMC
 }  // extern "C"
 
@@ -603,6 +710,9 @@ static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
   if (wf->p.kind == K_SLATER_JASTROW) {
     const int32_t rc = sj_dmc_launch(ctx, e, dp);
     if (rc != MOLE_OK) return rc;
+  } else if (wf->p.kind == K_LCAO_SJ) {
+    const int blocks = std::min(cdiv(e->W, LSJ_THREADS), e->partial_rows);
+    lsj_dmc_kernel<<<blocks, LSJ_THREADS, 0, STREAM(ctx)>>>(dp);
   } else {
     const int blocks = std::min(cdiv(e->W, SWEEP_THREADS), e->partial_rows);
     switch (wf->p.kind) {

@@ -138,4 +138,16 @@ int32_t mole_acc_allreduce(mole_ens_t e) {
   return MOLE_OK;
 }
 
+int32_t mole_gram_allreduce(mole_ens_t e) {
+  if (!e) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  if (ctx->nranks <= 1 || !e->gram) return MOLE_OK;
+  if (!ctx->nccl_comm) return mole_set_error(ctx, MOLE_ERR_NCCL, "mole_gram_allreduce before mole_comm_init");
+  MOLE_RANGE("mole_gram_allreduce");
+  cudaSetDevice(ctx->device);
+  const int rc = api().AllReduce(e->gram, e->gram, 48 * 48, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, (cudaStream_t)ctx->stream);
+  if (rc != 0) return nccl_fail(ctx, "ncclAllReduce", rc);
+  return MOLE_OK;
+}
+
 }  // extern "C"

@@ -52,28 +52,66 @@ static double vdot(const std::vector<double>& a, const std::vector<double>& b) {
   return r;
 }
 
+// the reduced moments every optimizer needs, from either source: the packed accumulators (P <= MOLE_ACC_MAX_PARAMS)
+// or the Gram matrix of the per-sample rows (1, E_L, O_1 .. O_P) of a large-P kind
+struct Moments {
+  int np = 0;
+  double n = 0.0, sum_e = 0.0;
+  std::vector<double> o, oe, oo;   // oo: full np x np, symmetric
+  bool finite() const {
+    bool ok = std::isfinite(n) && std::isfinite(sum_e);
+    for (double v : o) ok = ok && std::isfinite(v);
+    for (double v : oe) ok = ok && std::isfinite(v);
+    for (double v : oo) ok = ok && std::isfinite(v);
+    return ok;
+  }
+};
+
+static Moments moments_from_acc(const mole_acc_host* a, int np) {
+  Moments m;
+  m.np = np; m.n = a->n_samples; m.sum_e = a->sum_e;
+  m.o.assign(a->sum_o, a->sum_o + np);
+  m.oe.assign(a->sum_oe, a->sum_oe + np);
+  m.oo.assign((size_t)np * np, 0.0);
+  for (int k = 0; k < np; ++k)
+    for (int l = 0; l < np; ++l) m.oo[(size_t)k * np + l] = a->sum_oo[mole_oo_index(np, std::min(k, l), std::max(k, l))];
+  return m;
+}
+
+static Moments moments_from_gram(int n_cols, const double* g) {
+  Moments m;
+  const int np = n_cols - 2;
+  m.np = np; m.n = g[0]; m.sum_e = g[1];
+  m.o.resize(np); m.oe.resize(np); m.oo.resize((size_t)np * np);
+  for (int k = 0; k < np; ++k) {
+    m.o[k] = g[2 + k];
+    m.oe[k] = g[(size_t)n_cols + 2 + k];
+    for (int l = 0; l < np; ++l) m.oo[(size_t)k * np + l] = g[(size_t)(2 + k) * n_cols + 2 + l];
+  }
+  return m;
+}
+
 // gradient of the energy from the reduced moments: g_k = 2 (<O_k E> - <O_k><E>)   (util.rs:37-45)
-static bool energy_gradient(const mole_acc_host* a, int np, std::vector<double>& g) {
-  if (!(a->n_samples > 0.0)) return false;
-  const double n = a->n_samples, ebar = a->sum_e / n;
-  g.assign(np, 0.0);
-  for (int k = 0; k < np; ++k) g[k] = 2.0 * (a->sum_oe[k] / n - (a->sum_o[k] / n) * ebar);
+static bool energy_gradient(const Moments& a, std::vector<double>& g) {
+  if (!(a.n > 0.0)) return false;
+  const double n = a.n, ebar = a.sum_e / n;
+  g.assign(a.np, 0.0);
+  for (int k = 0; k < a.np; ++k) g[k] = 2.0 * (a.oe[k] / n - (a.o[k] / n) * ebar);
   return true;
 }
 
 // S_kl = <O_k O_l> - <O_k><O_l>, diagonal scaled by 1.01   (optimizers.rs:191-233)
-static void sr_matrix(const mole_opt_s* o, const mole_acc_host* a, std::vector<double>& S) {
+static void sr_matrix(const mole_opt_s* o, const Moments& a, std::vector<double>& S) {
   const int np = o->np;
-  const double n = a->n_samples;
+  const double n = a.n;
   S.assign((size_t)np * np, 0.0);
   double avg_sum = 0.0;
-  for (int k = 0; k < np; ++k) avg_sum += a->sum_o[k] / n;
+  for (int k = 0; k < np; ++k) avg_sum += a.o[k] / n;
   for (int k = 0; k < np; ++k)
     for (int l = 0; l < np; ++l) {
-      const int lo = std::min(k, l), hi = std::max(k, l);
-      double v = a->sum_oo[mole_oo_index(np, lo, hi)] / n;
+      double v = a.oo[(size_t)k * np + l] / n;
       if (o->compat & MOLE_COMPAT_SR_SUBTRACT) v -= avg_sum * avg_sum;   // sum_ij o_i o_j removed from every element (:219-224)
-      else v -= (a->sum_o[k] / n) * (a->sum_o[l] / n);
+      else v -= (a.o[k] / n) * (a.o[l] / n);
       S[(size_t)k * np + l] = v;
     }
   for (int k = 0; k < np; ++k) S[(size_t)k * np + k] = S[(size_t)k * np + k] * o->sr_diag_scale + o->sr_diag_shift;
@@ -110,14 +148,6 @@ static bool solve_dense(std::vector<double> a, std::vector<double> b, int n, std
     x[r] = s / a[(size_t)r * n + r];
   }
   return true;
-}
-
-// every moment the optimizers read must be finite: one NaN would otherwise reach the wavefunction parameters
-static bool moments_finite(const mole_acc_host* a, int np) {
-  bool ok = std::isfinite(a->n_samples) && std::isfinite(a->sum_e);
-  for (int k = 0; k < np; ++k) ok = ok && std::isfinite(a->sum_o[k]) && std::isfinite(a->sum_oe[k]);
-  for (int q = 0; q < np * (np + 1) / 2; ++q) ok = ok && std::isfinite(a->sum_oo[q]);
-  return ok;
 }
 
 static void lbfgs_push(mole_opt_s* o, const std::vector<double>& pars, const std::vector<double>& grad) {  // :148-159
@@ -179,14 +209,29 @@ int32_t mole_acc_finalize(const mole_acc_host* a, double* energy, double* error,
   if (acceptance) *acceptance = a->n_moves > 0.0 ? a->n_accept / a->n_moves : 0.0;   // vmc.rs:97
   if (grad) {
     std::vector<double> g;
-    energy_gradient(a, a->n_params, g);
+    energy_gradient(moments_from_acc(a, a->n_params), g);
     for (int k = 0; k < a->n_params; ++k) grad[k] = g[k];
   }
   return MOLE_OK;
 }
 
+// the same from the Gram matrix of a large-P kind: mean energy and gradient (the blocking error of such a run comes
+// from the ten scalar accumulators, mole_acc_finalize)
+int32_t mole_gram_finalize(int32_t n_cols, const double* gram, double* energy, double* grad) {
+  if (!gram || n_cols < 3) return MOLE_ERR_INVALID_ARG;
+  const Moments m = moments_from_gram(n_cols, gram);
+  if (!(m.n > 0.0)) return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "no samples in the Gram matrix");
+  if (energy) *energy = m.sum_e / m.n;
+  if (grad) {
+    std::vector<double> g;
+    energy_gradient(m, g);
+    for (int k = 0; k < m.np; ++k) grad[k] = g[k];
+  }
+  return MOLE_OK;
+}
+
 int32_t mole_opt_create(int32_t kind, int32_t np, double step, double mom, int32_t history, uint32_t compat, mole_opt_t* out) {
-  if (!out || kind < MOLE_OPT_SD || kind > MOLE_OPT_SR || np < 1 || np > MOLE_ACC_MAX_PARAMS)
+  if (!out || kind < MOLE_OPT_SD || kind > MOLE_OPT_SR || np < 1 || np > MOLE_WF_MAX_PARAMS)
     return mole_set_error(nullptr, MOLE_ERR_INVALID_ARG, "mole_opt_create: bad arguments");
   mole_opt_s* o = new mole_opt_s();
   o->kind = kind; o->np = np; o->step_size = step; o->momentum_parameter = mom; o->history = history; o->compat = compat;
@@ -201,15 +246,15 @@ int32_t mole_opt_sr_matrix(mole_opt_t o, const mole_acc_host* a, double* S) {
   if (!o || !a || !S) return MOLE_ERR_INVALID_ARG;
   if (a->n_params != o->np) return mole_set_error(nullptr, MOLE_ERR_SHAPE, "accumulator / optimizer parameter count mismatch");
   std::vector<double> m;
-  sr_matrix(o, a, m);
+  sr_matrix(o, moments_from_acc(a, o->np), m);
   std::copy(m.begin(), m.end(), S);
   return MOLE_OK;
 }
 
-static int32_t opt_step_unchecked(mole_opt_t o, const double* pars, const mole_acc_host* a, double* deltap) {
+static int32_t opt_step_unchecked(mole_opt_t o, const double* pars, const Moments& a, double* deltap) {
   const int np = o->np;
   std::vector<double> g;
-  if (!energy_gradient(a, np, g)) return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "no samples accumulated");
+  if (!energy_gradient(a, g)) return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "no samples accumulated");
   switch (o->kind) {
     case MOLE_OPT_SD:   // optimizers.rs:21-29
       for (int i = 0; i < np; ++i) deltap[i] = -(o->step_size * g[i]);
@@ -247,20 +292,42 @@ static int32_t opt_step_unchecked(mole_opt_t o, const double* pars, const mole_a
   return MOLE_ERR_INVALID_ARG;
 }
 
-int32_t mole_opt_step(mole_opt_t o, const double* pars, const mole_acc_host* a, double* deltap) {
-  if (!o || !pars || !a || !deltap) return MOLE_ERR_INVALID_ARG;
-  if (a->n_params != o->np)
-    return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "\"Parameter gradient\" moments missing or of the wrong size");
+static int32_t opt_step_checked(mole_opt_t o, const double* pars, const Moments& m, double* deltap) {
   MOLE_RANGE("mole_opt_step");
-  if (!moments_finite(a, o->np))
+  if (!m.finite())
     return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "non-finite optimisation moments (see mole_ensemble_health); no update computed");
   std::vector<double> dp(o->np, 0.0);
-  const int32_t rc = opt_step_unchecked(o, pars, a, dp.data());
+  const int32_t rc = opt_step_unchecked(o, pars, m, dp.data());
   if (rc != MOLE_OK) return rc;
   for (int i = 0; i < o->np; ++i)
     if (!std::isfinite(dp[i]))
       return mole_set_error(nullptr, MOLE_ERR_LINALG, "parameter update is not finite (ill-conditioned solve); parameters left untouched");
   for (int i = 0; i < o->np; ++i) deltap[i] = dp[i];
+  return MOLE_OK;
+}
+
+int32_t mole_opt_step(mole_opt_t o, const double* pars, const mole_acc_host* a, double* deltap) {
+  if (!o || !pars || !a || !deltap) return MOLE_ERR_INVALID_ARG;
+  if (a->n_params != o->np || o->np > MOLE_ACC_MAX_PARAMS)
+    return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "\"Parameter gradient\" moments missing or of the wrong size");
+  return opt_step_checked(o, pars, moments_from_acc(a, o->np), deltap);
+}
+
+// Optimizer::compute_parameter_update from the Gram matrix of the per-sample rows (1, E_L, O_1 .. O_P) of a large-P
+// kind (n_cols = P + 2, row-major, mole_gram_get): the same optimizers on the same moments
+int32_t mole_opt_step_gram(mole_opt_t o, const double* pars, int32_t n_cols, const double* gram, double* deltap) {
+  if (!o || !pars || !gram || !deltap) return MOLE_ERR_INVALID_ARG;
+  if (n_cols != o->np + 2)
+    return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "\"Parameter gradient\" moments missing or of the wrong size");
+  return opt_step_checked(o, pars, moments_from_gram(n_cols, gram), deltap);
+}
+
+int32_t mole_opt_sr_matrix_gram(mole_opt_t o, int32_t n_cols, const double* gram, double* S) {
+  if (!o || !gram || !S) return MOLE_ERR_INVALID_ARG;
+  if (n_cols != o->np + 2) return mole_set_error(nullptr, MOLE_ERR_SHAPE, "Gram matrix / optimizer parameter count mismatch");
+  std::vector<double> m;
+  sr_matrix(o, moments_from_gram(n_cols, gram), m);
+  std::copy(m.begin(), m.end(), S);
   return MOLE_OK;
 }
 
@@ -387,6 +454,13 @@ int32_t mole_vmc_run_optimization(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m,
     if (acceptance) acceptance[it] = accp;
     double pars[MOLE_WF_MAX_PARAMS], dp[MOLE_WF_MAX_PARAMS];
     mole_wf_get_parameters(wf, pars);
+    if (np > MOLE_ACC_MAX_PARAMS) {   // large-P kind: the moments are the Gram matrix of the per-sample rows
+      if (ctx->nranks > 1 && (rc = mole_gram_allreduce(ens)) != MOLE_OK) return rc;
+      int32_t nc = 0;
+      std::vector<double> gram((size_t)(np + 2) * (np + 2));
+      if ((rc = mole_gram_get(ens, &nc, gram.data())) != MOLE_OK) return rc;
+      if ((rc = mole_opt_step_gram(opt, pars, nc, gram.data(), dp)) != MOLE_OK) return rc;
+    } else
     if ((rc = mole_opt_step(opt, pars, &acc, dp)) != MOLE_OK) return rc;   // :85-89
     mole_wf_update_parameters(wf, dp);                                     // :91
     if (param_history) {

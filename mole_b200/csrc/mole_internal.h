@@ -89,6 +89,7 @@ struct SweepParams {
   double metrop_param;   // box side | tau
   // traces (device pointers, nullable)
   double* tr_energy; double* tr_wfvalue; double* tr_kinetic; double* tr_pgrad; uint8_t* tr_accept;
+  double* osamp;      // kinds with P > MOLE_ACC_MAX_PARAMS: per-sample rows (1, E_L, O_1..O_P), [sample][col][W]
   WfParams wf;
   HamParams ham;
 };
@@ -156,6 +157,12 @@ struct mole_ens_s {
   double* gath = nullptr;   // [nranks][4] all-gathered per-step DMC reductions (multi-rank block loop)
   int32_t* sb_list = nullptr; int32_t* sb_fen = nullptr; uint32_t* sb_mask = nullptr;   // SimpleBranching scratch
   int64_t* sb_draws = nullptr;
+  // kinds with P > MOLE_ACC_MAX_PARAMS: per-sample rows (1, E_L, O_k) and their Gram matrix (mole_gram.cuh)
+  double* osamp = nullptr; size_t osamp_cap = 0;       // doubles
+  double* gram = nullptr;                               // [48 x 48], upper triangle
+  double* gram_partials = nullptr; int gram_rows = 0;   // per-CTA partial matrices
+  int32_t gram_cols = 0;                                // P + 2 of the last sweep that touched gram
+  int32_t gram_impl = 0;                                // 0: DMMA (tensor cores), 1: FP64 vector pipe
 };
 
 // ---- host-only helpers (mole_host.cpp) ---------------------------------------------------------

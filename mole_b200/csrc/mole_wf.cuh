@@ -13,7 +13,7 @@
 #include "mole_math.cuh"
 
 enum { K_STO_1S = 0, K_GAUSSIAN = 1, K_STO_PRODUCT = 2, K_H2_HL_STO = 3, K_H2P_PRODUCT = 4, K_SLATER_JASTROW = 5,
-       K_CONSTANT = 6, K_LCAO_1E_2C = 7, K_LCAO_2E_1C = 8, K_LCAO_2E_2C = 9 };
+       K_CONSTANT = 6, K_LCAO_1E_2C = 7, K_LCAO_2E_1C = 8, K_LCAO_2E_2C = 9, K_LCAO_SJ = 10 };
 
 template <int KIND> struct WfDev;
 

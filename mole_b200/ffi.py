@@ -20,7 +20,8 @@ _ERR_NAMES = {1: "LinalgError", 2: "ShapeError", 3: "FuncError", 4: "OperatorVal
               102: "InvalidArgument", 103: "NoDevice", 104: "AssertionFailed"}
 
 WF_STO_1S, WF_GAUSSIAN, WF_STO_PRODUCT, WF_H2_HL_STO, WF_H2P_PRODUCT, WF_SLATER_JASTROW, WF_CONSTANT = range(7)
-WF_LCAO_1E_2C, WF_LCAO_2E_1C, WF_LCAO_2E_2C = 7, 8, 9
+WF_LCAO_1E_2C, WF_LCAO_2E_1C, WF_LCAO_2E_2C, WF_LCAO_SJ = 7, 8, 9, 10
+WF_MAX_PARAMS, WF_MAX_GEOM = 48, 40
 OP_KINETIC, OP_IONIC_POT, OP_ELEC_POT, OP_IONIC, OP_ELECTRONIC, OP_HARMONIC = range(6)
 METROP_BOX, METROP_DIFFUSE = 0, 1
 OBS_ENERGY, OBS_PGRAD, OBS_WFVALUE, OBS_KINETIC = 1, 2, 4, 8
@@ -43,7 +44,7 @@ class MoleError(RuntimeError):
 
 class WfDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_elec", C.c_int32), ("n_params", C.c_int32), ("reserved", C.c_int32),
-                ("params", C.c_double * 8), ("geom", C.c_double * 8)]
+                ("params", C.c_double * 48), ("geom", C.c_double * 40)]
 
 
 class OpDesc(C.Structure):
@@ -110,7 +111,8 @@ SYMBOLS = [
     "mole_dmc_diffuse", "mole_bench_fp64_peak", "mole_ctx_launch_count", "mole_math_probe",
     "mole_series_length", "mole_series_clear", "mole_series_block_sizes", "mole_series_analyze", "mole_series_get",
     "mole_series_write_text", "mole_runner_run_logged", "mole_ensemble_save", "mole_ensemble_load", "mole_dmc_block",
-    "mole_ensemble_health", "mole_opt_set_sr_regularization",
+    "mole_ensemble_health", "mole_opt_set_sr_regularization", "mole_gram_get", "mole_gram_allreduce",
+    "mole_gram_device_ptr", "mole_gram_select", "mole_gram_finalize", "mole_opt_step_gram", "mole_opt_sr_matrix_gram",
 ]
 
 _lib = None

@@ -58,6 +58,25 @@ def cases(mole=None):
     pt = [[-0.7, 0.1, 0], [0.7, -0.1, 0.2]]
     lcao("lcao_h2_triplet", O.WF_LCAO_2E_2C, [1.0, 1.0, 1.0, -1.0], 1.0 / 0.85, pt, [1, 1],
          lambda m: m.SingleDeterminant(orbs(m, pt, 0.85, [[1.0, 1.0], [1.0, -1.0]])))
+    # general LCAO Slater-Jastrow, same numbers as tests/golden/make_golden.py
+    def lsj(name, nup, ndn, pos, alphas, C, b, kappa=1.0):
+        geom = [kappa, nup, ndn, len(pos), 0, 0, 0, 0]
+        for i, R in enumerate(pos):
+            geom += list(R) + [alphas[i]]
+        params = [v for row in C for v in row] + list(b)
+        z = [1] * len(pos)
+        add(name, O.wf_desc(O.WF_LCAO_SJ, params, geom), O.ham_desc(O.HAM_ELECTRONIC, pos, z),
+            lambda m: (m.LcaoSlaterJastrow(nup, ndn, pos, [1.0 / a for a in alphas], C, b, kappa),
+                       m.ElectronicHamiltonian.from_ions(pos, z)))
+
+    h4 = [[-2.1, 0, 0], [-0.7, 0, 0], [0.7, 0, 0], [2.1, 0, 0]]
+    lsj("lsj_h4", 2, 2, h4, [1.0, 1.1, 1.1, 1.0], [[1, 1, 1, 1], [1, 0.5, -0.5, -1]], [0.5, 1.0, 0.1, -0.05])
+    lsj("lsj_h3", 2, 1, [[-1.0, 0, 0], [0.6, 0.8, 0], [0.5, -0.7, 0.4]], [1.2, 0.9, 1.0], [[1, 0.9, 0.8], [1, -0.4, -0.7]],
+        [0.4, 0.8, 0.0, 0.0], kappa=1.5)
+    h8 = [[1.4 * (i - 3.5), 0.3 * ((-1) ** i), 0.1 * i] for i in range(8)]
+    h8c = [[1.0, 1.1, 1.2, 1.3, 1.3, 1.2, 1.1, 1.0], [1.0, 0.8, 0.5, 0.2, -0.2, -0.5, -0.8, -1.0],
+           [1.0, 0.3, -0.6, -0.9, -0.9, -0.6, 0.3, 1.0], [0.7, -0.5, -0.9, 0.4, -0.4, 0.9, 0.5, -0.7]]
+    lsj("lsj_h8", 4, 4, h8, [1.0] * 8, h8c, [0.5, 1.0, 0.05, 0.02])
     return c
 
 

@@ -17,7 +17,8 @@ def _oracle_case(orc, name):
     kind = {"h2": orc.WF_H2_HL_STO, "he": orc.WF_STO_PRODUCT, "h2p": orc.WF_H2P_PRODUCT, "gauss_sho": orc.WF_GAUSSIAN,
             "gauss_h": orc.WF_GAUSSIAN, "sto_h": orc.WF_STO_1S, "sj_ne": orc.WF_SLATER_JASTROW,
             "sj_be": orc.WF_SLATER_JASTROW, "sj_li": orc.WF_SLATER_JASTROW, "lcao_h2p": orc.WF_LCAO_1E_2C,
-            "lcao_he": orc.WF_LCAO_2E_1C, "lcao_h2_singlet": orc.WF_LCAO_2E_2C, "lcao_h2_triplet": orc.WF_LCAO_2E_2C}[name]
+            "lcao_he": orc.WF_LCAO_2E_1C, "lcao_h2_singlet": orc.WF_LCAO_2E_2C, "lcao_h2_triplet": orc.WF_LCAO_2E_2C,
+            "lsj_h4": orc.WF_LCAO_SJ, "lsj_h3": orc.WF_LCAO_SJ, "lsj_h8": orc.WF_LCAO_SJ}[name]
     wf = orc.wf_desc(kind, g["params"], g["geom"], n_elec=g["n_elec"])
     wf.n_params = g["n_params"]
     if g["ham"][0] == "electronic":
@@ -105,7 +106,7 @@ def test_survey_golden_diffusion_move(orc):
 @pytest.mark.parametrize("name", sorted(GOLD.keys()))
 def test_mpmath_golden(orc, name):
     g, wf, ham = _oracle_case(orc, name)
-    sj = name.startswith("sj")
+    sj = name.startswith(("sj", "lsj"))
     tol = 2e-10 if sj else 1e-12   # row-replacement determinants lose a few digits near nodes
     for e in g["entries"]:
         cfg = np.array(e["cfg"]).reshape(-1, 3)
