@@ -426,6 +426,11 @@ int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops);
  * which = 0 exp, 1 reciprocal, 2 reciprocal square root, 3 square root, 4 natural log,
  * 5 / 6 sine / cosine of a fraction of a full turn */
 int32_t mole_math_probe(mole_ctx_t ctx, int32_t which, const double* in, int64_t n, double* out);
+/* the Gram contraction of the large-P path timed alone on synthetic rows (W walkers x n_samples x cols columns),
+ * impl 0: DMMA, 1: FP64 vector pipe; mean milliseconds of `reps` launches (CUDA events); checksum: sum of the upper
+ * triangle, to compare the two implementations.  Algorithmic bytes = 8 W n_samples cols (every row read once). */
+int32_t mole_bench_gram(mole_ctx_t ctx, int64_t n_walkers, int64_t n_samples, int32_t cols, int32_t impl, int32_t reps,
+                        double* ms, double* checksum);
 /* number of kernels this library has launched on ctx since creation */
 int32_t mole_ctx_launch_count(mole_ctx_t ctx, int64_t* n);
 

@@ -57,6 +57,13 @@ class Context:
         check(lib().mole_bench_fp64_peak(self.handle, C.byref(t)), self.handle)
         return t.value
 
+    def bench_gram(self, n_walkers, n_samples, cols, impl=0, reps=5):
+        """(ms per launch, GB/s of algorithmic bytes, checksum) of the Gram contraction alone on synthetic rows."""
+        ms, cs = C.c_double(), C.c_double()
+        check(lib().mole_bench_gram(self.handle, C.c_int64(n_walkers), C.c_int64(n_samples), C.c_int32(cols), C.c_int32(impl),
+                                    C.c_int32(reps), C.byref(ms), C.byref(cs)), self.handle)
+        return ms.value, 8.0 * n_walkers * n_samples * cols / (ms.value * 1e-3) / 1e9, cs.value
+
     def math_probe(self, which, x):
         """Device evaluation of the kernels' branch-free exp / rcp / rsqrt / sqrt (which = 0..3)."""
         x = np.ascontiguousarray(x, dtype=np.float64)

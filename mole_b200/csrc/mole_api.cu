@@ -948,6 +948,52 @@ int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops) {
   return MOLE_OK;
 }
 
+// ------------------------------------------------------------------ Gram contraction timed alone (roofline of the large-P path)
+// rows of (1, E, O_k)-like synthetic values, W walkers x n_samples samples x cols columns; returns the mean time of
+// `reps` launches (CUDA events on the context's stream) of the chosen implementation (0 DMMA, 1 FP64 vector pipe)
+int32_t mole_bench_gram(mole_ctx_t ctx, int64_t W, int64_t n_samples, int32_t cols, int32_t impl, int32_t reps, double* ms_out,
+                        double* checksum) {
+  if (!ctx || !ms_out || W < 1 || n_samples < 1 || cols < 3 || cols > GRAM_PAD || reps < 1) return MOLE_ERR_INVALID_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)W * n_samples * cols;
+  double *data = nullptr, *partials = nullptr, *gram = nullptr;
+  const int rows = ctx->sm_count * 2;
+  CU(ctx, cudaMalloc(&data, n * sizeof(double)));
+  CU(ctx, cudaMalloc(&partials, (size_t)rows * GRAM_PAD * GRAM_PAD * sizeof(double)));
+  CU(ctx, cudaMalloc(&gram, GRAM_PAD * GRAM_PAD * sizeof(double)));
+  CU(ctx, cudaMemsetAsync(gram, 0, GRAM_PAD * GRAM_PAD * sizeof(double), STREAM(ctx)));
+  gram_fill_kernel<<<ctx->sm_count * 8, 256, 0, STREAM(ctx)>>>(data, n);
+  KERNEL_CHECK(ctx);
+  cudaEvent_t a, b;
+  CU(ctx, cudaEventCreate(&a));
+  CU(ctx, cudaEventCreate(&b));
+  float total = 0.f;
+  for (int r = 0; r < reps + 1; ++r) {
+    CU(ctx, cudaEventRecord(a, STREAM(ctx)));
+    if (impl == 0) gram_dmma_kernel<<<rows, GRAM_THREADS, 0, STREAM(ctx)>>>(data, W, n_samples, cols, partials);
+    else gram_fma_kernel<<<rows, GRAM_THREADS, 0, STREAM(ctx)>>>(data, W, n_samples, cols, partials);
+    KERNEL_CHECK(ctx);
+    gram_fold_kernel<<<cdiv(GRAM_PAD * GRAM_PAD, 256), 256, 0, STREAM(ctx)>>>(partials, rows, gram);
+    KERNEL_CHECK(ctx);
+    CU(ctx, cudaEventRecord(b, STREAM(ctx)));
+    CU(ctx, cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, a, b));
+    if (r > 0) total += ms;
+  }
+  if (checksum) {
+    std::vector<double> h(GRAM_PAD * GRAM_PAD);
+    CU(ctx, cudaMemcpy(h.data(), gram, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    double s = 0.0;
+    for (int i = 0; i < cols; ++i)
+      for (int j = i; j < cols; ++j) s += h[i * GRAM_PAD + j];
+    *checksum = s / (reps + 1);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(data); cudaFree(partials); cudaFree(gram);
+  *ms_out = total / reps;
+  return MOLE_OK;
+}
+
 #include "mole_api_series.inc"
 
 }  // extern "C"

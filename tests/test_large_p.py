@@ -145,3 +145,13 @@ def test_gram_dmma_matches_the_vector_pipe_at_size(mole):
         out.append(ens.gram_get())
     assert out[0][0, 0] == W * 40
     assert np.max(np.abs(out[0] - out[1])) < 1e-11 * np.max(np.abs(out[0]))
+
+
+@pytest.mark.parametrize("W,ns,cols", [(333, 7, 38), (334, 5, 46), (16, 3, 3), (4099, 2, 14), (1 << 15, 20, 38)])
+def test_gram_kernels_agree_on_synthetic_rows(mole, W, ns, cols):
+    """odd and even walker counts (8-byte / 16-byte load paths of the DMMA kernel), ragged tails, 3 .. 46 columns: the
+    tensor-core contraction and the vector-pipe one give the same Gram matrix (checksum of the upper triangle)."""
+    ctx = mole.default_context()
+    a = ctx.bench_gram(W, ns, cols, 0, 1)
+    b = ctx.bench_gram(W, ns, cols, 1, 1)
+    assert abs(a[2] - b[2]) <= 1e-11 * max(abs(b[2]), 1.0), (a, b)
