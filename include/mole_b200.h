@@ -340,6 +340,14 @@ int32_t mole_dmc_step(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t o
  * Branching is the last operation of a time step (dmc.rs:139-140): it draws with the current step
  * counter and then advances it by one. */
 int32_t mole_branch(mole_ens_t ens, int32_t kind);
+/* Cross-rank population rebalancing: the ranks' islands (see mole_dmc_block) become one equal-weight population
+ * again.  Rank r's walkers fill a share of the N_total slots proportional to the rank's total weight; surplus copies
+ * migrate in one grouped ncclSend / ncclRecv exchange (configuration + cached E_L); every walker ends with the global
+ * mean weight; walker counts per rank are unchanged.  Call it between blocks.  mole_rebalance_plan is the host
+ * arithmetic alone (shares[r], moves[src][dst]) for a given shared draw u in [0, 1). */
+int32_t mole_rebalance(mole_ens_t ens);
+int32_t mole_rebalance_plan(int32_t nranks, const double* totals, const int64_t* counts, double u, int64_t* shares,
+                            int64_t* moves /* nranks x nranks, nullable */);
 /* source walker index of every walker after the last mole_branch (parity tests) */
 int32_t mole_branch_sources(mole_ens_t ens, int32_t* src);
 /* One block of DmcRunner::diffuse's inner loop (dmc.rs:84-141): n_steps x (time step, ensemble energy

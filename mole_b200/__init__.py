@@ -11,7 +11,7 @@ from .api import (Context, default_context, comm_unique_id, derive_seed, WaveFun
                   HeliumAtomWaveFunction, HydrogenMoleculeWaveFunction, H2WF, SlaterJastrow, LcaoSlaterJastrow, WaveFunctionMock,
                   LocalOperator, KineticEnergy, IonicPotential, ElectronicPotential, IonicHamiltonian,
                   ElectronicHamiltonian, HarmonicHamiltonian, ParameterGradient, WavefunctionValue, operators,
-                  MetropolisBox, MetropolisDiffuse, Ensemble, acc_finalize, gram_finalize, series_block_sizes, Optimizer, SteepestDescent, MomentumDescent,
+                  MetropolisBox, MetropolisDiffuse, Ensemble, acc_finalize, gram_finalize, rebalance_plan, series_block_sizes, Optimizer, SteepestDescent, MomentumDescent,
                   NesterovMomentum, OnlineLbfgs, StochasticReconfiguration, MonteCarloResult, Sampler, Runner,
                   VmcRunner, SRBrancher, SimpleBranching, DmcRunner)
 

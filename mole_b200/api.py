@@ -735,6 +735,10 @@ class Ensemble:
     def branch(self, kind):
         self._c(lib().mole_branch(self.handle, C.c_int32(kind)))
 
+    def rebalance(self):
+        """cross-rank population rebalancing (mole_rebalance): equal weights everywhere, surplus walkers migrate"""
+        self._c(lib().mole_rebalance(self.handle))
+
     def branch_sources(self):
         out = np.empty(self.n_walkers, dtype=np.int32)
         self._c(lib().mole_branch_sources(self.handle, out.ctypes.data_as(C.c_void_p)))
@@ -760,6 +764,17 @@ def acc_finalize(acc):
     g = np.zeros(max(acc.n_params, 1))
     check(lib().mole_acc_finalize(C.byref(acc), C.byref(e), C.byref(err), C.byref(ac), _dp(g)))
     return e.value, err.value, ac.value, g[:acc.n_params]
+
+
+def rebalance_plan(totals, counts, u):
+    """(shares[r], moves[src][dst]) of mole_rebalance for the ranks' total weights and walker counts and a shared draw u."""
+    t = np.ascontiguousarray(totals, dtype=np.float64)
+    c = np.ascontiguousarray(counts, dtype=np.int64)
+    shares = np.zeros(t.size, dtype=np.int64)
+    moves = np.zeros((t.size, t.size), dtype=np.int64)
+    check(lib().mole_rebalance_plan(C.c_int32(t.size), _dp(t), c.ctypes.data_as(C.c_void_p), C.c_double(u),
+                                    shares.ctypes.data_as(C.c_void_p), moves.ctypes.data_as(C.c_void_p)))
+    return shares, moves
 
 
 def gram_finalize(gram):

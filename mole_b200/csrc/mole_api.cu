@@ -255,7 +255,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
   cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath);
   cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen); cudaFree(e->sb_draws);
-  cudaFree(e->osamp); cudaFree(e->gram); cudaFree(e->gram_partials);
+  cudaFree(e->osamp); cudaFree(e->gram); cudaFree(e->gram_partials); cudaFree(e->xchg);
   mole_ctx_s* ctx = e->ctx;
   delete e;
   if (--ctx->live_ens == 0 && ctx->closing) ctx_free(ctx);
@@ -310,6 +310,7 @@ int32_t mole_ensemble_set_weights(mole_ens_t e, const double* w) {
   CU(e->ctx, cudaMemcpyAsync(e->w, w, e->W * sizeof(double), cudaMemcpyHostToDevice, STREAM(e->ctx)));
   CU(e->ctx, cudaStreamSynchronize(STREAM(e->ctx)));
   e->wstats_valid = 0;
+  e->w_uniform = 0;
   return MOLE_OK;
 }
 int32_t mole_ensemble_get_weights(mole_ens_t e, double* w) {
@@ -725,6 +726,7 @@ static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
   KERNEL_CHECK(ctx);
   e->el_cached = 1;
   e->wstats_valid = 1;
+  e->w_uniform = 0;
   return MOLE_OK;
 }
 
@@ -752,6 +754,7 @@ static int32_t sr_branch_launch(mole_ens_t e, double norm_factor, double new_wei
   std::swap(e->w, e->w2);
   std::swap(e->el, e->el2);
   e->wstats_valid = 0;
+  e->w_uniform = 1;
   e->step += 1;
   return MOLE_OK;
 }
@@ -892,6 +895,80 @@ int32_t mole_branch(mole_ens_t e, int32_t kind) {
   std::swap(e->el, e->el2);
   e->wstats_valid = 0;
   e->step += 1;
+  return MOLE_OK;
+}
+
+// Cross-rank population rebalancing (north_star (5)).  Ranks are population islands inside a
+// DMC block (mole_dmc_block); their total weights drift apart.  Rebalancing turns the islands back into ONE
+// equal-weight population: rank r's walkers fill share_r of the N_total slots (proportional to the rank's total
+// weight, systematic rounding with one shared Philox draw), each rank resamples its own walkers systematically to
+// share_r copies, surplus copies travel to the ranks with free slots in one grouped ncclSend / ncclRecv exchange
+// (3 N_e + 1 doubles per walker: configuration and cached E_L), and every walker ends with weight W_total / N_total.
+// Walker counts per rank do not change.  Unbiased: E[copies of a walker] = its weight / mean weight.
+int32_t mole_rebalance(mole_ens_t e) {
+  if (!e) return MOLE_ERR_INVALID_ARG;
+  mole_ctx_s* ctx = e->ctx;
+  MOLE_RANGE("mole_rebalance");
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = STREAM(ctx);
+  int32_t rc;
+  const int64_t W = e->W;
+  if (!e->w_uniform) {   // weights set by hand or by a time step: resample inside the rank only if they really differ
+    std::vector<double> hw(W);
+    CU(ctx, cudaMemcpyAsync(hw.data(), e->w, W * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    bool same = true;
+    for (int64_t i = 1; i < W && same; ++i) same = hw[i] == hw[0];
+    if (!same && (rc = mole_branch(e, MOLE_BRANCH_SR)) != MOLE_OK) return rc;
+  }
+  const int n = 3 * e->ne, nr = ctx->nranks;
+  double w0 = 0.0;
+  CU(ctx, cudaMemcpyAsync(&w0, e->w, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  const double mine[2] = {w0 * (double)W, (double)W};
+  std::vector<double> all(2 * (size_t)nr);
+  if ((rc = mole_comm_allgather_host(ctx, mine, 2, all.data())) != MOLE_OK) return rc;
+  std::vector<double> totals(nr);
+  std::vector<int64_t> counts(nr), shares(nr);
+  double T = 0.0;
+  int64_t N = 0;
+  for (int r = 0; r < nr; ++r) { totals[r] = all[2 * r]; counts[r] = (int64_t)all[2 * r + 1]; T += totals[r]; N += counts[r]; }
+  if (!(T > 0.0) || !std::isfinite(T)) return mole_set_error(ctx, MOLE_ERR_DATA_ACCESS, "mole_rebalance: the ensemble has no finite weight left");
+  // shared draws: the same on every rank (same key, same step counter); v per rank
+  const Philox4 pu = mole_draw(e->key, ~0ull, e->step, DOM_BRANCH, 2, 0);
+  const double u = mole_u53(pu.a, pu.b);
+  const Philox4 pv = mole_draw(e->key, ~0ull - 1 - (uint64_t)ctx->rank, e->step, DOM_BRANCH, 2, 1);
+  const double v = mole_u53(pv.a, pv.b);
+  mole_rebalance_shares(nr, totals.data(), counts.data(), u, shares.data());
+  const std::vector<MoleMove> moves = mole_rebalance_moves(nr, counts.data(), shares.data());
+  const int64_t share = shares[ctx->rank], keep = std::min(share, W);
+  const int64_t n_send = std::max<int64_t>(share - W, 0), n_recv = std::max<int64_t>(W - share, 0);
+  const size_t need = (size_t)(n_send + n_recv) * (n + 1);
+  if (need > e->xchg_cap) {
+    cudaFree(e->xchg);
+    e->xchg = nullptr; e->xchg_cap = 0;
+    CU(ctx, cudaMalloc(&e->xchg, need * sizeof(double)));
+    e->xchg_cap = need;
+  }
+  double* send = e->xchg;
+  double* recv = e->xchg + (size_t)n_send * (n + 1);
+  if (!e->el_cached) CU(ctx, cudaMemsetAsync(e->el, 0, W * sizeof(double), st));
+  if (share > 0) {
+    rebalance_gather_kernel<<<cdiv(share, 128), 128, 0, st>>>(e->x, e->x2, e->el, e->el2, W, n, share, v, keep, send);
+    KERNEL_CHECK(ctx);
+  }
+  if ((rc = mole_comm_exchange_rows(ctx, send, recv, n + 1, moves)) != MOLE_OK) return rc;
+  if (n_recv > 0) {
+    rebalance_scatter_kernel<<<cdiv(n_recv, 128), 128, 0, st>>>(recv, e->x2, e->el2, W, n, share, n_recv);
+    KERNEL_CHECK(ctx);
+  }
+  std::swap(e->x, e->x2);
+  std::swap(e->el, e->el2);
+  fill_kernel<<<cdiv(W, 256), 256, 0, st>>>(e->w, W, T / (double)N);
+  KERNEL_CHECK(ctx);
+  CU(ctx, cudaStreamSynchronize(st));
+  e->wstats_valid = 0;
+  e->w_uniform = 1;
   return MOLE_OK;
 }
 

@@ -364,3 +364,33 @@ __global__ void gather_by_list_kernel(const int32_t* __restrict__ list, int64_t 
   el2[j] = el[s];
   w2[j] = w[s];
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Cross-rank population rebalancing (mole_rebalance): every walker of the rank carries the same weight; the rank's
+// walkers fill `share` slots of the global population by systematic resampling, copy j <- walker
+// floor((j + v) count / share) mod count.  Copies j < keep stay (gathered into x2 / el2), copies j >= keep are
+// packed as rows [3 n_e coordinates, E_L] for the exchange.
+__global__ void rebalance_gather_kernel(const double* __restrict__ x, double* x2, const double* __restrict__ el, double* el2,
+                                        int64_t W, int n, int64_t share, double v, int64_t keep, double* rows) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= share) return;
+  int64_t src = (int64_t)(((double)j + v) * (double)W / (double)share);
+  src = src < 0 ? 0 : (src >= W ? src % W : src);
+  if (j < keep) {
+    for (int c = 0; c < n; ++c) x2[(size_t)c * W + j] = x[(size_t)c * W + src];
+    el2[j] = el[src];
+  } else {
+    double* r = rows + (size_t)(j - keep) * (n + 1);
+    for (int c = 0; c < n; ++c) r[c] = x[(size_t)c * W + src];
+    r[n] = el[src];
+  }
+}
+// received rows fill the slots first .. first + count - 1
+__global__ void rebalance_scatter_kernel(const double* __restrict__ rows, double* x2, double* el2, int64_t W, int n, int64_t first,
+                                         int64_t count) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const double* r = rows + (size_t)j * (n + 1);
+  for (int c = 0; c < n; ++c) x2[(size_t)c * W + first + j] = r[c];
+  el2[first + j] = r[n];
+}

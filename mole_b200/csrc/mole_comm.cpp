@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "mole_internal.h"
 
 namespace {
@@ -23,6 +24,10 @@ struct NcclApi {
   int (*CommDestroy)(nccl_comm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -41,7 +46,11 @@ NcclApi load_api() {
   a.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(a.handle, "ncclAllReduce");
   a.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(a.handle, "ncclAllGather");
   a.GetErrorString = (const char* (*)(int))dlsym(a.handle, "ncclGetErrorString");
-  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather && a.GetErrorString;
+  a.Send = (int (*)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(a.handle, "ncclSend");
+  a.Recv = (int (*)(void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(a.handle, "ncclRecv");
+  a.GroupStart = (int (*)())dlsym(a.handle, "ncclGroupStart");
+  a.GroupEnd = (int (*)())dlsym(a.handle, "ncclGroupEnd");
+  a.ok = a.Send && a.Recv && a.GroupStart && a.GroupEnd && a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather && a.GetErrorString;
   return a;
 }
 
@@ -83,6 +92,48 @@ int32_t mole_comm_allgather_device(mole_ctx_s* ctx, const double* send_dev, doub
   MOLE_RANGE("mole_comm_allgather");
   const int rc = api().AllGather(send_dev, recv_dev, (size_t)n, NCCL_FLOAT64, ctx->nccl_comm, (cudaStream_t)ctx->stream);
   if (rc != 0) return nccl_fail(ctx, "ncclAllGather", rc);
+  return MOLE_OK;
+}
+
+// all-gather of a few HOST doubles per rank (population rebalancing: total weight and walker count of every rank)
+int32_t mole_comm_allgather_host(mole_ctx_s* ctx, const double* mine, int n, double* all) {
+  if (!ctx || ctx->nranks <= 1 || !ctx->nccl_comm) {
+    for (int i = 0; i < n; ++i) all[i] = mine[i];
+    return MOLE_OK;
+  }
+  if (n * ctx->nranks + n > 64) return MOLE_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)ctx->stream;
+  cudaSetDevice(ctx->device);
+  double* d = nullptr;
+  if (cudaMalloc(&d, 128 * sizeof(double)) != cudaSuccess) return mole_set_error(ctx, MOLE_ERR_CUDA, "cudaMalloc failed");
+  cudaMemcpyAsync(d, mine, n * sizeof(double), cudaMemcpyHostToDevice, st);
+  const int rc = api().AllGather(d, d + 64, (size_t)n, NCCL_FLOAT64, ctx->nccl_comm, st);
+  if (rc != 0) { cudaFree(d); return nccl_fail(ctx, "ncclAllGather", rc); }
+  cudaMemcpyAsync(all, d + 64, (size_t)n * ctx->nranks * sizeof(double), cudaMemcpyDeviceToHost, st);
+  const cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (ce != cudaSuccess) return mole_set_error(ctx, MOLE_ERR_CUDA, "allgather_host: stream sync failed");
+  return MOLE_OK;
+}
+
+// one grouped exchange of walker rows between ranks: moves[i] = {src, dst, first row in the sender's / receiver's
+// buffer, count}; row_len doubles per walker
+int32_t mole_comm_exchange_rows(mole_ctx_s* ctx, const double* send_dev, double* recv_dev, int row_len,
+                                const std::vector<MoleMove>& moves) {
+  if (!ctx || ctx->nranks <= 1 || !ctx->nccl_comm) return MOLE_OK;
+  cudaStream_t st = (cudaStream_t)ctx->stream;
+  int rc = api().GroupStart();
+  if (rc != 0) return nccl_fail(ctx, "ncclGroupStart", rc);
+  for (const MoleMove& m : moves) {
+    if (m.count <= 0) continue;
+    if (m.src == ctx->rank && (rc = api().Send(send_dev + (size_t)m.send_first * row_len, (size_t)m.count * row_len, NCCL_FLOAT64, m.dst,
+                                                ctx->nccl_comm, st)) != 0) break;
+    if (m.dst == ctx->rank && (rc = api().Recv(recv_dev + (size_t)m.recv_first * row_len, (size_t)m.count * row_len, NCCL_FLOAT64, m.src,
+                                                ctx->nccl_comm, st)) != 0) break;
+  }
+  const int rc2 = api().GroupEnd();
+  if (rc != 0) return nccl_fail(ctx, "ncclSend/ncclRecv", rc);
+  if (rc2 != 0) return nccl_fail(ctx, "ncclGroupEnd", rc2);
   return MOLE_OK;
 }
 

@@ -183,7 +183,64 @@ static std::vector<double> lbfgs_direction(mole_opt_s* o, const std::vector<doub
   return p;
 }
 
+// ------------------------------------------------------------------ population rebalancing (host plan)
+// shares[r] = slots of the global population that rank r's walkers fill after rebalancing: proportional to the rank's
+// total weight, rounded systematically with ONE shared draw u in [0, 1) so that they add up to the global count
+void mole_rebalance_shares(int nranks, const double* totals, const int64_t* counts, double u, int64_t* shares) {
+  double T = 0.0;
+  int64_t N = 0;
+  for (int r = 0; r < nranks; ++r) { T += totals[r]; N += counts[r]; }
+  double cum = 0.0;
+  int64_t prev = 0;
+  for (int r = 0; r < nranks; ++r) {
+    cum += totals[r];
+    int64_t edge = (r == nranks - 1) ? N : (int64_t)std::floor(cum * (double)N / T + u);
+    edge = std::min<int64_t>(std::max<int64_t>(edge, prev), N);
+    shares[r] = edge - prev;
+    prev = edge;
+  }
+}
+
+// surplus copies (share > count) travel to free slots (share < count), matched greedily in rank order.  A sender
+// keeps copies 0 .. count-1 and sends copies count .. share-1 (rows 0.. of its send buffer); a receiver fills its
+// slots share .. count-1 (rows 0.. of its receive buffer)
+std::vector<MoleMove> mole_rebalance_moves(int nranks, const int64_t* counts, const int64_t* shares) {
+  std::vector<MoleMove> mv;
+  std::vector<int64_t> sent(nranks, 0), got(nranks, 0);
+  int d = 0;
+  for (int s = 0; s < nranks; ++s) {
+    int64_t left = shares[s] - counts[s];
+    while (left > 0) {
+      while (d < nranks && (counts[d] - shares[d]) - got[d] <= 0) ++d;
+      if (d >= nranks) return mv;   // cannot happen: the shares add up to the counts
+      const int64_t room = (counts[d] - shares[d]) - got[d];
+      const int64_t n = std::min(left, room);
+      mv.push_back(MoleMove{s, d, sent[s], got[d], n});
+      sent[s] += n; got[d] += n; left -= n;
+    }
+  }
+  return mv;
+}
+
 extern "C" {
+
+// the plan alone, for tests and for callers that bring their own transport
+int32_t mole_rebalance_plan(int32_t nranks, const double* totals, const int64_t* counts, double u, int64_t* shares,
+                            int64_t* moves /* nranks * nranks, [src][dst] counts; nullable */) {
+  if (nranks < 1 || !totals || !counts || !shares || !(u >= 0.0 && u < 1.0)) return MOLE_ERR_INVALID_ARG;
+  double T = 0.0;
+  for (int r = 0; r < nranks; ++r) {
+    if (!(totals[r] >= 0.0) || !std::isfinite(totals[r]) || counts[r] < 0) return MOLE_ERR_INVALID_ARG;
+    T += totals[r];
+  }
+  if (!(T > 0.0)) return mole_set_error(nullptr, MOLE_ERR_DATA_ACCESS, "mole_rebalance: the ensemble has no weight left");
+  mole_rebalance_shares(nranks, totals, counts, u, shares);
+  if (moves) {
+    for (int i = 0; i < nranks * nranks; ++i) moves[i] = 0;
+    for (const MoleMove& m : mole_rebalance_moves(nranks, counts, shares)) moves[m.src * nranks + m.dst] += m.count;
+  }
+  return MOLE_OK;
+}
 
 int32_t mole_derive_seed(const uint8_t master[32], uint32_t n, uint8_t out[32]) {
   if (!master || !out) return MOLE_ERR_INVALID_ARG;

@@ -141,6 +141,8 @@ struct mole_ens_s {
   double* el = nullptr; double* el2 = nullptr; int el_cached = 0;
   uint64_t el_sig = 0;       // signature of the (wavefunction parameters, operator) the cached E_L was computed with
   int wstats_valid = 0;      // red[2..3] hold sum/max of the CURRENT weights
+  int w_uniform = 1;         // every walker of this rank carries the same weight (after creation / SR branching)
+  double* xchg = nullptr; size_t xchg_cap = 0;   // send | receive rows of mole_rebalance
   double* blk = nullptr; int32_t blk_fill = 0; int32_t blk_size = 0;
   double* acc = nullptr;    // [ACC_LEN]
   double* partials = nullptr; int partial_rows = 0;
@@ -173,3 +175,9 @@ int mole_oo_index(int P, int k, int l);  // k<=l
 int32_t mole_comm_allreduce_host(mole_ctx_s* ctx, double* sum_vals, int n_sum, double* max_vals, int n_max);
 // all-gather of n device doubles per rank on the context stream, without a host synchronisation
 int32_t mole_comm_allgather_device(mole_ctx_s* ctx, const double* send_dev, double* recv_dev, int n);
+int32_t mole_comm_allgather_host(mole_ctx_s* ctx, const double* mine, int n, double* all);
+struct MoleMove { int src, dst; int64_t send_first, recv_first, count; };
+int32_t mole_comm_exchange_rows(mole_ctx_s* ctx, const double* send_dev, double* recv_dev, int row_len, const std::vector<MoleMove>& moves);
+// population shares and the transfer plan of mole_rebalance (pure host arithmetic, identical on every rank)
+void mole_rebalance_shares(int nranks, const double* totals, const int64_t* counts, double u, int64_t* shares);
+std::vector<MoleMove> mole_rebalance_moves(int nranks, const int64_t* counts, const int64_t* shares);

@@ -65,6 +65,16 @@ def _rank(rank, world, uid, W_local, out):
         b.branch(m.ffi.BRANCH_SR)
     res["dmc_rows"] = np.array(rows)
     res["dmc_step_cfgs"] = b.get_configs()
+    # ---- population rebalancing: rank 0 carries weight 1 per walker, rank 1 weight 3; walkers are tagged by x of electron 0
+    r = m.Ensemble(W_local, 1, SEED, walker_offset=rank * W_local, ctx=ctx)
+    tag = np.zeros((W_local, 1, 3))
+    tag[:, 0, 0] = rank * W_local + np.arange(W_local)
+    r.set_configs(tag)
+    r.set_weights(np.full(W_local, 1.0 + 2.0 * rank))
+    r.rebalance()
+    res["reb_cfgs"] = r.get_configs()
+    res["reb_weights"] = r.get_weights()
+    del r
     out[rank] = res
     del ens, a, b
     ctx.close()
@@ -107,3 +117,13 @@ def test_two_gpu_allreduce_and_dmc_block():
     swe = r0["dmc_rows"][:, 0] + r1["dmc_rows"][:, 0]
     sw = r0["dmc_rows"][:, 1] + r1["dmc_rows"][:, 1]
     assert np.array_equal(r0["dmc_block_energies"], swe / sw)
+    # rebalancing: total weight conserved, equal weights everywhere, rank 1's walkers fill 3/4 of all slots
+    for r in (r0, r1):
+        assert np.all(r["reb_weights"] == 2.0) and r["reb_cfgs"].shape[0] == W_local
+    tags = np.concatenate([r0["reb_cfgs"][:, 0, 0], r1["reb_cfgs"][:, 0, 0]]).astype(np.int64)
+    from0, from1 = (tags < W_local).sum(), (tags >= W_local).sum()
+    assert abs(from0 - W_local // 2) <= 1 and from0 + from1 == 2 * W_local
+    mult = np.bincount(tags, minlength=2 * W_local)
+    assert mult[:W_local].max() <= 1 and 1 <= mult[W_local:].min() and mult[W_local:].max() <= 2   # systematic: copies within 1 of the expectation
+    assert np.all(r1["reb_cfgs"][:, 0, 0] >= W_local)                  # the heavy rank keeps its own walkers ...
+    assert (r0["reb_cfgs"][:, 0, 0] >= W_local).sum() == W_local - from0  # ... and its surplus fills rank 0's free slots

@@ -93,3 +93,29 @@ def test_two_rank_gloo_matches_single_process():
     assert abs(r0["e"] - e1) < 1e-12 * abs(e1) and abs(r0["err"] - err1) < 1e-9 * err1
     assert r0["accp"] == accp1
     assert np.allclose(r0["g"], g1, rtol=1e-10, atol=1e-13) and np.allclose(r0["dp"], dp1, rtol=1e-9, atol=1e-13)
+
+
+def test_rebalance_plan_shares_and_moves():
+    """Host arithmetic of mole_rebalance (north_star (5)): shares proportional to the ranks' total weights, summing to
+    the global walker count for every shared draw; surplus matched to free slots; unbiased over the draw."""
+    import mole_b200 as m
+    counts = np.array([1000, 1000, 1000, 1000])
+    totals = np.array([1000.0, 3000.0, 500.0, 1500.0])
+    acc = np.zeros(4)
+    for u in np.linspace(0.0, 0.999, 200):
+        shares, moves = m.rebalance_plan(totals, counts, float(u))
+        assert shares.sum() == counts.sum() and np.all(shares >= 0)
+        assert np.all(np.abs(shares - 4000 * totals / totals.sum()) < 1.0 + 1e-9)
+        surplus = shares - counts
+        assert np.array_equal(moves.sum(axis=1), np.maximum(surplus, 0))       # everything a rank has too much leaves it
+        assert np.array_equal(moves.sum(axis=0), np.maximum(-surplus, 0))      # every free slot is filled
+        assert np.all(np.diag(moves) == 0)
+        acc += shares
+    assert np.allclose(acc / 200, 4000 * totals / totals.sum(), atol=0.51)
+    # equal islands: nothing moves; one dead rank: it is refilled entirely by the others
+    shares, moves = m.rebalance_plan([2.0, 2.0], [7, 7], 0.3)
+    assert list(shares) == [7, 7] and moves.sum() == 0
+    shares, moves = m.rebalance_plan([0.0, 5.0, 5.0], [10, 10, 10], 0.5)
+    assert shares[0] == 0 and shares.sum() == 30 and moves[:, 0].sum() == 10
+    with pytest.raises(m.MoleError):
+        m.rebalance_plan([0.0, 0.0], [4, 4], 0.1)

@@ -168,3 +168,23 @@ def test_two_contexts_driven_from_two_threads(mole, orc):
     for i in range(2):
         for a, b in zip(par[i], serial["a"]):
             assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_rebalance_on_one_rank_is_the_identity_after_equalising_weights(mole):
+    """mole_rebalance with a single rank: unequal weights are first resampled (SRBrancher, stratified), then every
+    walker keeps its slot and carries the mean weight; total weight conserved."""
+    c = cases()["sto_h"]
+    wf, op = c["make"](mole)
+    W = 512
+    ens = mole.Ensemble(W, 1, SEED0)
+    ens.init_normal(1.0)
+    x0 = ens.get_configs().copy()
+    ens.rebalance()                                              # uniform weights: nothing changes
+    assert np.array_equal(ens.get_configs(), x0) and np.all(ens.get_weights() == 1.0)
+    w = np.linspace(0.5, 1.5, W)
+    ens.set_weights(w)
+    ens.rebalance()
+    got = ens.get_weights()
+    assert np.all(got == got[0]) and abs(got[0] - w.mean()) < 1e-12
+    src = ens.branch_sources()
+    assert np.array_equal(ens.get_configs()[:, 0, :], x0[src, 0, :])
