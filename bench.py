@@ -45,7 +45,12 @@ FLOPS = json.load(open(os.path.join(ROOT, "bench_data", "flops.json")))
 # DMC (BASELINE.json configs[3], examples/dmc.rs:189-210): H atom, Gaussian guide at its VMC optimum 1/a^2 = 8/(9 pi)
 DMC_A = float(np.sqrt(9.0 * np.pi / 8.0))   # psi = exp(-(r/a)^2), examples/dmc.rs:44-57: optimum 1/a^2 = 8/(9 pi)
 DMC_TAU = 0.025
-DMC_EREF = {"gaussian": -0.4244, "sto": -0.495}   # VMC energies of the guides: -4/(3 pi); alpha^2/2 - alpha at alpha = 0.9
+# 1s STO guide with alpha > 1: E_L = -alpha^2/2 + (alpha - 1)/r is bounded BELOW, so walkers next to the nucleus die instead of
+# multiplying.  With alpha < 1 (or the example's cusp-less Gaussian) E_L -> -inf at the nucleus and the reference's cut-off-free
+# DMC collapses a large population onto it sooner or later (observed at 2 x 2^15 walkers after ~4400 steps with alpha = 0.9:
+# island energy -55, weights 1e192, then overflow; upstream behaviour)
+DMC_STO_ALPHA = 1.1
+DMC_EREF = {"gaussian": -0.4244, "sto": -0.495}   # VMC energies of the guides: -4/(3 pi); alpha^2/2 - alpha at alpha = 1.1
 DMC_SEED = bytes([1] * 32)
 
 
@@ -109,7 +114,7 @@ def dmc_config(args, world, walkers=None, steps=None, bounded=False):
     steps = args.dmc_steps if steps is None else steps
     cfg = {"workload": "h_atom_dmc_sr_brancher (BASELINE.json configs[3], examples/dmc.rs:189-210): H atom, %s guide, "
                        "MetropolisDiffuse tau=%.3g, SRBrancher, E_ref updated between blocks" % (
-                           "Gaussian 1/a^2=8/(9 pi)" if args.dmc_guide == "gaussian" else "1s STO alpha=0.9", DMC_TAU),
+                           "Gaussian 1/a^2=8/(9 pi)" if args.dmc_guide == "gaussian" else "1s STO alpha=%.2f" % DMC_STO_ALPHA, DMC_TAU),
            "walkers_per_gpu": walkers, "global_walkers": walkers * world, "time_steps_per_step": steps,
            "parallelism": "walkers sharded (population islands, one all-gather per block), dp%d" % world,
            "cache": "L2 flushed between timed steps (256 MiB write)"}
@@ -125,10 +130,10 @@ def dmc_config(args, world, walkers=None, steps=None, bounded=False):
 def dmc_pair(m_or_o, guide, ctx=None, oracle=False):
     if oracle:
         O = m_or_o
-        wf = O.wf_desc(O.WF_GAUSSIAN, [DMC_A]) if guide == "gaussian" else O.wf_desc(O.WF_STO_1S, [0.9])
+        wf = O.wf_desc(O.WF_GAUSSIAN, [DMC_A]) if guide == "gaussian" else O.wf_desc(O.WF_STO_1S, [DMC_STO_ALPHA])
         return wf, O.ham_desc(O.HAM_ELECTRONIC, [[0, 0, 0]], [1])
     m = m_or_o
-    wf = m.GaussianWaveFunction(DMC_A, ctx=ctx) if guide == "gaussian" else m.STO(0.9, ctx=ctx)
+    wf = m.GaussianWaveFunction(DMC_A, ctx=ctx) if guide == "gaussian" else m.STO(DMC_STO_ALPHA, ctx=ctx)
     return wf, m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1], ctx=ctx)
 
 
@@ -472,6 +477,9 @@ def run_dmc(args):
         eb = float(se.mean())
         if not np.isfinite(eb):
             fail("DMC block %d: non-finite ensemble energy (health %s)" % (it, ens.health()))
+        if args.verbose:
+            print("  rank %d block %d (%s): E = %.5f  [%.4f, %.4f]  E_ref %.5f" % (rank, it, "e2e" if state["e2e"] else "resident", eb,
+                                                                             se.min(), se.max(), state["eref"]), file=sys.stderr, flush=True)
         state["eref"] = 0.5 * (state["eref"] + eb)                          # dmc.rs:163-177
         hist.append(eb)
 
