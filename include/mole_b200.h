@@ -430,6 +430,9 @@ int32_t mole_ensemble_load(mole_ens_t ens, const char* path); /* W and N_e must 
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 /* sustained DFMA throughput of the device (TFLOP/s) measured with a register-resident FMA chain */
 int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops);
+/* fp64 tensor-core (mma.m8n8k4, DMMA) throughput with `chains` (1,2,4,8,16) independent accumulators per warp and
+ * `warps_per_sm` (1..32) resident warps: the compute ceiling of the Gram contraction */
+int32_t mole_bench_dmma_peak(mole_ctx_t ctx, int32_t chains, int32_t warps_per_sm, double* tflops);
 /* evaluates the kernels' branch-free fp64 elementary functions on the device (accuracy tests):
  * which = 0 exp, 1 reciprocal, 2 reciprocal square root, 3 square root, 4 natural log,
  * 5 / 6 sine / cosine of a fraction of a full turn */

@@ -57,6 +57,11 @@ class Context:
         check(lib().mole_bench_fp64_peak(self.handle, C.byref(t)), self.handle)
         return t.value
 
+    def dmma_peak_tflops(self, chains=8, warps_per_sm=8):
+        t = C.c_double()
+        check(lib().mole_bench_dmma_peak(self.handle, C.c_int32(chains), C.c_int32(warps_per_sm), C.byref(t)), self.handle)
+        return t.value
+
     def bench_gram(self, n_walkers, n_samples, cols, impl=0, reps=5):
         """(ms per launch, GB/s of algorithmic bytes, checksum) of the Gram contraction alone on synthetic rows."""
         ms, cs = C.c_double(), C.c_double()

@@ -579,7 +579,7 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
     if (sp.osamp) {                                          // S = O^T O (and every other moment): the Gram matrix of the rows
       KERNEL_CHECK(ctx);
       MOLE_RANGE("mole_gram");
-      if (e->gram_impl == 0) gram_dmma_kernel<<<e->gram_rows, GRAM_THREADS, 0, STREAM(ctx)>>>(e->osamp, W, nsamp, cols, e->gram_partials);
+      if (e->gram_impl == 0) gram_dmma_launch(e->gram_rows, STREAM(ctx), e->osamp, W, nsamp, cols, e->gram_partials);
       else gram_fma_kernel<<<e->gram_rows, GRAM_THREADS, 0, STREAM(ctx)>>>(e->osamp, W, nsamp, cols, e->gram_partials);
       KERNEL_CHECK(ctx);
       gram_fold_kernel<<<cdiv(GRAM_PAD * GRAM_PAD, 256), 256, 0, STREAM(ctx)>>>(e->gram_partials, e->gram_rows, e->gram);
@@ -1025,6 +1025,40 @@ int32_t mole_bench_fp64_peak(mole_ctx_t ctx, double* tflops) {
   return MOLE_OK;
 }
 
+// DMMA (m8n8k4 fp64) issue rate: `chains` independent accumulators per warp, `warps_per_sm` resident warps
+int32_t mole_bench_dmma_peak(mole_ctx_t ctx, int32_t chains, int32_t warps_per_sm, double* tflops) {
+  if (!ctx || !tflops || warps_per_sm < 1 || warps_per_sm > 32) return MOLE_ERR_INVALID_ARG;
+  if (chains != 1 && chains != 2 && chains != 4 && chains != 8 && chains != 16) return MOLE_ERR_INVALID_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count, threads = 32 * warps_per_sm, iters = 1 << 14;
+  double* out = nullptr;
+  CU(ctx, cudaMalloc(&out, blocks * sizeof(double)));
+  cudaEvent_t a, b;
+  CU(ctx, cudaEventCreate(&a));
+  CU(ctx, cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(ctx, cudaEventRecord(a, STREAM(ctx)));
+    switch (chains) {
+      case 1: dmma_peak_kernel<1><<<blocks, threads, 0, STREAM(ctx)>>>(out, iters, 1.0 + rep); break;
+      case 2: dmma_peak_kernel<2><<<blocks, threads, 0, STREAM(ctx)>>>(out, iters, 1.0 + rep); break;
+      case 4: dmma_peak_kernel<4><<<blocks, threads, 0, STREAM(ctx)>>>(out, iters, 1.0 + rep); break;
+      case 8: dmma_peak_kernel<8><<<blocks, threads, 0, STREAM(ctx)>>>(out, iters, 1.0 + rep); break;
+      default: dmma_peak_kernel<16><<<blocks, threads, 0, STREAM(ctx)>>>(out, iters, 1.0 + rep); break;
+    }
+    KERNEL_CHECK(ctx);
+    CU(ctx, cudaEventRecord(b, STREAM(ctx)));
+    CU(ctx, cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, a, b));
+    const double fl = (double)blocks * warps_per_sm * (double)iters * chains * 512.0;   // 8 x 8 x 4 x 2 flops per MMA
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  *tflops = best;
+  return MOLE_OK;
+}
+
 // ------------------------------------------------------------------ Gram contraction timed alone (roofline of the large-P path)
 // rows of (1, E, O_k)-like synthetic values, W walkers x n_samples samples x cols columns; returns the mean time of
 // `reps` launches (CUDA events on the context's stream) of the chosen implementation (0 DMMA, 1 FP64 vector pipe)
@@ -1047,7 +1081,7 @@ int32_t mole_bench_gram(mole_ctx_t ctx, int64_t W, int64_t n_samples, int32_t co
   float total = 0.f;
   for (int r = 0; r < reps + 1; ++r) {
     CU(ctx, cudaEventRecord(a, STREAM(ctx)));
-    if (impl == 0) gram_dmma_kernel<<<rows, GRAM_THREADS, 0, STREAM(ctx)>>>(data, W, n_samples, cols, partials);
+    if (impl == 0) gram_dmma_launch(rows, STREAM(ctx), data, W, n_samples, cols, partials);
     else gram_fma_kernel<<<rows, GRAM_THREADS, 0, STREAM(ctx)>>>(data, W, n_samples, cols, partials);
     KERNEL_CHECK(ctx);
     gram_fold_kernel<<<cdiv(GRAM_PAD * GRAM_PAD, 256), 256, 0, STREAM(ctx)>>>(partials, rows, gram);

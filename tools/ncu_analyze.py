@@ -4,11 +4,11 @@ import csv, sys, re, subprocess, collections, io, os
 rep, ksub = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 raw = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
-rows=list(csv.reader(io.StringIO(raw))); hdr=rows[0]; d=dict(zip(hdr,rows[2]))
+rows=list(csv.reader(io.StringIO(raw))); hdr=rows[0]; d=dict(zip(hdr,rows[2])); units=dict(zip(hdr,rows[1]))
 keys=['gpu__time_duration.sum','smsp__inst_executed.sum','sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.pct_of_peak_sustained_active','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','launch__grid_size','launch__occupancy_limit_registers','launch__occupancy_limit_shared_mem','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','smsp__thread_inst_executed_per_inst_executed.ratio','dram__bytes_read.sum','dram__bytes_write.sum','l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum','l1tex__t_requests_pipe_lsu_mem_local_op_st.sum','smsp__inst_executed_op_shared_ld.sum','smsp__inst_executed_op_shared_st.sum']
 print(d['Kernel Name'])
 for k in keys:
-    if k in d: print('  %-75s %s' % (k, d[k]))
+    if k in d: print('  %-75s %s %s' % (k, d[k], units.get(k,'')))
 src = subprocess.run(['ncu','-i',rep,'--page','source','--csv'],capture_output=True,text=True).stdout
 rows=list(csv.reader(io.StringIO(src))); hdr=rows[1]; data=rows[2:]
 iS=hdr.index('Source'); iE=hdr.index('Instructions Executed'); iSamp=hdr.index('# Samples')

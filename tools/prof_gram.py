@@ -18,6 +18,8 @@ except OSError:
     pass
 hbm = peaks.get("hbm_gbs", 6650.0)
 print("HBM peak used: %.0f GB/s (%s)" % (hbm, "MEASURED_PEAKS.json" if peaks else "fallback"))
+for ch in (1, 2, 4, 8):
+    print("dmma m8n8k4 probe, %2d chains/warp: " % ch + "  ".join("%dw %.1f" % (w, ctx.dmma_peak_tflops(ch, w)) for w in (4, 8, 16, 32)) + "  TFLOP/s", flush=True)
 for W, ns, cols in ((1 << 16, 190, 38), (1 << 17, 40, 38), (1 << 16, 190, 14), (1 << 14, 190, 46)):
     out = []
     for impl in (0, 1):
