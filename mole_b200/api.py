@@ -708,6 +708,10 @@ class Ensemble:
     def gram_allreduce(self):
         self._c(lib().mole_gram_allreduce(self.handle))
 
+    def dmc_block_select(self, impl):
+        """0: one persistent cooperative launch per DMC block where eligible (default); 1: per-step launches."""
+        self._c(lib().mole_dmc_block_select(self.handle, C.c_int32(impl)))
+
     def gram_select(self, impl):
         """0: DMMA (tensor cores, default); 1: FP64 vector pipe."""
         self._c(lib().mole_gram_select(self.handle, C.c_int32(impl)))

@@ -13,6 +13,7 @@
 #include "mole_sj.cuh"
 #include "mole_lsj.cuh"
 #include "mole_gram.cuh"
+#include "mole_dmc_block.cuh"
 #include "mole_stats.cuh"
 
 // errors raised without a context (NULL handles, mole_ctx_create); per thread, because different contexts may be
@@ -253,7 +254,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->x0);
   cudaFree(e->x); cudaFree(e->x2); cudaFree(e->w); cudaFree(e->w2); cudaFree(e->el); cudaFree(e->el2);
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
-  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath);
+  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath); cudaFree(e->bar);
   cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen); cudaFree(e->sb_draws);
   cudaFree(e->osamp); cudaFree(e->gram); cudaFree(e->gram_partials); cudaFree(e->xchg);
   mole_ctx_s* ctx = e->ctx;
@@ -679,6 +680,12 @@ int32_t mole_gram_device_ptr(mole_ens_t e, void** p, int32_t* n_doubles) {
   return MOLE_OK;
 }
 
+int32_t mole_dmc_block_select(mole_ens_t e, int32_t impl) {
+  if (!e || (impl != 0 && impl != 1)) return MOLE_ERR_INVALID_ARG;
+  e->dmc_block_impl = impl;
+  return MOLE_OK;
+}
+
 int32_t mole_gram_select(mole_ens_t e, int32_t impl) {
   if (!e || (impl != 0 && impl != 1)) return MOLE_ERR_INVALID_ARG;
   e->gram_impl = impl;
@@ -690,15 +697,13 @@ int32_t mole_gram_select(mole_ens_t e, int32_t impl) {
 
 // one time step for all walkers, enqueued on the stream; the reduction leaves
 // red[0..3] = {sum w E_old, sum w, sum w', max w'} on the device
-static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref) {
+static int32_t dmc_params_fill(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref, DmcParams& dp) {
   if (!e || !wf || !m || !op) return mole_set_error(e ? e->ctx : nullptr, MOLE_ERR_INVALID_ARG, "mole_dmc_step: NULL argument");
   mole_ctx_s* ctx = e->ctx;
   if (m->kind != MOLE_METROP_DIFFUSE) return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "DmcRunner takes a MetropolisDiffuse (dmc.rs:28)");
   if (wf->p.ne != e->ne) return mole_set_error(ctx, MOLE_ERR_SHAPE, "wavefunction / ensemble electron count mismatch");
   if (wf->p.kind == MOLE_WF_CONSTANT) return mole_set_error(ctx, MOLE_ERR_FUNC, "WaveFunctionMock::gradient is unimplemented");
-  MOLE_RANGE("mole_dmc_step");
   CU(ctx, cudaSetDevice(ctx->device));
-  DmcParams dp;
   memset(&dp, 0, sizeof(dp));
   dp.x = e->x; dp.w = e->w; dp.el = e->el; dp.red = e->red; dp.partials = e->partials; dp.ticket = e->ticket; dp.health = e->acc + ACC_BAD_DMC;
   dp.W = e->W; dp.walker_offset = e->walker_offset; dp.key = e->key; dp.step = e->step;
@@ -708,6 +713,15 @@ static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
   e->el_sig = sig;
   dp.tau_move = m->param; dp.tau_weight = time_step; dp.e_ref = e_ref; dp.el_cached = e->el_cached; dp.compat = m->compat;
   dp.wf = wf->p; dp.ham = op->p;
+  return MOLE_OK;
+}
+
+static int32_t dmc_step_launch(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref) {
+  DmcParams dp;
+  int32_t rcf = dmc_params_fill(e, wf, m, op, time_step, e_ref, dp);
+  if (rcf != MOLE_OK) return rcf;
+  mole_ctx_s* ctx = e->ctx;
+  MOLE_RANGE("mole_dmc_step");
   if (wf->p.kind == K_SLATER_JASTROW) {
     const int32_t rc = sj_dmc_launch(ctx, e, dp);
     if (rc != MOLE_OK) return rc;
@@ -756,6 +770,78 @@ static int32_t sr_branch_launch(mole_ens_t e, double norm_factor, double new_wei
   e->wstats_valid = 0;
   e->w_uniform = 1;
   e->step += 1;
+  return MOLE_OK;
+}
+
+// A whole block of SRBrancher time steps as ONE cooperative launch (mole_dmc_block.cuh).  Returns MOLE_OK with
+// *done = 0 when the combination is not eligible (cooperative kinds, population too large for a co-resident grid,
+// per-step launches selected): the caller then enqueues the per-step kernels, with identical results.
+template <int KIND>
+static int32_t dmc_block_launch_kind(mole_ctx_s* ctx, const DmcBlockParams& bp, int n_vb, int* grid_out) {
+  int occ = 0;
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmc_block_kernel<KIND>, SWEEP_THREADS, 0));
+  const int grid = std::min(n_vb, occ * ctx->sm_count);
+  *grid_out = grid;
+  if (grid < 1) return MOLE_OK;
+  void* args[] = {(void*)&bp};
+  CU(ctx, cudaLaunchCooperativeKernel((const void*)dmc_block_kernel<KIND>, dim3(grid), dim3(SWEEP_THREADS), args, 0, STREAM(ctx)));
+  return MOLE_OK;
+}
+
+static int32_t dmc_block_fused(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, double time_step, double e_ref,
+                               int n_steps, int* done) {
+  *done = 0;
+  mole_ctx_s* ctx = e->ctx;
+  const int kind = wf->p.kind;
+  const int n_vb = cdiv(e->W, SWEEP_THREADS);
+  if (e->dmc_block_impl != 0 || kind == K_SLATER_JASTROW || kind == K_LCAO_SJ) return MOLE_OK;
+  if (n_vb > e->partial_rows || e->n_scan_blocks > DMCB_MAX_TILES) return MOLE_OK;
+  int coop = 0;
+  CU(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  if (!coop) return MOLE_OK;
+  DmcBlockParams bp;
+  memset(&bp, 0, sizeof(bp));
+  int32_t rc = dmc_params_fill(e, wf, m, op, time_step, e_ref, bp.dp);
+  if (rc != MOLE_OK) return rc;
+  MOLE_RANGE("mole_dmc_block_fused");
+  cudaStream_t st = STREAM(ctx);
+  if (!e->bar) CU(ctx, cudaMalloc(&e->bar, 2 * sizeof(unsigned int)));
+  // the arrival counter counts 2 * grid per step: chunks keep it far below 2^32
+  const int max_chunk = 1 << 14;
+  for (int first = 0; first < n_steps; first += max_chunk) {
+    const int chunk = std::min(max_chunk, n_steps - first);
+    CU(ctx, cudaMemsetAsync(e->bar, 0, 2 * sizeof(unsigned int), st));
+    bp.dp.x = e->x; bp.dp.w = e->w; bp.dp.el = e->el; bp.dp.step = e->step; bp.dp.el_cached = e->el_cached;
+    bp.x2 = e->x2; bp.w2 = e->w2; bp.el2 = e->el2;
+    bp.cum = e->cum; bp.tile_sums = e->blocksums; bp.src = e->src;
+    bp.step_e = e->step_e + 2 * (size_t)first; bp.bar = e->bar;
+    bp.n_tiles = e->n_scan_blocks; bp.n_steps = chunk; bp.n = 3 * e->ne;
+    int grid = 0;
+    switch (kind) {
+#define DB(K) case K: rc = dmc_block_launch_kind<K>(ctx, bp, n_vb, &grid); break;
+      DB(K_STO_1S) DB(K_GAUSSIAN) DB(K_STO_PRODUCT) DB(K_H2_HL_STO) DB(K_H2P_PRODUCT) DB(K_LCAO_1E_2C) DB(K_LCAO_2E_1C) DB(K_LCAO_2E_2C)
+#undef DB
+      default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");
+    }
+    if (rc != MOLE_OK) return rc;
+    if (grid < 1) {
+      if (first == 0) return MOLE_OK;                          // nothing launched yet: per-step path
+      return mole_set_error(ctx, MOLE_ERR_CUDA, "dmc_block_kernel: no co-resident grid");
+    }
+    KERNEL_CHECK(ctx);
+    if (chunk & 1) { std::swap(e->x, e->x2); std::swap(e->w, e->w2); std::swap(e->el, e->el2); }
+    e->step += (uint32_t)chunk;
+    e->el_cached = 1;
+    e->wstats_valid = 0;
+    e->w_uniform = 1;
+    unsigned int flag[2] = {0u, 0u};
+    if (first + chunk < n_steps) {                             // (the last chunk's flag is read with the block's rows)
+      CU(ctx, cudaMemcpyAsync(flag, e->bar, sizeof(flag), cudaMemcpyDeviceToHost, st));
+      CU(ctx, cudaStreamSynchronize(st));
+      if (flag[1]) return mole_set_error(ctx, MOLE_ERR_CUDA, "dmc_block_kernel: grid barrier timed out");
+    }
+  }
+  *done = 1;
   return MOLE_OK;
 }
 
@@ -814,7 +900,9 @@ int32_t mole_dmc_block(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op
   // Every rank is a population island inside a block: SRBrancher normalises with the rank's own N / w_max and resets
   // to the rank's own mean weight (stratified resampling, unbiased), so NO collective sits in the step loop; the
   // per-step {sum w E, sum w} rows of all ranks are gathered ONCE per block and every rank forms the same energies.
-  for (int j = 0; j < n_steps; ++j) {
+  int fused = 0;
+  if ((rc = dmc_block_fused(e, wf, m, op, time_step, e_ref, n_steps, &fused)) != MOLE_OK) return rc;
+  for (int j = 0; j < n_steps && !fused; ++j) {
     if ((rc = dmc_step_launch(e, wf, m, op, time_step, e_ref)) != MOLE_OK) return rc;
     if ((rc = sr_branch_launch(e, 0.0, 0.0, e->red, 1, (double)e->W, e->red + 2, e->step_e + 2 * j)) != MOLE_OK) return rc;
   }
@@ -825,7 +913,10 @@ int32_t mole_dmc_block(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op
   } else {
     CU(ctx, cudaMemcpyAsync(rows.data(), e->step_e, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
+  unsigned int bar_flag[2] = {0u, 0u};
+  if (fused) CU(ctx, cudaMemcpyAsync(bar_flag, e->bar, sizeof(bar_flag), cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
+  if (bar_flag[1]) return mole_set_error(ctx, MOLE_ERR_CUDA, "dmc_block_kernel: grid barrier timed out");
   for (int j = 0; j < n_steps; ++j) {
     double swe = 0.0, sw = 0.0;                                    // rank order: identical on every rank
     for (int r = 0; r < nr; ++r) { swe += rows[((size_t)r * n_steps + j) * 2]; sw += rows[((size_t)r * n_steps + j) * 2 + 1]; }

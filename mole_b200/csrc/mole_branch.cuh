@@ -10,14 +10,16 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-// inclusive scan of one tile held as SCAN_ITEMS consecutive values per thread; returns tile total
-MOLE_D unsigned long long mole_tile_scan(unsigned long long v[SCAN_ITEMS]) {
-  __shared__ unsigned long long warp_tot[SCAN_THREADS / 32];
+// inclusive scan of one tile held as ITEMS consecutive values per thread (THREADS threads); returns tile total.
+// Integer sums: the result does not depend on the CTA shape.
+template <int THREADS, int ITEMS>
+MOLE_D unsigned long long mole_tile_scan_t(unsigned long long v[ITEMS]) {
+  __shared__ unsigned long long warp_tot[THREADS / 32];
   __shared__ unsigned long long tile_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 1; i < SCAN_ITEMS; ++i) v[i] += v[i - 1];
-  unsigned long long run = v[SCAN_ITEMS - 1];
+  for (int i = 1; i < ITEMS; ++i) v[i] += v[i - 1];
+  unsigned long long run = v[ITEMS - 1];
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned long long t = __shfl_up_sync(0xffffffffu, run, o);
@@ -26,21 +28,22 @@ MOLE_D unsigned long long mole_tile_scan(unsigned long long v[SCAN_ITEMS]) {
   if (lane == 31) warp_tot[warp] = run;
   __syncthreads();
   if (warp == 0) {
-    unsigned long long t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0ull;
+    unsigned long long t = lane < THREADS / 32 ? warp_tot[lane] : 0ull;
 #pragma unroll
-    for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+    for (int o = 1; o < THREADS / 32; o <<= 1) {
       const unsigned long long u = __shfl_up_sync(0xffffffffu, t, o);
       if (lane >= o) t += u;
     }
-    if (lane < SCAN_THREADS / 32) warp_tot[lane] = t;
-    if (lane == SCAN_THREADS / 32 - 1) tile_total = t;
+    if (lane < THREADS / 32) warp_tot[lane] = t;
+    if (lane == THREADS / 32 - 1) tile_total = t;
   }
   __syncthreads();
-  const unsigned long long excl = (run - v[SCAN_ITEMS - 1]) + (warp > 0 ? warp_tot[warp - 1] : 0ull);
+  const unsigned long long excl = (run - v[ITEMS - 1]) + (warp > 0 ? warp_tot[warp - 1] : 0ull);
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) v[i] += excl;
+  for (int i = 0; i < ITEMS; ++i) v[i] += excl;
   return tile_total;
 }
+MOLE_D unsigned long long mole_tile_scan(unsigned long long v[SCAN_ITEMS]) { return mole_tile_scan_t<SCAN_THREADS, SCAN_ITEMS>(v); }
 
 // pass 1 (SR): integer weights k_i = trunc(w_i * N/w_max) (branching.rs:24-30, `as u32` saturates),
 // tile-local inclusive scan -> cum, tile totals -> tile_sums

@@ -422,50 +422,48 @@ MOLE_D void mole_dmc_fold_partials(const double* partials, unsigned rows, double
 }
 
 // ------------------------------------------------------------------ DMC time step (dmc.rs:87-130)
-// red[0] += sum w E_old, red[1] += sum w (pre-update), red[2] = sum w (post-update), red[3] = max w (post-update)
+// one walker's time step: drift-diffusion move of every electron, weight update, contribution to the step's sums.
+// x / wgt / el are read through L2 (__ldcg): inside dmc_block_kernel other CTAs wrote them earlier in the same launch.
 template <int KIND>
-__global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams dp) {
-  mole_math_smem_init();
+MOLE_D void mole_dmc_walker_step(const DmcParams& dp, double* x, double* wgt, double* el, int64_t w, int el_cached, uint32_t step,
+                                 double sd, double& s_we, double& s_w, double& s_wn, double& m_wn) {
   using WF = WfDev<KIND>;
   constexpr int NE = WF::NE;
   const WfParams& p = dp.wf;
-  const double sd = sqrt(dp.tau_move);
-  double s_we = 0.0, s_w = 0.0, s_wn = 0.0, m_wn = 0.0;
   const int64_t W = dp.W;
-  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
-    Walker<WF> wk;
+  Walker<WF> wk;
 #pragma unroll
-    for (int c = 0; c < 3 * NE; ++c) wk.st.x[c] = dp.x[(size_t)c * W + w];
-    WF::init(p, wk.st);
-    wk.refresh(p);
-    double hp, kp;
-    // E_L before the move (dmc.rs:89-96).  It equals the post-move E_L of the previous step for the
-    // same configuration, so it is carried in `el` (and gathered by branching) instead of recomputed.
-    const double e_old = dp.el_cached ? dp.el[w] : mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);
-    const uint64_t wid = dp.walker_offset + (uint64_t)w;
+  for (int c = 0; c < 3 * NE; ++c) wk.st.x[c] = __ldcg(x + (size_t)c * W + w);
+  WF::init(p, wk.st);
+  wk.refresh(p);
+  double hp, kp;
+  // E_L before the move (dmc.rs:89-96).  It equals the post-move E_L of the previous step for the
+  // same configuration, so it is carried in `el` (and gathered by branching) instead of recomputed.
+  const double e_old = el_cached ? __ldcg(el + w) : mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);
+  const uint64_t wid = dp.walker_offset + (uint64_t)w;
 #pragma unroll
-    for (int e = 0; e < NE; ++e) mole_move_state<WF, MOLE_METROP_DIFFUSE>(p, wk, e, dp.tau_move, sd, dp.key, wid, dp.step, dp.compat);
-    const double e_new = mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);   // :115-124
-    // a walker whose local energy is not finite (upstream: NaN ensemble energy from here on) is counted
-    // (acc[ACC_BAD_DMC]) and dies: weight 0 before and after the step, never picked by the brancher
-    const double w_in = dp.w[w];
-    const double w_up = w_in * exp(-dp.tau_weight * ((e_old + e_new) / 2.0 - dp.e_ref));           // :126-128
-    const bool bad = !isfinite(e_old) || !isfinite(e_new) || !isfinite(w_up);
-    if (bad) atomicAdd(dp.health, 1.0);
-    const double wt = bad ? 0.0 : w_in;
-    s_we = fma(wt, bad ? 0.0 : e_old, s_we);                    // dmc.rs:112-113
-    s_w += wt;
-    const double wn = bad ? 0.0 : w_up;
-    s_wn += wn;
-    m_wn = fmax(m_wn, wn);
-    dp.w[w] = wn;
-    dp.el[w] = bad ? 0.0 : e_new;
+  for (int e = 0; e < NE; ++e) mole_move_state<WF, MOLE_METROP_DIFFUSE>(p, wk, e, dp.tau_move, sd, dp.key, wid, step, dp.compat);
+  const double e_new = mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);   // :115-124
+  // a walker whose local energy is not finite (upstream: NaN ensemble energy from here on) is counted
+  // (acc[ACC_BAD_DMC]) and dies: weight 0 before and after the step, never picked by the brancher
+  const double w_in = __ldcg(wgt + w);
+  const double w_up = w_in * exp(-dp.tau_weight * ((e_old + e_new) / 2.0 - dp.e_ref));           // :126-128
+  const bool bad = !isfinite(e_old) || !isfinite(e_new) || !isfinite(w_up);
+  if (bad) atomicAdd(dp.health, 1.0);
+  const double wt = bad ? 0.0 : w_in;
+  s_we = fma(wt, bad ? 0.0 : e_old, s_we);                    // dmc.rs:112-113
+  s_w += wt;
+  const double wn = bad ? 0.0 : w_up;
+  s_wn += wn;
+  m_wn = fmax(m_wn, wn);
+  wgt[w] = wn;
+  el[w] = bad ? 0.0 : e_new;
 #pragma unroll
-    for (int c = 0; c < 3 * NE; ++c) dp.x[(size_t)c * W + w] = wk.st.x[c];
-  }
-  // block reduction (3 sums + 1 max)
-  __shared__ double sm[32][4];
-  __shared__ bool is_last;
+  for (int c = 0; c < 3 * NE; ++c) x[(size_t)c * W + w] = wk.st.x[c];
+}
+
+// CTA reduction of the step's sums (3 sums + 1 max) into one row of `partials`; fixed order for a given CTA shape
+MOLE_D void mole_dmc_cta_reduce(double s_we, double s_w, double s_wn, double m_wn, double (*sm)[4], double* row) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -479,8 +477,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams
   if (threadIdx.x < 4) {
     double s = 0.0;
     for (int q = 0; q < nwarp; ++q) s = (threadIdx.x == 3) ? fmax(s, sm[q][3]) : s + sm[q][threadIdx.x];
-    dp.partials[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+    row[threadIdx.x] = s;
   }
+}
+
+// red[0] += sum w E_old, red[1] += sum w (pre-update), red[2] = sum w (post-update), red[3] = max w (post-update)
+template <int KIND>
+__global__ void __launch_bounds__(SWEEP_THREADS) dmc_step_kernel(const DmcParams dp) {
+  mole_math_smem_init();
+  const double sd = sqrt(dp.tau_move);
+  double s_we = 0.0, s_w = 0.0, s_wn = 0.0, m_wn = 0.0;
+  const int64_t W = dp.W;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x)
+    mole_dmc_walker_step<KIND>(dp, dp.x, dp.w, dp.el, w, dp.el_cached, dp.step, sd, s_we, s_w, s_wn, m_wn);
+  __shared__ double sm[32][4];
+  __shared__ bool is_last;
+  mole_dmc_cta_reduce(s_we, s_w, s_wn, m_wn, sm, dp.partials + (size_t)blockIdx.x * 4);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicInc(dp.ticket, gridDim.x - 1) == gridDim.x - 1);

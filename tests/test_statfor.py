@@ -235,3 +235,53 @@ def test_dmc_block_equals_step_by_step(mole, W):
     # SimpleBranching goes through the step-by-step path inside mole_dmc_block
     es = b.dmc_block(wf, met, op, mole.ffi.BRANCH_SIMPLE, 0.025, -0.47, 3)
     assert np.isfinite(es).all() and b.step == 26
+
+
+def _dmc_case(mole, name):
+    if name == "sto":
+        return mole.STO(0.9), mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1]), 1, -0.47
+    if name == "gaussian":
+        return mole.GaussianWaveFunction(1.3), mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1]), 1, -0.42
+    if name == "h2":
+        return (mole.HydrogenMoleculeWaveFunction(1.4, [0.5]),
+                mole.ElectronicHamiltonian.from_ions([[-0.7, 0, 0], [0.7, 0, 0]], [1, 1]), 2, -1.1)
+    bs = mole.Hydrogen1sBasis([[-0.7, 0, 0], [0.7, 0, 0]], [0.85])
+    wf = mole.SingleDeterminant([mole.Orbital([[1.0], [1.0]], bs), mole.Orbital([[1.0], [-1.0]], bs)])
+    return wf, mole.ElectronicHamiltonian.from_ions([[-0.7, 0, 0], [0.7, 0, 0]], [1, 1]), 2, -0.8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,W,n_steps", [("sto", 1, 4), ("sto", 129, 7), ("sto", 32768, 40), ("sto", 100003, 9), ("sto", 300000, 6),
+                                            ("gaussian", 4097, 10), ("h2", 3000, 11), ("lcao_triplet", 2500, 8)])
+def test_dmc_block_persistent_launch_is_bit_identical_to_per_step_launches(mole, name, W, n_steps):
+    """the whole-block cooperative launch (mole_dmc_block.cuh: three phases, two grid barriers per step, virtual blocks of
+    128 walkers) against the per-step launches selected with mole_dmc_block_select(1): configurations, weights, cached
+    local energies (through the next block), branching sources, step energies and launch counts.  100 003 walkers need
+    more virtual blocks than one co-resident grid holds; 300 000 is the largest population class served by the
+    persistent launch (2368 partial rows)."""
+    seed = bytes(range(7, 39))
+    wf, op, ne, eref = _dmc_case(mole, name)
+    met = mole.MetropolisDiffuse.from_rng(0.02, seed)
+    ens = []
+    for impl in (0, 1):
+        e = mole.Ensemble(W, ne, seed)
+        e.init_normal(0.8)
+        e.dmc_block_select(impl)
+        ens.append(e)
+    a, b = ens
+    ctx = a.ctx
+    n0 = ctx.launch_count()
+    ea = a.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.02, eref, n_steps)
+    n1 = ctx.launch_count()
+    eb = b.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.02, eref, n_steps)
+    n2 = ctx.launch_count()
+    assert n1 - n0 == 1 and n2 - n1 == 3 * n_steps
+    assert np.array_equal(ea, eb) and np.isfinite(ea).all()
+    assert a.step == b.step == n_steps
+    assert np.array_equal(a.get_configs(), b.get_configs()) and np.array_equal(a.get_weights(), b.get_weights())
+    assert np.array_equal(a.branch_sources(), b.branch_sources())
+    # a second block continues from the carried state (cached E_L, swapped buffers after an odd step count)
+    ea2 = a.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.02, eref, 3)
+    eb2 = b.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.02, eref, 3)
+    assert np.array_equal(ea2, eb2) and np.array_equal(a.get_configs(), b.get_configs())
+    assert a.health() == b.health()
