@@ -254,7 +254,7 @@ int32_t mole_ensemble_destroy(mole_ens_t e) {
   cudaFree(e->x0);
   cudaFree(e->x); cudaFree(e->x2); cudaFree(e->w); cudaFree(e->w2); cudaFree(e->el); cudaFree(e->el2);
   cudaFree(e->blk); cudaFree(e->acc); cudaFree(e->partials); cudaFree(e->ticket); cudaFree(e->red);
-  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath); cudaFree(e->bar);
+  cudaFree(e->cum); cudaFree(e->blocksums); cudaFree(e->src); cudaFree(e->series); cudaFree(e->step_e); cudaFree(e->gath); cudaFree(e->bar); cudaFree(e->vb_sums); cudaFree(e->vb_coarse);
   cudaFree(e->sb_list); cudaFree(e->sb_mask); cudaFree(e->sb_fen); cudaFree(e->sb_draws);
   cudaFree(e->osamp); cudaFree(e->gram); cudaFree(e->gram_partials); cudaFree(e->xchg);
   mole_ctx_s* ctx = e->ctx;
@@ -777,14 +777,16 @@ static int32_t sr_branch_launch(mole_ens_t e, double norm_factor, double new_wei
 // *done = 0 when the combination is not eligible (cooperative kinds, population too large for a co-resident grid,
 // per-step launches selected): the caller then enqueues the per-step kernels, with identical results.
 template <int KIND>
-static int32_t dmc_block_launch_kind(mole_ctx_s* ctx, const DmcBlockParams& bp, int n_vb, int* grid_out) {
+static int32_t dmc_block_launch_kind(mole_ctx_s* ctx, const DmcBlockParams& bp, int n_vb, size_t smem, int* grid_out) {
+  if (smem > 48 * 1024)
+    CU(ctx, cudaFuncSetAttribute(dmc_block_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmc_block_kernel<KIND>, SWEEP_THREADS, 0));
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmc_block_kernel<KIND>, SWEEP_THREADS, smem));
   const int grid = std::min(n_vb, occ * ctx->sm_count);
   *grid_out = grid;
   if (grid < 1) return MOLE_OK;
   void* args[] = {(void*)&bp};
-  CU(ctx, cudaLaunchCooperativeKernel((const void*)dmc_block_kernel<KIND>, dim3(grid), dim3(SWEEP_THREADS), args, 0, STREAM(ctx)));
+  CU(ctx, cudaLaunchCooperativeKernel((const void*)dmc_block_kernel<KIND>, dim3(grid), dim3(SWEEP_THREADS), args, smem, STREAM(ctx)));
   return MOLE_OK;
 }
 
@@ -795,7 +797,7 @@ static int32_t dmc_block_fused(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
   const int kind = wf->p.kind;
   const int n_vb = cdiv(e->W, SWEEP_THREADS);
   if (e->dmc_block_impl != 0 || kind == K_SLATER_JASTROW || kind == K_LCAO_SJ) return MOLE_OK;
-  if (n_vb > e->partial_rows || e->n_scan_blocks > DMCB_MAX_TILES) return MOLE_OK;
+  if (n_vb > e->partial_rows) return MOLE_OK;
   int coop = 0;
   CU(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   if (!coop) return MOLE_OK;
@@ -805,7 +807,16 @@ static int32_t dmc_block_fused(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
   if (rc != MOLE_OK) return rc;
   MOLE_RANGE("mole_dmc_block_fused");
   cudaStream_t st = STREAM(ctx);
-  if (!e->bar) CU(ctx, cudaMalloc(&e->bar, 2 * sizeof(unsigned int)));
+  if (!e->bar) {
+    CU(ctx, cudaMalloc(&e->bar, 2 * sizeof(unsigned int)));
+    CU(ctx, cudaMalloc(&e->vb_sums, (size_t)(n_vb + 1) * sizeof(unsigned long long)));
+    CU(ctx, cudaMalloc(&e->vb_coarse, (size_t)n_vb * DMCB_SUBS * sizeof(unsigned long long)));
+  }
+  // shared memory: exclusive offsets of the virtual blocks, plus the coarse prefix sums when they fit
+  size_t smem = (size_t)(n_vb + 1) * sizeof(unsigned long long);
+  const size_t with_coarse = smem + (size_t)n_vb * DMCB_SUBS * sizeof(unsigned long long);
+  const int stage_coarse = with_coarse <= (size_t)DMCB_STAGE_BYTES;
+  if (stage_coarse) smem = with_coarse;
   // the arrival counter counts 2 * grid per step: chunks keep it far below 2^32
   const int max_chunk = 1 << 14;
   for (int first = 0; first < n_steps; first += max_chunk) {
@@ -813,12 +824,12 @@ static int32_t dmc_block_fused(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole
     CU(ctx, cudaMemsetAsync(e->bar, 0, 2 * sizeof(unsigned int), st));
     bp.dp.x = e->x; bp.dp.w = e->w; bp.dp.el = e->el; bp.dp.step = e->step; bp.dp.el_cached = e->el_cached;
     bp.x2 = e->x2; bp.w2 = e->w2; bp.el2 = e->el2;
-    bp.cum = e->cum; bp.tile_sums = e->blocksums; bp.src = e->src;
+    bp.cum = e->cum; bp.tile_sums = e->vb_sums; bp.coarse = e->vb_coarse; bp.src = e->src;
     bp.step_e = e->step_e + 2 * (size_t)first; bp.bar = e->bar;
-    bp.n_tiles = e->n_scan_blocks; bp.n_steps = chunk; bp.n = 3 * e->ne;
+    bp.n_steps = chunk; bp.n = 3 * e->ne; bp.stage_coarse = stage_coarse;
     int grid = 0;
     switch (kind) {
-#define DB(K) case K: rc = dmc_block_launch_kind<K>(ctx, bp, n_vb, &grid); break;
+#define DB(K) case K: rc = dmc_block_launch_kind<K>(ctx, bp, n_vb, smem, &grid); break;
       DB(K_STO_1S) DB(K_GAUSSIAN) DB(K_STO_PRODUCT) DB(K_H2_HL_STO) DB(K_H2P_PRODUCT) DB(K_LCAO_1E_2C) DB(K_LCAO_2E_1C) DB(K_LCAO_2E_2C)
 #undef DB
       default: return mole_set_error(ctx, MOLE_ERR_INVALID_ARG, "unknown wavefunction kind");

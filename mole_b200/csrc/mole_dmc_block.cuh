@@ -7,30 +7,40 @@
 // step; the state stays in the same global (L2-resident) arrays, so every phase is the code of the per-step kernels:
 //   1  mole_dmc_walker_step per walker, CTA reduction -> one row of `partials` per 128 walkers
 //      -- barrier --
-//   2  the CTAs that own a scan tile fold the partial rows (mole_dmc_fold_partials, the per-step kernels' order),
-//      form N / w_max, the integer weights and the tile-local prefix sums
+//   2  every CTA folds the partial rows (mole_dmc_fold_partials, the per-step kernels' order), forms N / w_max, the
+//      integer weights of its walkers and their prefix sums inside the virtual block (tile = 128 walkers), plus a
+//      coarse copy of the prefix at the end of every 16 walkers
 //      -- barrier --
-//   3  every CTA scans the tile totals in shared memory, then draws, searches (mole_pick_tiled_ld) and gathers
-//      its walkers into the other buffer set; no barrier is needed before the next step's phase 1, which touches
+//   3  every CTA stages the exclusive tile offsets and the coarse prefix sums in shared memory, draws, searches
+//      (tile and 16-walker group in shared memory, then ONE 128-byte line of prefix sums from L2) and gathers its
+//      walkers into the other buffer set; no barrier is needed before the next step's phase 1, which touches
 //      only the CTA's own walkers of that set.
-// A CTA walks "virtual blocks" of 128 walkers (vb = blockIdx.x, + gridDim.x, ..), so the partial rows, their fold
-// and therefore every result are bit-identical to mole_dmc_step + mole_branch whatever the co-resident grid size.
-// Arrays another CTA wrote earlier in the launch are read through L2 (__ldcg): L1 is not coherent across SMs.
+// Measured at 2^15 walkers (B200, -DMOLE_DMCB_PROF prints CTA 0's phase times; ns per step):
+//                                           phase 1  barrier  phase 2  barrier  phase 3   step
+//   per-step kernels (3 launches)                                                         25 950
+//   first fused version (1024-walker scan tiles, 4-ary search: 6-7 dependent L2 round trips per pick)
+//                                             2 500    1 650    3 950    2 030    8 100   18 400
+//   this version                              2 410    1 790    2 130    2 090    5 240   14 000
+// What is left is ~7 dependent L2 round trips per step (own walker, partial rows, staged sums, prefix line, gather and
+// one per barrier) at ~1.2 us each under this access pattern, plus ~3 us of arithmetic.
 #pragma once
 #include "mole_kernels.cuh"
 #include "mole_branch.cuh"
 
-constexpr int DMCB_ITEMS = SCAN_TILE / SWEEP_THREADS;          // 8 weights per thread and scan tile
-constexpr int DMCB_MAX_TILES = 320;                            // >= partial_rows * SWEEP_THREADS / SCAN_TILE (296 on 148 SMs)
+constexpr int DMCB_SUB = 16;                                   // walkers per coarse prefix entry: one 128-byte line of `cum`
+constexpr int DMCB_SUBS = SWEEP_THREADS / DMCB_SUB;            // 8 coarse entries per virtual block
+constexpr int DMCB_STAGE_BYTES = 64 * 1024;                    // coarse prefix sums are staged in shared memory up to this size
 
 struct DmcBlockParams {
   DmcParams dp;                       // x / w / el: the buffer set that holds the walkers at entry
   double* x2; double* w2; double* el2;
-  unsigned long long* cum; unsigned long long* tile_sums;
+  unsigned long long* cum;            // [W] inclusive prefix sums of the integer weights inside the virtual block
+  unsigned long long* tile_sums;      // [n_vb] totals of the virtual blocks
+  unsigned long long* coarse;         // [n_vb * 8] prefix (inside the virtual block) at the end of every 16 walkers
   int32_t* src;
   double* step_e;                     // [n_steps][2] {sum w E, sum w}
   unsigned int* bar;                  // [0] arrival counter (zero at launch), [1] barrier time-out flag
-  int n_tiles, n_steps, n;
+  int n_steps, n, stage_coarse;
 };
 
 // Monotonic-counter grid barrier.  All CTAs are co-resident (cooperative launch), so the spin terminates; the bound
@@ -49,22 +59,43 @@ MOLE_D void mole_grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
 }
 
-struct MoleCgLoad {
-  MOLE_D unsigned long long operator()(const unsigned long long* p) const { return __ldcg(p); }
-};
+// inclusive scan of one value per thread over the CTA (SWEEP_THREADS threads); *total = sum over the CTA
+MOLE_D unsigned long long mole_cta_scan_u64(unsigned long long v, unsigned long long* s_wt, unsigned long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long run = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, run, o);
+    if (lane >= o) run += t;
+  }
+  __syncthreads();                                              // s_wt may still be read from the previous call
+  if (lane == 31) s_wt[warp] = run;
+  __syncthreads();
+  unsigned long long off = 0ull, tot = 0ull;
+#pragma unroll
+  for (int q = 0; q < SWEEP_THREADS / 32; ++q) {
+    const unsigned long long t = s_wt[q];
+    if (q < warp) off += t;
+    tot += t;
+  }
+  *total = tot;
+  return run + off;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(SWEEP_THREADS) dmc_block_kernel(const DmcBlockParams bp) {
   mole_math_smem_init();
+  extern __shared__ unsigned long long s_dyn[];
   __shared__ double sm[32][4];
   __shared__ double s_red[4];
-  __shared__ unsigned long long s_tiles[DMCB_MAX_TILES + 1];
-  __shared__ unsigned long long s_carry;
+  __shared__ unsigned long long s_wt[SWEEP_THREADS / 32];
   const DmcParams& dp = bp.dp;
   double *x = dp.x, *w = dp.w, *el = dp.el, *x2 = bp.x2, *w2 = bp.w2, *el2 = bp.el2;
   const int64_t W = dp.W;
   const int n_vb = (int)((W + SWEEP_THREADS - 1) / SWEEP_THREADS);
-  const int n_tiles = bp.n_tiles;
+  const int n_coarse = n_vb * DMCB_SUBS;
+  unsigned long long* const s_tiles = s_dyn;                    // [n_vb + 1] exclusive offsets of the virtual blocks, grand total
+  unsigned long long* const s_coarse = s_dyn + n_vb + 1;        // [n_coarse] when staged
   const double sd = sqrt(dp.tau_move);
   unsigned int target = 0;
 #ifdef MOLE_DMCB_PROF
@@ -88,72 +119,124 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_block_kernel(const DmcBlock
     target += gridDim.x;
     mole_grid_barrier(bp.bar, target);
     DMCB_T(1);
-    // ---- 2: fold of the partial rows, integer weights k_i = trunc(w_i N / w_max) (branching.rs:24-30), tile scans
-    if ((int)blockIdx.x < n_tiles || blockIdx.x == 0) {
+    // ---- 2: fold of the partial rows, integer weights k_i = trunc(w_i N / w_max) (branching.rs:24-30), prefix sums
+    {
+      const int64_t w0 = (int64_t)blockIdx.x * SWEEP_THREADS + threadIdx.x;
+      double wv = w0 < W ? __ldcg(w + w0) : 0.0;                // in flight during the fold
       mole_dmc_fold_partials(dp.partials, (unsigned)n_vb, s_red, sm);
       __syncthreads();
       if (blockIdx.x == 0 && threadIdx.x < 4) dp.red[threadIdx.x] = s_red[threadIdx.x];
       const double norm_factor = (double)W / s_red[3];          // branching.rs:24
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        unsigned long long v[DMCB_ITEMS];
-        const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * DMCB_ITEMS;
-#pragma unroll
-        for (int i = 0; i < DMCB_ITEMS; ++i) {
-          unsigned long long k = 0;
-          if (base + i < W) {
-            const double s = __ldcg(w + base + i) * norm_factor;
-            k = (s >= 4294967295.0) ? 4294967295ull : (s > 0.0 ? (unsigned long long)(uint32_t)s : 0ull);
-          }
-          v[i] = k;
+      for (int vb = blockIdx.x; vb < n_vb; vb += gridDim.x) {
+        const int64_t wi = (int64_t)vb * SWEEP_THREADS + threadIdx.x;
+        if (vb != (int)blockIdx.x) wv = wi < W ? __ldcg(w + wi) : 0.0;
+        unsigned long long k = 0ull;
+        if (wi < W) {
+          const double s = wv * norm_factor;
+          k = (s >= 4294967295.0) ? 4294967295ull : (s > 0.0 ? (unsigned long long)(uint32_t)s : 0ull);
         }
-        __syncthreads();
-        const unsigned long long tot = mole_tile_scan_t<SWEEP_THREADS, DMCB_ITEMS>(v);
-#pragma unroll
-        for (int i = 0; i < DMCB_ITEMS; ++i)
-          if (base + i < W) bp.cum[base + i] = v[i];
-        if (threadIdx.x == 0) bp.tile_sums[tile] = tot;
+        unsigned long long tot;
+        const unsigned long long incl = mole_cta_scan_u64(k, s_wt, &tot);
+        if (wi < W) bp.cum[wi] = incl;
+        if ((threadIdx.x & (DMCB_SUB - 1)) == DMCB_SUB - 1) bp.coarse[(size_t)vb * DMCB_SUBS + (threadIdx.x / DMCB_SUB)] = incl;
+        if (threadIdx.x == 0) bp.tile_sums[vb] = tot;
       }
     }
     DMCB_T(2);
     target += gridDim.x;
     mole_grid_barrier(bp.bar, target);
     DMCB_T(3);
-    // ---- 3: exclusive tile offsets in shared memory, N weighted draws, gather (branching.rs:32-37)
-    if (threadIdx.x == 0) s_carry = 0ull;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      unsigned long long carry = 0ull;
-      for (int b = 0; b < n_tiles; b += 32) {
-        const unsigned long long v = (b + lane < n_tiles) ? __ldcg(bp.tile_sums + b + lane) : 0ull;
-        unsigned long long run = v;
+    // ---- 3: exclusive tile offsets (and the coarse prefix sums) in shared memory, N weighted draws, gather (branching.rs:32-37)
+    {
+      if (bp.stage_coarse)
+        for (int i = threadIdx.x; i < n_coarse; i += SWEEP_THREADS) s_coarse[i] = __ldcg(bp.coarse + i);
+      // CTA-wide exclusive scan of the n_vb totals: thread t takes the consecutive entries [t c, (t + 1) c)
+      const int c = (n_vb + SWEEP_THREADS - 1) / SWEEP_THREADS;
+      unsigned long long tv[4] = {0ull, 0ull, 0ull, 0ull}, mine = 0ull;
+      if (c <= 4) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned long long t = __shfl_up_sync(0xffffffffu, run, o);
-          if (lane >= o) run += t;
+        for (int i = 0; i < 4; ++i) {
+          const int idx = threadIdx.x * c + i;
+          if (i < c && idx < n_vb) tv[i] = __ldcg(bp.tile_sums + idx);
+          mine += tv[i];
         }
-        if (b + lane < n_tiles) s_tiles[b + lane] = carry + run - v;
-        carry += __shfl_sync(0xffffffffu, run, 31);
+      } else {
+        for (int i = 0; i < c; ++i) {
+          const int idx = threadIdx.x * c + i;
+          if (idx < n_vb) mine += __ldcg(bp.tile_sums + idx);
+        }
       }
-      if (lane == 0) s_tiles[n_tiles] = carry;
-    }
-    __syncthreads();
-    const double new_weight = __ldcg(dp.red + 2) / (double)W;   // branching.rs:21
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                  // dmc.rs:112-113,133: the division happens on the host
-      bp.step_e[2 * j] = __ldcg(dp.red);
-      bp.step_e[2 * j + 1] = __ldcg(dp.red + 1);
-    }
-    const unsigned long long total = s_tiles[n_tiles];
-    for (int vb = blockIdx.x; vb < n_vb; vb += gridDim.x) {
-      const int64_t jw = (int64_t)vb * SWEEP_THREADS + threadIdx.x;
-      if (jw < W) {
-        const Philox4 p = mole_draw(dp.key, dp.walker_offset + (uint64_t)jw, step, DOM_BRANCH, 0, 0);
-        const unsigned long long u = __umul64hi(mole_u64(p), total);     // uniform integer in [0,total)
-        const int64_t lo = mole_pick_tiled_ld(bp.cum, s_tiles, n_tiles, W, SCAN_TILE, u, MoleCgLoad());
-        bp.src[jw] = (int32_t)lo;
-        for (int c = 0; c < bp.n; ++c) x2[(size_t)c * W + jw] = __ldcg(x + (size_t)c * W + lo);
-        el2[jw] = __ldcg(el + lo);
-        w2[jw] = new_weight;
+      unsigned long long total;
+      unsigned long long run = mole_cta_scan_u64(mine, s_wt, &total) - mine;
+      if (c <= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = threadIdx.x * c + i;
+          if (i < c && idx < n_vb) { s_tiles[idx] = run; run += tv[i]; }
+        }
+      } else {
+        for (int i = 0; i < c; ++i) {
+          const int idx = threadIdx.x * c + i;
+          if (idx < n_vb) { s_tiles[idx] = run; run += __ldcg(bp.tile_sums + idx); }
+        }
+      }
+      if (threadIdx.x == 0) s_tiles[n_vb] = total;
+      __syncthreads();
+      const double new_weight = s_red[2] / (double)W;           // branching.rs:21
+      if (blockIdx.x == 0 && threadIdx.x == 0) {                // dmc.rs:112-113,133: the division happens on the host
+        bp.step_e[2 * j] = s_red[0];
+        bp.step_e[2 * j + 1] = s_red[1];
+      }
+      for (int vb = blockIdx.x; vb < n_vb; vb += gridDim.x) {
+        const int64_t jw = (int64_t)vb * SWEEP_THREADS + threadIdx.x;
+        if (jw < W) {
+          const Philox4 p = mole_draw(dp.key, dp.walker_offset + (uint64_t)jw, step, DOM_BRANCH, 0, 0);
+          const unsigned long long u = __umul64hi(mole_u64(p), total);     // uniform integer in [0,total)
+          // WeightedChoice: the first walker whose inclusive prefix sum exceeds u.  Virtual block: last one whose
+          // exclusive offset is <= u (empty blocks are skipped by construction: offset[t + 1] > u)
+          int tl = 0, th = n_vb - 1;
+          while (tl < th) {
+            const int mid = (tl + th) >> 1;
+            if (s_tiles[mid + 1] > u) th = mid; else tl = mid + 1;
+          }
+          const unsigned long long ul = u - s_tiles[tl];
+          // group of 16 walkers inside the block: first coarse prefix > ul (the last group if none: all-zero weights)
+          int sub = 0;
+          if (bp.stage_coarse) {
+            const unsigned long long* cs = s_coarse + (size_t)tl * DMCB_SUBS;
+#pragma unroll
+            for (int q = DMCB_SUBS - 2; q >= 0; --q) sub += (cs[q] <= ul) ? 1 : 0;   // prefix sums are non-decreasing
+          } else {
+            const unsigned long long* cs = bp.coarse + (size_t)tl * DMCB_SUBS;
+            unsigned long long cv[DMCB_SUBS - 1];
+#pragma unroll
+            for (int q = 0; q < DMCB_SUBS - 1; ++q) cv[q] = __ldcg(cs + q);
+#pragma unroll
+            for (int q = 0; q < DMCB_SUBS - 1; ++q) sub += (cv[q] <= ul) ? 1 : 0;
+          }
+          // one 128-byte line of prefix sums: first entry > ul
+          const int64_t base = (int64_t)tl * SWEEP_THREADS + (int64_t)sub * DMCB_SUB;
+          unsigned long long line[DMCB_SUB];
+#pragma unroll
+          for (int q = 0; q < DMCB_SUB; q += 2) {
+            if (base + q + 1 < W) {
+              const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(bp.cum + base + q));
+              line[q] = t.x; line[q + 1] = t.y;
+            } else {
+              line[q] = base + q < W ? __ldcg(bp.cum + base + q) : ~0ull;
+              line[q + 1] = ~0ull;
+            }
+          }
+          int off = 0;
+#pragma unroll
+          for (int q = 0; q < DMCB_SUB - 1; ++q) off += (line[q] <= ul) ? 1 : 0;
+          int64_t lo = base + off;
+          lo = lo < W ? lo : W - 1;
+          bp.src[jw] = (int32_t)lo;
+          for (int cc = 0; cc < bp.n; ++cc) x2[(size_t)cc * W + jw] = __ldcg(x + (size_t)cc * W + lo);
+          el2[jw] = __ldcg(el + lo);
+          w2[jw] = new_weight;
+        }
       }
     }
     DMCB_T(4);

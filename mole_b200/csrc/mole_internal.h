@@ -165,6 +165,8 @@ struct mole_ens_s {
   double* gram_partials = nullptr; int gram_rows = 0;   // per-CTA partial matrices
   int32_t gram_cols = 0;                                // P + 2 of the last sweep that touched gram
   unsigned int* bar = nullptr;                          // [2] grid-barrier counter + time-out flag of dmc_block_kernel
+  unsigned long long* vb_sums = nullptr;                // [n_vb + 1] / [8 n_vb]: prefix-sum levels of dmc_block_kernel
+  unsigned long long* vb_coarse = nullptr;
   int32_t dmc_block_impl = 0;                           // 0: one persistent launch per block where eligible, 1: per-step launches
   int32_t gram_impl = 0;                                // 0: DMMA (tensor cores), 1: FP64 vector pipe
 };
