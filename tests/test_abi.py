@@ -216,8 +216,10 @@ def test_hot_kernels_do_not_spill():
         assert r["regs"] <= 255
     # (the general LCAO kind's first CUDA path keeps its walker in local memory by design: mole_lsj.cuh; the 6-tile Gram
     # kernel is held to 128 registers for two CTAs per SM and measured faster with its 40-double spill than without)
+    # (the persistent DMC block kernel parks a few step-loop invariants - <= 64 bytes - across its grid barriers)
+    assert all(r["spill_st"] <= 64 for r in rows if "dmc_block_kernel" in r["demangled"])
     assert all(r["spill_st"] == 0 and r["spill_ld"] == 0 for r in rows
-               if not any(t in r["demangled"] for t in ("lsj_", "gram_fma", "gram_dmma_kernel<6>", "sj_sweep_kernel<0, false>"))), \
+               if not any(t in r["demangled"] for t in ("lsj_", "gram_fma", "gram_dmma_kernel<6>", "sj_sweep_kernel<0, false>", "dmc_block_kernel"))), \
         [r["demangled"] for r in rows if r["spill_st"]]
     # two warps per scheduler at 255 registers is the SJ kernel's design point
     assert all(r["regs"] >= 169 for r in rows if r["demangled"].startswith("void sj_sweep_kernel"))
