@@ -23,7 +23,8 @@ pub const MOLE_ERR_INVALID_ARG: i32 = 102;
 pub const MOLE_ERR_NO_DEVICE: i32 = 103;
 pub const MOLE_ERR_ASSERT: i32 = 104;
 
-#[repr(C)] #[derive(Clone, Copy)] pub struct mole_wf_desc { pub kind: i32, pub n_elec: i32, pub n_params: i32, pub reserved: i32, pub params: [f64; 8], pub geom: [f64; 8] }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct mole_ens_health { pub nonfinite_samples: i64, pub nonfinite_dmc_walkers: i64, pub reserved: [i64; 2] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct mole_wf_desc { pub kind: i32, pub n_elec: i32, pub n_params: i32, pub reserved: i32, pub params: [f64; 48], pub geom: [f64; 40] }   // MOLE_WF_MAX_PARAMS, MOLE_WF_MAX_GEOM
 #[repr(C)] #[derive(Clone, Copy)] pub struct mole_op_desc { pub kind: i32, pub n_ions: i32, pub ion_pos: [f64; 24], pub ion_charge: [i32; 8], pub frequency: f64 }
 #[repr(C)] pub struct mole_sweep_args { pub n_sweeps: i32, pub n_discard: i32, pub block_size: i32, pub observables: u32, pub compat: u32, pub flags: u32,
     pub energy_trace: *mut f64, pub wfvalue_trace: *mut f64, pub kinetic_trace: *mut f64, pub pgrad_trace: *mut f64, pub accept_trace: *mut u8 }
@@ -110,6 +111,21 @@ extern "C" {
     pub fn mole_runner_run_logged(ens: *mut mole_ens_s, wf: *mut mole_wf_s, m: *mut mole_metrop_s, op: *mut mole_op_s, observables: u32, compat: u32, steps: i32, block_size: i32, sweep_flags: u32, log: mole_log_fn, user: *mut core::ffi::c_void) -> i32;
     pub fn mole_ensemble_save(ens: *mut mole_ens_s, path: *const core::ffi::c_char) -> i32;
     pub fn mole_ensemble_load(ens: *mut mole_ens_s, path: *const core::ffi::c_char) -> i32;
+    // second round: health counters, SR regularisation, large-P Gram path, DMC block selection, rebalancing, probes
+    pub fn mole_ensemble_health(ens: *mut mole_ens_s, out: *mut mole_ens_health) -> i32;
+    pub fn mole_opt_set_sr_regularization(opt: *mut mole_opt_s, diag_scale: f64, diag_shift: f64) -> i32;
+    pub fn mole_gram_get(ens: *mut mole_ens_s, n_cols: *mut i32, gram: *mut f64) -> i32;
+    pub fn mole_gram_allreduce(ens: *mut mole_ens_s) -> i32;
+    pub fn mole_gram_device_ptr(ens: *mut mole_ens_s, ptr_dev: *mut *mut core::ffi::c_void, n_doubles: *mut i32) -> i32;
+    pub fn mole_gram_select(ens: *mut mole_ens_s, impl_: i32) -> i32;
+    pub fn mole_gram_finalize(n_cols: i32, gram: *const f64, energy: *mut f64, grad: *mut f64) -> i32;
+    pub fn mole_opt_step_gram(opt: *mut mole_opt_s, pars: *const f64, n_cols: i32, gram: *const f64, deltap: *mut f64) -> i32;
+    pub fn mole_opt_sr_matrix_gram(opt: *mut mole_opt_s, n_cols: i32, gram: *const f64, s: *mut f64) -> i32;
+    pub fn mole_dmc_block_select(ens: *mut mole_ens_s, impl_: i32) -> i32;
+    pub fn mole_rebalance(ens: *mut mole_ens_s) -> i32;
+    pub fn mole_rebalance_plan(nranks: i32, totals: *const f64, counts: *const i64, u: f64, shares: *mut i64, moves: *mut i64) -> i32;
+    pub fn mole_bench_gram(ctx: *mut mole_ctx_s, n_walkers: i64, n_samples: i64, cols: i32, impl_: i32, reps: i32, ms: *mut f64, checksum: *mut f64) -> i32;
+    pub fn mole_bench_dmma_peak(ctx: *mut mole_ctx_s, chains: i32, warps_per_sm: i32, tflops: *mut f64) -> i32;
 }
 
 // enumerations of include/mole_b200.h
