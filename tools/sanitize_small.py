@@ -36,5 +36,25 @@ d.dmc_step(st, met, oph, 0.025, -0.47); d.branch(m.ffi.BRANCH_SIMPLE)
 sjb = m.SlaterJastrow(2, 2, (3.68, 0.96, 0.96), (0.5, 1.0, 0.2, 0.1), 1.0); opb = m.ElectronicHamiltonian.from_ions([[0,0,0]],[4])
 db = m.DmcRunner.new(sjb, 100, -14.6, opb, m.MetropolisDiffuse.from_rng(0.01, seed), m.SRBrancher.new(), identical_start=False).ensemble
 print("sj dmc", db.dmc_block(sjb, m.MetropolisDiffuse.from_rng(0.01, seed), opb, m.ffi.BRANCH_SR, 0.01, -14.6, 3)[-1])
+# second round: general LCAO Slater-Jastrow kind (rows + Gram on both pipes, DMC), persistent DMC block kernel against the
+# per-step launches, single-rank rebalancing, the probes
+h4 = [[-2.1, 0, 0], [-0.7, 0, 0], [0.7, 0, 0], [2.1, 0, 0]]
+lw = m.LcaoSlaterJastrow(2, 2, h4, [1.0, 1 / 1.1, 1 / 1.1, 1.0], [[1, 1, 1, 1], [1, 0.5, -0.5, -1]], [0.5, 1.0, 0.1, -0.05])
+lop = m.ElectronicHamiltonian.from_ions(h4, [1, 1, 1, 1])
+for impl in (0, 1):
+    le = m.Ensemble(130, 4, seed); le.init_normal(1.5); le.gram_select(impl)
+    le.sweep(lw, m.MetropolisDiffuse(0.05, seed), lop, n_sweeps=12, n_discard=4, block_size=4, observables=obs)
+    g = le.gram_get()
+    print("lsj gram", impl, g.shape, float(g[0][0]), float(g[0][1]))
+le.dmc_step(lw, m.MetropolisDiffuse(0.02, seed), lop, 0.02, -2.0); le.branch(m.ffi.BRANCH_SR)
+for W in (300, 5000):
+    out = []
+    for impl in (0, 1):
+        de = m.Ensemble(W, 1, seed); de.init_normal(1.0); de.dmc_block_select(impl)
+        out.append(de.dmc_block(st, met, oph, m.ffi.BRANCH_SR, 0.025, -0.47, 7))
+    assert (out[0] == out[1]).all()
+    print("dmc block fused == per-step", W, out[0][-1])
+de.rebalance()
+print("probes", m.default_context().bench_gram(4096, 20, 38, 0, 1)[0] > 0, m.default_context().dmma_peak_tflops(2, 4) > 0)
 m.default_context().synchronize()
 print("done")
