@@ -97,6 +97,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_block_kernel(const DmcBlock
   unsigned long long* const s_tiles = s_dyn;                    // [n_vb + 1] exclusive offsets of the virtual blocks, grand total
   unsigned long long* const s_coarse = s_dyn + n_vb + 1;        // [n_coarse] when staged
   const double sd = sqrt(dp.tau_move);
+  // a CTA that owns exactly one virtual block keeps its walkers in registers from the gather into the next time step
+  constexpr int NE = WfDev<KIND>::NE;
+  const bool single = (int)gridDim.x == n_vb;
+  double xr[3 * NE], el_r = 0.0, w_r = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3 * NE; ++c) xr[c] = 0.0;
   unsigned int target = 0;
 #ifdef MOLE_DMCB_PROF
   unsigned long long tprof[6] = {0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
@@ -111,7 +117,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_block_kernel(const DmcBlock
     for (int vb = blockIdx.x; vb < n_vb; vb += gridDim.x) {
       double s_we = 0.0, s_w = 0.0, s_wn = 0.0, m_wn = 0.0;
       const int64_t wi = (int64_t)vb * SWEEP_THREADS + threadIdx.x;
-      if (wi < W) mole_dmc_walker_step<KIND>(dp, x, w, el, wi, j == 0 ? dp.el_cached : 1, step, sd, s_we, s_w, s_wn, m_wn);
+      if (wi < W) {
+        if (single && j > 0) {                                  // the walker gathered in the previous step is still in registers
+          const double wn = mole_dmc_walker_core<KIND>(dp, xr, w_r, el_r, 1, wi, step, sd, s_we, s_w, s_wn, m_wn);
+          w[wi] = wn;
+          el[wi] = el_r;
+#pragma unroll
+          for (int c = 0; c < 3 * NE; ++c) x[(size_t)c * W + wi] = xr[c];
+          w_r = wn;
+        } else {
+          mole_dmc_walker_step<KIND>(dp, x, w, el, wi, j == 0 ? dp.el_cached : 1, step, sd, s_we, s_w, s_wn, m_wn);
+        }
+      }
       __syncthreads();                                          // sm is reused from the previous virtual block
       mole_dmc_cta_reduce(s_we, s_w, s_wn, m_wn, sm, dp.partials + (size_t)vb * 4);
     }
@@ -120,9 +137,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_block_kernel(const DmcBlock
     mole_grid_barrier(bp.bar, target);
     DMCB_T(1);
     // ---- 2: fold of the partial rows, integer weights k_i = trunc(w_i N / w_max) (branching.rs:24-30), prefix sums
+    unsigned long long draw0;
     {
       const int64_t w0 = (int64_t)blockIdx.x * SWEEP_THREADS + threadIdx.x;
-      double wv = w0 < W ? __ldcg(w + w0) : 0.0;                // in flight during the fold
+      double wv = (single && j > 0) ? w_r : (w0 < W ? __ldcg(w + w0) : 0.0);   // in flight during the fold
+      // the branching variate depends on (walker, step) only: drawn here, in the shadow of the barrier
+      draw0 = mole_u64(mole_draw(dp.key, dp.walker_offset + (uint64_t)w0, step, DOM_BRANCH, 0, 0));
       mole_dmc_fold_partials(dp.partials, (unsigned)n_vb, s_red, sm);
       __syncthreads();
       if (blockIdx.x == 0 && threadIdx.x < 4) dp.red[threadIdx.x] = s_red[threadIdx.x];
@@ -190,8 +210,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_block_kernel(const DmcBlock
       for (int vb = blockIdx.x; vb < n_vb; vb += gridDim.x) {
         const int64_t jw = (int64_t)vb * SWEEP_THREADS + threadIdx.x;
         if (jw < W) {
-          const Philox4 p = mole_draw(dp.key, dp.walker_offset + (uint64_t)jw, step, DOM_BRANCH, 0, 0);
-          const unsigned long long u = __umul64hi(mole_u64(p), total);     // uniform integer in [0,total)
+          const unsigned long long draw = vb == (int)blockIdx.x ? draw0 : mole_u64(mole_draw(dp.key, dp.walker_offset + (uint64_t)jw, step, DOM_BRANCH, 0, 0));
+          const unsigned long long u = __umul64hi(draw, total);            // uniform integer in [0,total)
           // WeightedChoice: the first walker whose inclusive prefix sum exceeds u.  Virtual block: last one whose
           // exclusive offset is <= u (empty blocks are skipped by construction: offset[t + 1] > u)
           int tl = 0, th = n_vb - 1;
@@ -233,8 +253,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) dmc_block_kernel(const DmcBlock
           int64_t lo = base + off;
           lo = lo < W ? lo : W - 1;
           bp.src[jw] = (int32_t)lo;
-          for (int cc = 0; cc < bp.n; ++cc) x2[(size_t)cc * W + jw] = __ldcg(x + (size_t)cc * W + lo);
-          el2[jw] = __ldcg(el + lo);
+#pragma unroll
+          for (int cc = 0; cc < 3 * NE; ++cc) { xr[cc] = __ldcg(x + (size_t)cc * W + lo); x2[(size_t)cc * W + jw] = xr[cc]; }
+          el_r = __ldcg(el + lo);
+          el2[jw] = el_r;
+          w_r = new_weight;
           w2[jw] = new_weight;
         }
       }

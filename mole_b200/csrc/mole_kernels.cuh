@@ -422,31 +422,30 @@ MOLE_D void mole_dmc_fold_partials(const double* partials, unsigned rows, double
 }
 
 // ------------------------------------------------------------------ DMC time step (dmc.rs:87-130)
-// one walker's time step: drift-diffusion move of every electron, weight update, contribution to the step's sums.
-// x / wgt / el are read through L2 (__ldcg): inside dmc_block_kernel other CTAs wrote them earlier in the same launch.
+// one walker's time step on values held in registers: drift-diffusion move of every electron, weight update,
+// contribution to the step's sums.  In: xr = configuration, e_io = E_L before the move when el_cached, w_in = weight.
+// Out: xr = configuration after the move, e_io = E_L after it (0 for a killed walker), returns the new weight.
 template <int KIND>
-MOLE_D void mole_dmc_walker_step(const DmcParams& dp, double* x, double* wgt, double* el, int64_t w, int el_cached, uint32_t step,
-                                 double sd, double& s_we, double& s_w, double& s_wn, double& m_wn) {
+MOLE_D double mole_dmc_walker_core(const DmcParams& dp, double* xr, double w_in, double& e_io, int el_cached, int64_t w, uint32_t step,
+                                   double sd, double& s_we, double& s_w, double& s_wn, double& m_wn) {
   using WF = WfDev<KIND>;
   constexpr int NE = WF::NE;
   const WfParams& p = dp.wf;
-  const int64_t W = dp.W;
   Walker<WF> wk;
 #pragma unroll
-  for (int c = 0; c < 3 * NE; ++c) wk.st.x[c] = __ldcg(x + (size_t)c * W + w);
+  for (int c = 0; c < 3 * NE; ++c) wk.st.x[c] = xr[c];
   WF::init(p, wk.st);
   wk.refresh(p);
   double hp, kp;
   // E_L before the move (dmc.rs:89-96).  It equals the post-move E_L of the previous step for the
   // same configuration, so it is carried in `el` (and gathered by branching) instead of recomputed.
-  const double e_old = el_cached ? __ldcg(el + w) : mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);
+  const double e_old = el_cached ? e_io : mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);
   const uint64_t wid = dp.walker_offset + (uint64_t)w;
 #pragma unroll
   for (int e = 0; e < NE; ++e) mole_move_state<WF, MOLE_METROP_DIFFUSE>(p, wk, e, dp.tau_move, sd, dp.key, wid, step, dp.compat);
   const double e_new = mole_local_energy<WF>(p, dp.ham, wk.st, wk.psi, hp, kp);   // :115-124
   // a walker whose local energy is not finite (upstream: NaN ensemble energy from here on) is counted
   // (acc[ACC_BAD_DMC]) and dies: weight 0 before and after the step, never picked by the brancher
-  const double w_in = __ldcg(wgt + w);
   const double w_up = w_in * exp(-dp.tau_weight * ((e_old + e_new) / 2.0 - dp.e_ref));           // :126-128
   const bool bad = !isfinite(e_old) || !isfinite(e_new) || !isfinite(w_up);
   if (bad) atomicAdd(dp.health, 1.0);
@@ -456,10 +455,28 @@ MOLE_D void mole_dmc_walker_step(const DmcParams& dp, double* x, double* wgt, do
   const double wn = bad ? 0.0 : w_up;
   s_wn += wn;
   m_wn = fmax(m_wn, wn);
-  wgt[w] = wn;
-  el[w] = bad ? 0.0 : e_new;
+  e_io = bad ? 0.0 : e_new;
 #pragma unroll
-  for (int c = 0; c < 3 * NE; ++c) x[(size_t)c * W + w] = wk.st.x[c];
+  for (int c = 0; c < 3 * NE; ++c) xr[c] = wk.st.x[c];
+  return wn;
+}
+
+// the same from / to the ensemble arrays.  x / wgt / el are read through L2 (__ldcg): inside dmc_block_kernel other
+// CTAs wrote them earlier in the same launch.
+template <int KIND>
+MOLE_D void mole_dmc_walker_step(const DmcParams& dp, double* x, double* wgt, double* el, int64_t w, int el_cached, uint32_t step,
+                                 double sd, double& s_we, double& s_w, double& s_wn, double& m_wn) {
+  constexpr int NE = WfDev<KIND>::NE;
+  const int64_t W = dp.W;
+  double xr[3 * NE];
+#pragma unroll
+  for (int c = 0; c < 3 * NE; ++c) xr[c] = __ldcg(x + (size_t)c * W + w);
+  double e_io = el_cached ? __ldcg(el + w) : 0.0;
+  const double wn = mole_dmc_walker_core<KIND>(dp, xr, __ldcg(wgt + w), e_io, el_cached, w, step, sd, s_we, s_w, s_wn, m_wn);
+  wgt[w] = wn;
+  el[w] = e_io;
+#pragma unroll
+  for (int c = 0; c < 3 * NE; ++c) x[(size_t)c * W + w] = xr[c];
 }
 
 // CTA reduction of the step's sums (3 sums + 1 max) into one row of `partials`; fixed order for a given CTA shape

@@ -204,6 +204,33 @@ def test_config5_ne_slater_jastrow_full_size(mole, orc):
     assert np.isfinite(e) and np.isfinite(err) and np.isfinite(g).all()   # 200 sweeps from N(0, 0.5): not yet equilibrated
 
 
+def test_config5_energy_at_full_size_agrees_with_the_oracle(mole, orc):
+    """config 5 had no energy check.  The bench's own schedule (N(0, 0.5) start, 200 box sweeps, 50 diffusion
+    sweeps, then 200 measured sweeps at 2^17 walkers): the GPU energy against the oracle's independent estimate from 768 of
+    the same equilibrated walkers (60 more sweeps on the CPU, error from the spread over walkers), and against the window
+    the trial function allows (single-zeta Ne with the test case's unoptimised Jastrow: -126.8; Hartree-Fock limit -128.55)."""
+    c = cases()["sj_ne"]
+    wf, op = c["make"](mole)
+    W, steps, block = 1 << 17, 200, 10
+    ens = mole.Ensemble(W, 10, SEED0)
+    ens.init_normal(0.5)
+    met = mole.MetropolisDiffuse(0.02, SEED0)
+    ens.sweep(wf, mole.MetropolisBox(0.5, SEED0), op, n_sweeps=200, observables=0)
+    ens.sweep(wf, met, op, n_sweeps=50, observables=0)
+    x_eq = ens.get_configs().copy()
+    ens.acc_reset()
+    ens.sweep(wf, met, op, n_sweeps=steps, n_discard=block, block_size=block, observables=mole.ffi.OBS_ENERGY)
+    e, err, accp, _ = mole.acc_finalize(ens.acc_get())
+    assert ens.health() == (0, 0)
+    assert -127.6 < e < -126.4 and err < 0.01 and 0.8 < accp < 0.95, (e, err, accp)   # measured: -126.802 +/- 0.004
+    sub = np.ascontiguousarray(x_eq[::W // 768][:768])
+    opts = orc.run_options(orc.METROP_DIFFUSE, 0.02, orc.OBS_ENERGY, nan_reject=1)
+    r = orc.ensemble_run(c["owf"], c["oham"], opts, sub, bytes([3] * 32), 60, 10)
+    per_walker = np.asarray(r["energy"]).reshape(len(sub), -1).mean(axis=1)
+    e_orc, se_orc = per_walker.mean(), per_walker.std(ddof=1) / np.sqrt(len(sub))
+    assert se_orc < 0.2 and abs(e - e_orc) < 4.0 * np.hypot(se_orc, err), (e, err, e_orc, se_orc)   # oracle: -126.74 +/- 0.10
+
+
 def test_config4_dmc_full_size_step_and_branch_match_oracle(mole, orc):
     """DMC, Gaussian guide for the H atom, tau = 0.025, SRBrancher, 2^18 walkers (examples/dmc.rs): one full-size time
     step and one full-size branching against the oracle, then the launch-bound block loop against the step loop."""
