@@ -1,5 +1,6 @@
-"""Multi-rank DEVICE paths: mole_acc_allreduce over NCCL and the multi-rank mole_dmc_block
-(population islands, one all-gather per block) on two GPUs, against single-rank runs of the same global walker ids.
+"""Multi-rank DEVICE paths: mole_acc_allreduce and mole_gram_allreduce over NCCL, the multi-rank
+mole_dmc_block (population islands, one all-gather per block) and mole_rebalance on two GPUs, against single-rank runs of
+the same global walker ids.
 Needs >= 2 visible GPUs (gpurun --gpus 2); skipped otherwise.  One process per GPU, like the bench."""
 import os
 import sys
@@ -27,6 +28,12 @@ def _dmc_setup(m, ctx):
     wf = m.STO(0.9, ctx=ctx)
     op = m.ElectronicHamiltonian.from_ions([[0, 0, 0]], [1], ctx=ctx)
     return wf, op, m.MetropolisDiffuse.from_rng(0.025, SEED)
+
+
+def _lsj_setup(m, ctx):
+    h4 = [[-2.1, 0, 0], [-0.7, 0, 0], [0.7, 0, 0], [2.1, 0, 0]]
+    wf = m.LcaoSlaterJastrow(2, 2, h4, [1.0, 1 / 1.1, 1 / 1.1, 1.0], [[1, 1, 1, 1], [1, 0.5, -0.5, -1]], [0.5, 1.0, 0.1, -0.05], ctx=ctx)
+    return wf, m.ElectronicHamiltonian.from_ions(h4, [1, 1, 1, 1], ctx=ctx)
 
 
 def _rank(rank, world, uid, W_local, out):
@@ -75,6 +82,15 @@ def _rank(rank, world, uid, W_local, out):
     res["reb_cfgs"] = r.get_configs()
     res["reb_weights"] = r.get_weights()
     del r
+    # ---- large-P path: sample rows on each shard, Gram matrices summed over NCCL
+    lwf, lop = _lsj_setup(m, ctx)
+    g = m.Ensemble(W_local // 2, 4, SEED, walker_offset=rank * (W_local // 2), ctx=ctx)
+    g.init_normal(1.5)
+    g.sweep(lwf, m.MetropolisDiffuse.from_rng(0.05, SEED), lop, n_sweeps=16, n_discard=4, block_size=4, observables=obs)
+    res["gram_local"] = g.gram_get()
+    g.gram_allreduce()
+    res["gram_total"] = g.gram_get()
+    del g
     out[rank] = res
     del ens, a, b
     ctx.close()
@@ -117,6 +133,16 @@ def test_two_gpu_allreduce_and_dmc_block():
     swe = r0["dmc_rows"][:, 0] + r1["dmc_rows"][:, 0]
     sw = r0["dmc_rows"][:, 1] + r1["dmc_rows"][:, 1]
     assert np.array_equal(r0["dmc_block_energies"], swe / sw)
+    # large-P path: every rank holds the same summed Gram matrix = the single-rank contraction over the same global walkers
+    assert np.array_equal(r0["gram_total"], r1["gram_total"])
+    assert np.allclose(r0["gram_total"], r0["gram_local"] + r1["gram_local"], rtol=1e-14, atol=0)
+    lwf, lop = _lsj_setup(m, ctx)
+    g = m.Ensemble(W_local, 4, SEED)
+    g.init_normal(1.5)
+    g.sweep(lwf, m.MetropolisDiffuse.from_rng(0.05, SEED), lop, n_sweeps=16, n_discard=4, block_size=4, observables=obs)
+    one = g.gram_get()
+    assert one.shape == (14, 14) and one[0, 0] == W_local * 12
+    assert np.max(np.abs(np.triu(one - r0["gram_total"]))) < 1e-11 * np.max(np.abs(one))
     # rebalancing: total weight conserved, equal weights everywhere, rank 1's walkers fill 3/4 of all slots
     for r in (r0, r1):
         assert np.all(r["reb_weights"] == 2.0) and r["reb_cfgs"].shape[0] == W_local
