@@ -347,18 +347,6 @@ __global__ void __launch_bounds__(LSJ_THREADS) lsj_eval_kernel(const double* __r
   hk.kind = MOLE_OP_KINETIC;
   double kin, pot, O[MOLE_WF_MAX_PARAMS], g[3 * LSJ_MAXE];
   lsj_measure(c, hk, w, kin, pot, O, g);
-#ifdef MOLE_LSJ_DEBUG
-  if (wi == 0) {
-    printf("DBG ne %d np %d nc %d psi %.10e kin %.10e\n", c.ne, c.np, c.nc, w.psi, kin);
-    for (int e = 0; e < c.ne; ++e) {
-      double G[3];
-      lsj_gradlnD(w.dphi[e], w.minv[lsj_spin(c, e)], lsj_n(c, lsj_spin(c, e)), lsj_idx(c, e), G);
-      printf("DBG e %d g %.8e %.8e %.8e | G(state) %.8e %.8e %.8e gf %.8e %.8e %.8e\n", e, g[3 * e], g[3 * e + 1], g[3 * e + 2], G[0], G[1], G[2],
-             w.gf[e][0], w.gf[e][1], w.gf[e][2]);
-    }
-    for (int k = 0; k < c.np; ++k) printf("DBG O %d %.8e\n", k, O[k]);
-  }
-#endif
   if (psi) psi[wi] = w.psi;
   if (lap) lap[wi] = -2.0 * kin * w.psi;
   if (grad)
