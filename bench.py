@@ -64,7 +64,7 @@ def clocks_sampler(stop, out, gpu_index):
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except OSError:
         return
@@ -509,7 +509,7 @@ def run_dmc(args):
         "us_per_time_step": 1e3 * ms / (args.steps * S),
         "energy": {"value": e_mean, "error_over_blocks": e_err, "exact": -0.5, "reference_energy_end": state["eref"]},
         "health": {"nonfinite_dmc_walker_steps": int(state["bad"])},
-        "roofline": {"bound": "latency (3 launches per time step; fp64 figure for context)", "kernel": "dmc_step_kernel + sr_weights_scan_fused + sr_pick_gather_tiled",
+        "roofline": {"bound": "latency (one cooperative launch per block: ~7 dependent L2 round trips and 2 grid barriers per time step; fp64 figure for context)", "kernel": "dmc_block_kernel<KIND>",
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                      "f_alg_per_walker_step": f_alg, "traffic": None},
         "e2e": {"value": units / (ms_e2e * 1e-3), "unit": "walker-steps/s", "h2d_bytes_per_step": W * 4 * 8 * world,
