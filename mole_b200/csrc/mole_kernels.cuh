@@ -277,11 +277,14 @@ __global__ void eval_kernel(const double* __restrict__ x, int64_t W, WfParams p,
 // ------------------------------------------------------------------ fused sweep
 // One thread per walker (grid-stride).  Per launch: load state -> n_sweeps x (N_e Metropolis moves
 // [+ sample E_L, O_k, moments]) -> store state -> block-tree reduction of the accumulators.
-// Occupancy target (measured at 2^20 walkers): 16 warps/SM (128 registers) is +3..4 % for the one- and
-// two-electron STO / Gaussian kinds and +10 % at 2^16 walkers; the H2 Heitler-London kind would spill there
-// and keeps 12 warps/SM, like the two-electron LCAO kinds.
+// Occupancy target: 16 warps/SM (128 registers) for every kind.  Measured (B200, SR sweeps with moments): +3..4 % for the
+// one- and two-electron STO / Gaussian kinds at 2^20 walkers and +10 % at 2^16.  The H2 Heitler-London and two-electron
+// LCAO kinds spill 100-200 bytes per thread at 128 registers and ran at 12 warps/SM (156 registers, no spill) until the
+// second round; timed side by side they are equal at 2^18 and 2^20 walkers (H2 13.81 / 13.76 ms for 2^20 x 200 sweeps,
+// LCAO singlet 17.12 / 17.09) and the 16-warp build is 10-12 % faster at 2^16 walkers x 2500 sweeps (H2 14.48 -> 13.18 ms,
+// LCAO singlet 18.05 -> 16.09), where 512 CTAs fit one wave of 592 instead of one and a tail of 444.
 #ifndef MOLE_SWEEP_MIN_CTAS
-#define MOLE_SWEEP_MIN_CTAS(KIND) ((KIND) == K_H2_HL_STO || (KIND) == K_LCAO_2E_1C || (KIND) == K_LCAO_2E_2C ? 3 : 4)
+#define MOLE_SWEEP_MIN_CTAS(KIND) 4
 #endif
 template <int KIND, int METROP, bool OPT>
 __global__ void __launch_bounds__(SWEEP_THREADS, MOLE_SWEEP_MIN_CTAS(KIND)) sweep_kernel(const SweepParams sp) {

@@ -196,8 +196,8 @@ def test_struct_sizes_of_series_and_log_records(mole):
 def test_hot_kernels_do_not_spill():
     """Static check on the ptxas -v log of the build (tools/ptxas_report.py): the Slater-Jastrow sweep / DMC kernels
     (the bench workload) and the DMC step kernels hold their state in registers -- a spill there is a silent 10-20 %
-    regression that parity tests cannot see.  Round 2: no kernel of the library spills any more (the two-centre LCAO SR
-    variant keeps its 18 moments in shared memory)."""
+    regression that parity tests cannot see.  Round 2: the two-centre LCAO SR variant keeps its 18 moments in shared
+    memory; the spills that remain are listed below, each with the measurement that keeps it."""
     import os, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "tools"))
@@ -216,10 +216,14 @@ def test_hot_kernels_do_not_spill():
         assert r["regs"] <= 255
     # (the general LCAO kind's first CUDA path keeps its walker in local memory by design: mole_lsj.cuh; the 6-tile Gram
     # kernel is held to 128 registers for two CTAs per SM and measured faster with its 40-double spill than without)
+    # (the H2 Heitler-London and two-electron LCAO sweeps are held to 128 registers for 16 warps/SM: equal at 2^20 walkers,
+    # 10-12 % faster at 2^16 than the spill-free 156-register build, mole_kernels.cuh)
+    two_e = ("sweep_kernel<3,", "sweep_kernel<8,", "sweep_kernel<9,")
+    assert all(r["spill_st"] <= 256 for r in rows if any(t in r["demangled"] for t in two_e))
     # (the persistent DMC block kernel parks a few step-loop invariants - <= 64 bytes - across its grid barriers)
     assert all(r["spill_st"] <= 64 for r in rows if "dmc_block_kernel" in r["demangled"])
     assert all(r["spill_st"] == 0 and r["spill_ld"] == 0 for r in rows
-               if not any(t in r["demangled"] for t in ("lsj_", "gram_fma", "gram_dmma_kernel<6>", "sj_sweep_kernel<0, false>", "dmc_block_kernel"))), \
+               if not any(t in r["demangled"] for t in ("lsj_", "gram_fma", "gram_dmma_kernel<6>", "sj_sweep_kernel<0, false>", "dmc_block_kernel") + two_e)), \
         [r["demangled"] for r in rows if r["spill_st"]]
     # two warps per scheduler at 255 registers is the SJ kernel's design point
     assert all(r["regs"] >= 169 for r in rows if r["demangled"].startswith("void sj_sweep_kernel"))
