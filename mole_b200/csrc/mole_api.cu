@@ -569,6 +569,9 @@ int32_t mole_sweep(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op, co
       }
       sp.osamp = e->osamp;
     }
+    // all walkers resident (up to 16 CTAs of 64 threads per SM): the kernel streams its local-memory frames through
+    // DRAM at 2^16 walkers (ncu: 30 GB per 20 sweeps, frames 275 MB > L2), yet fewer resident CTAs so that the frames
+    // fit L2 measured slower at every setting (H8, 2^16 walkers, 50 sweeps: 16 CTAs/SM 35.4 ms, 8 34.7, 4 43.9, 2 54.1)
     const int blocks = std::min(cdiv(W, LSJ_THREADS), e->partial_rows);
     if (m->kind == MOLE_METROP_BOX) {
       if (opt) lsj_sweep_kernel<MOLE_METROP_BOX, true><<<blocks, LSJ_THREADS, 0, STREAM(ctx)>>>(sp);
