@@ -245,6 +245,18 @@ def _dmc_case(mole, name):
     if name == "h2":
         return (mole.HydrogenMoleculeWaveFunction(1.4, [0.5]),
                 mole.ElectronicHamiltonian.from_ions([[-0.7, 0, 0], [0.7, 0, 0]], [1, 1]), 2, -1.1)
+    if name == "he":
+        return mole.HeliumAtomWaveFunction(1.6875), mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [2]), 2, -2.85
+    ions = [[-1.25, 0, 0], [1.25, 0, 0]]
+    if name == "h2p":
+        return mole.H2WF(2.5, 1.0), mole.ElectronicHamiltonian.from_ions(ions, [1, 1]), 1, -0.55
+    if name == "lcao_h2p":
+        return (mole.SingleDeterminant([mole.Orbital([[1.0], [1.0]], mole.Hydrogen1sBasis(ions, [1.0]))]),
+                mole.ElectronicHamiltonian.from_ions(ions, [1, 1]), 1, -0.55)
+    if name == "lcao_he":
+        b1 = mole.Hydrogen1sBasis([[0, 0, 0]], [1.0 / 1.6875])
+        return (mole.SpinDeterminantProduct([mole.Orbital([[1.0]], b1), mole.Orbital([[1.0]], b1)], 1),
+                mole.ElectronicHamiltonian.from_ions([[0, 0, 0]], [2]), 2, -2.85)
     bs = mole.Hydrogen1sBasis([[-0.7, 0, 0], [0.7, 0, 0]], [0.85])
     wf = mole.SingleDeterminant([mole.Orbital([[1.0], [1.0]], bs), mole.Orbital([[1.0], [-1.0]], bs)])
     return wf, mole.ElectronicHamiltonian.from_ions([[-0.7, 0, 0], [0.7, 0, 0]], [1, 1]), 2, -0.8
@@ -252,7 +264,8 @@ def _dmc_case(mole, name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,W,n_steps", [("sto", 1, 4), ("sto", 129, 7), ("sto", 32768, 40), ("sto", 100003, 9), ("sto", 300000, 6),
-                                            ("gaussian", 4097, 10), ("h2", 3000, 11), ("lcao_triplet", 2500, 8)])
+                                            ("gaussian", 4097, 10), ("h2", 3000, 11), ("lcao_triplet", 2500, 8),
+                                            ("he", 2000, 6), ("h2p", 1500, 6), ("lcao_h2p", 1500, 6), ("lcao_he", 1200, 6)])
 def test_dmc_block_persistent_launch_is_bit_identical_to_per_step_launches(mole, name, W, n_steps):
     """the whole-block cooperative launch (mole_dmc_block.cuh: three phases, two grid barriers per step, virtual blocks of
     128 walkers) against the per-step launches selected with mole_dmc_block_select(1): configurations, weights, cached
