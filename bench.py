@@ -45,6 +45,7 @@ FLOPS = json.load(open(os.path.join(ROOT, "bench_data", "flops.json")))
 # DMC (BASELINE.json configs[3], examples/dmc.rs:189-210): H atom, Gaussian guide at its VMC optimum 1/a^2 = 8/(9 pi)
 DMC_A = float(np.sqrt(9.0 * np.pi / 8.0))   # psi = exp(-(r/a)^2), examples/dmc.rs:44-57: optimum 1/a^2 = 8/(9 pi)
 DMC_TAU = 0.025
+REBALANCE_RATIO = 1.05      # include/mole_b200.h MOLE_REBALANCE_RATIO
 # 1s STO guide with alpha > 1: E_L = -alpha^2/2 + (alpha - 1)/r is bounded BELOW, so walkers next to the nucleus die instead of
 # multiplying.  With alpha < 1 (or the example's cusp-less Gaussian) E_L -> -inf at the nucleus and the reference's cut-off-free
 # DMC collapses a large population onto it sooner or later (observed at 2 x 2^15 walkers after ~4400 steps with alpha = 0.9:
@@ -467,6 +468,8 @@ def run_dmc(args):
     host_cfgs.numpy()[...] = ens.get_configs()
     host_w = torch.ones(W, dtype=torch.float64, pin_memory=True)
     state = {"e2e": False, "eref": DMC_EREF[args.dmc_guide], "bad": 0}
+    if world > 1:
+        ens.rebalance()      # untimed: opens the NCCL send/recv channels once (~0.3 s); the islands start with equal weights anyway
     hist = []
 
     def step(it, timed):
@@ -482,6 +485,17 @@ def run_dmc(args):
                                                                              se.min(), se.max(), state["eref"]), file=sys.stderr, flush=True)
         state["eref"] = 0.5 * (state["eref"] + eb)                          # dmc.rs:163-177
         hist.append(eb)
+        if world > 1:                                                       # as mole_dmc_diffuse does between blocks
+            ratio = ens.island_imbalance()
+            if args.verbose:
+                print("  rank %d block %d: island weight ratio %.6f" % (rank, it, ratio), file=sys.stderr, flush=True)
+            if ratio > REBALANCE_RATIO:
+                t_r = time.perf_counter()
+                ens.rebalance()
+                state["rebalanced"] = state.get("rebalanced", 0) + 1
+                if args.verbose:
+                    ctx.synchronize()
+                    print("  rank %d block %d: rebalanced in %.3f ms" % (rank, it, 1e3 * (time.perf_counter() - t_r)), file=sys.stderr, flush=True)
 
     def reset():
         state["eref"] = DMC_EREF[args.dmc_guide]
@@ -507,6 +521,7 @@ def run_dmc(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": dmc_config(args, world),
         "us_per_time_step": 1e3 * ms / (args.steps * S),
+        "island_rebalances": state.get("rebalanced", 0),
         "energy": {"value": e_mean, "error_over_blocks": e_err, "exact": -0.5, "reference_energy_end": state["eref"]},
         "health": {"nonfinite_dmc_walker_steps": int(state["bad"])},
         "roofline": {"bound": "latency (one cooperative launch per block: ~7 dependent L2 round trips and 2 grid barriers per time step; fp64 figure for context)", "kernel": "dmc_block_kernel<KIND>",

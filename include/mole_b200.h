@@ -346,6 +346,11 @@ int32_t mole_branch(mole_ens_t ens, int32_t kind);
  * mean weight; walker counts per rank are unchanged.  Call it between blocks.  mole_rebalance_plan is the host
  * arithmetic alone (shares[r], moves[src][dst]) for a given shared draw u in [0, 1). */
 int32_t mole_rebalance(mole_ens_t ens);
+/* largest / smallest island weight per walker at the last step of the last SRBrancher block (1.0 on one rank; the same
+ * value on every rank, no extra collective beyond the walker counts): mole_dmc_diffuse rebalances between blocks when
+ * it exceeds MOLE_REBALANCE_RATIO (measured: two islands of 2^15 H-atom walkers drift 3 % apart in 2800 time steps) */
+#define MOLE_REBALANCE_RATIO 1.05
+int32_t mole_dmc_island_imbalance(mole_ens_t ens, double* ratio);
 int32_t mole_rebalance_plan(int32_t nranks, const double* totals, const int64_t* counts, double u, int64_t* shares,
                             int64_t* moves /* nranks x nranks, nullable */);
 /* source walker index of every walker after the last mole_branch (parity tests) */

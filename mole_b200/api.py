@@ -744,6 +744,12 @@ class Ensemble:
     def branch(self, kind):
         self._c(lib().mole_branch(self.handle, C.c_int32(kind)))
 
+    def island_imbalance(self):
+        """largest / smallest island weight per walker after the last SRBrancher block (1.0 on a single rank)."""
+        r = C.c_double()
+        self._c(lib().mole_dmc_island_imbalance(self.handle, C.byref(r)))
+        return r.value
+
     def rebalance(self):
         """cross-rank population rebalancing (mole_rebalance): equal weights everywhere, surplus walkers migrate"""
         self._c(lib().mole_rebalance(self.handle))

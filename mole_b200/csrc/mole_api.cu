@@ -683,6 +683,32 @@ int32_t mole_gram_device_ptr(mole_ens_t e, void** p, int32_t* n_doubles) {
   return MOLE_OK;
 }
 
+// Ratio of the largest to the smallest island weight PER WALKER at the last step of the last SRBrancher block (1 on a
+// single rank, or before any block): the same number on every rank, formed from rows that block gathered anyway.
+int32_t mole_dmc_island_imbalance(mole_ens_t e, double* ratio) {
+  if (!e || !ratio) return MOLE_ERR_INVALID_ARG;
+  *ratio = 1.0;
+  if (e->island_sw.size() < 2) return MOLE_OK;
+  // every island has the rank's own walker count; counts are equal under the bench's sharding, and in general the
+  // per-walker mean is what rebalancing equalises - the counts come from the communicator
+  if (e->island_cnt.size() != e->island_sw.size()) {            // constant for the life of the ensemble: gathered once
+    e->island_cnt.assign(e->island_sw.size(), (double)e->W);
+    if (e->ctx->nranks > 1) {
+      double mine = (double)e->W;
+      int32_t rc = mole_comm_allgather_host(e->ctx, &mine, 1, e->island_cnt.data());
+      if (rc != MOLE_OK) { e->island_cnt.clear(); return rc; }
+    }
+  }
+  const std::vector<double>& cnt = e->island_cnt;
+  double lo = 1e300, hi = 0.0;
+  for (size_t r = 0; r < e->island_sw.size(); ++r) {
+    const double m = e->island_sw[r] / cnt[r];
+    lo = std::min(lo, m); hi = std::max(hi, m);
+  }
+  *ratio = (lo > 0.0 && std::isfinite(hi)) ? hi / lo : HUGE_VAL;
+  return MOLE_OK;
+}
+
 int32_t mole_dmc_block_select(mole_ens_t e, int32_t impl) {
   if (!e || (impl != 0 && impl != 1)) return MOLE_ERR_INVALID_ARG;
   e->dmc_block_impl = impl;
@@ -931,6 +957,8 @@ int32_t mole_dmc_block(mole_ens_t e, mole_wf_t wf, mole_metrop_t m, mole_op_t op
   if (fused) CU(ctx, cudaMemcpyAsync(bar_flag, e->bar, sizeof(bar_flag), cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
   if (bar_flag[1]) return mole_set_error(ctx, MOLE_ERR_CUDA, "dmc_block_kernel: grid barrier timed out");
+  e->island_sw.assign(nr, 0.0);                                    // island totals, for mole_dmc_island_imbalance
+  for (int r = 0; r < nr; ++r) e->island_sw[r] = rows[((size_t)r * n_steps + n_steps - 1) * 2 + 1];
   for (int j = 0; j < n_steps; ++j) {
     double swe = 0.0, sw = 0.0;                                    // rank order: identical on every rank
     for (int r = 0; r < nr; ++r) { swe += rows[((size_t)r * n_steps + j) * 2]; sw += rows[((size_t)r * n_steps + j) * 2 + 1]; }
@@ -1018,6 +1046,7 @@ int32_t mole_rebalance(mole_ens_t e) {
   cudaStream_t st = STREAM(ctx);
   int32_t rc;
   const int64_t W = e->W;
+  if ((rc = mole_comm_warm_p2p(ctx)) != MOLE_OK) return rc;   // first call on a communicator: opens every peer pair once
   if (!e->w_uniform) {   // weights set by hand or by a time step: resample inside the rank only if they really differ
     std::vector<double> hw(W);
     CU(ctx, cudaMemcpyAsync(hw.data(), e->w, W * sizeof(double), cudaMemcpyDeviceToHost, st));

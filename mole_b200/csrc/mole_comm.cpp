@@ -137,6 +137,23 @@ int32_t mole_comm_exchange_rows(mole_ctx_s* ctx, const double* send_dev, double*
   return MOLE_OK;
 }
 
+int32_t mole_comm_warm_p2p(mole_ctx_s* ctx) {
+  if (!ctx || ctx->nranks <= 1 || !ctx->nccl_comm || ctx->p2p_warm) return MOLE_OK;
+  const int n = ctx->nranks;
+  double* buf = nullptr;                                       // [0] what this rank sends, [1 + src] what it receives
+  if (cudaMalloc(&buf, (size_t)(n + 1) * sizeof(double)) != cudaSuccess) return mole_set_error(ctx, MOLE_ERR_CUDA, "cudaMalloc failed");
+  cudaMemsetAsync(buf, 0, (size_t)(n + 1) * sizeof(double), (cudaStream_t)ctx->stream);
+  std::vector<MoleMove> moves;
+  for (int src = 0; src < n; ++src)
+    for (int dst = 0; dst < n; ++dst)
+      if (src != dst) moves.push_back(MoleMove{src, dst, 0, 1 + src, 1});
+  const int32_t rc = mole_comm_exchange_rows(ctx, buf, buf, 1, moves);
+  cudaStreamSynchronize((cudaStream_t)ctx->stream);
+  cudaFree(buf);
+  if (rc == MOLE_OK) ctx->p2p_warm = 1;
+  return rc;
+}
+
 extern "C" {
 
 int32_t mole_comm_get_unique_id(uint8_t id[MOLE_NCCL_UNIQUE_ID_BYTES]) {

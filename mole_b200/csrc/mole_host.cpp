@@ -543,6 +543,13 @@ int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_
   for (int block_nr = 0; block_nr < blocks; ++block_nr) {
     // the whole block is enqueued without host reads: E_ref only changes between blocks (:143-145)
     if ((rc = mole_dmc_block(ens, wf, m, op, branch_kind, time_step, e_ref, block_size, se.data())) != MOLE_OK) return rc;
+    // multi-rank: the ranks are population islands inside a block; when their weights per walker have drifted more than
+    // 5 % apart they become one equal-weight population again (mole_rebalance).  Every rank takes the same decision.
+    if (branch_kind == MOLE_BRANCH_SR && ens->ctx->nranks > 1) {
+      double ratio = 1.0;
+      if ((rc = mole_dmc_island_imbalance(ens, &ratio)) != MOLE_OK) return rc;
+      if (ratio > MOLE_REBALANCE_RATIO && (rc = mole_rebalance(ens)) != MOLE_OK) return rc;
+    }
     double sum = 0.0;
     for (int j = 0; j < block_size; ++j, ++t) {
       sum += se[j];                // :133-135

@@ -117,6 +117,7 @@ struct mole_ctx_s {
   void* nccl_comm = nullptr;
   double* comm_scratch = nullptr;  // device, 16 doubles
   int nranks = 1, rank = 0;
+  int p2p_warm = 0;                // every send/recv pair of the communicator has been opened (mole_comm_warm_p2p)
   // ensembles keep a pointer to their context: a context destroyed while ensembles are alive is only marked and
   // is freed with the last of them (bindings with garbage-collected wrappers destroy in arbitrary order)
   int live_ens = 0;
@@ -167,6 +168,8 @@ struct mole_ens_s {
   unsigned int* bar = nullptr;                          // [2] grid-barrier counter + time-out flag of dmc_block_kernel
   unsigned long long* vb_sums = nullptr;                // [n_vb + 1] / [8 n_vb]: prefix-sum levels of dmc_block_kernel
   unsigned long long* vb_coarse = nullptr;
+  std::vector<double> island_cnt;                       // walker counts of all ranks (gathered once)
+  std::vector<double> island_sw;                        // per-rank sum of weights at the last step of the last SR block
   int32_t dmc_block_impl = 0;                           // 0: one persistent launch per block where eligible, 1: per-step launches
   int32_t gram_impl = 0;                                // 0: DMMA (tensor cores), 1: FP64 vector pipe
 };
@@ -184,4 +187,6 @@ struct MoleMove { int src, dst; int64_t send_first, recv_first, count; };
 int32_t mole_comm_exchange_rows(mole_ctx_s* ctx, const double* send_dev, double* recv_dev, int row_len, const std::vector<MoleMove>& moves);
 // population shares and the transfer plan of mole_rebalance (pure host arithmetic, identical on every rank)
 void mole_rebalance_shares(int nranks, const double* totals, const int64_t* counts, double u, int64_t* shares);
+// one 8-byte exchange between every pair of ranks: NCCL connects peers lazily, ~0.15 s for the first send/recv of a pair
+int32_t mole_comm_warm_p2p(mole_ctx_s* ctx);
 std::vector<MoleMove> mole_rebalance_moves(int nranks, const int64_t* counts, const int64_t* shares);

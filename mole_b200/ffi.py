@@ -112,7 +112,7 @@ SYMBOLS = [
     "mole_series_length", "mole_series_clear", "mole_series_block_sizes", "mole_series_analyze", "mole_series_get",
     "mole_series_write_text", "mole_runner_run_logged", "mole_ensemble_save", "mole_ensemble_load", "mole_dmc_block",
     "mole_ensemble_health", "mole_opt_set_sr_regularization", "mole_gram_get", "mole_gram_allreduce",
-    "mole_gram_device_ptr", "mole_gram_select", "mole_gram_finalize", "mole_opt_step_gram", "mole_opt_sr_matrix_gram", "mole_bench_gram", "mole_bench_dmma_peak", "mole_dmc_block_select", "mole_rebalance", "mole_rebalance_plan",
+    "mole_gram_device_ptr", "mole_gram_select", "mole_gram_finalize", "mole_opt_step_gram", "mole_opt_sr_matrix_gram", "mole_bench_gram", "mole_bench_dmma_peak", "mole_dmc_block_select", "mole_dmc_island_imbalance", "mole_rebalance", "mole_rebalance_plan",
 ]
 
 _lib = None

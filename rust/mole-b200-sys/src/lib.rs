@@ -123,6 +123,7 @@ extern "C" {
     pub fn mole_opt_sr_matrix_gram(opt: *mut mole_opt_s, n_cols: i32, gram: *const f64, s: *mut f64) -> i32;
     pub fn mole_dmc_block_select(ens: *mut mole_ens_s, impl_: i32) -> i32;
     pub fn mole_rebalance(ens: *mut mole_ens_s) -> i32;
+    pub fn mole_dmc_island_imbalance(ens: *mut mole_ens_s, ratio: *mut f64) -> i32;
     pub fn mole_rebalance_plan(nranks: i32, totals: *const f64, counts: *const i64, u: f64, shares: *mut i64, moves: *mut i64) -> i32;
     pub fn mole_bench_gram(ctx: *mut mole_ctx_s, n_walkers: i64, n_samples: i64, cols: i32, impl_: i32, reps: i32, ms: *mut f64, checksum: *mut f64) -> i32;
     pub fn mole_bench_dmma_peak(ctx: *mut mole_ctx_s, chains: i32, warps_per_sm: i32, tflops: *mut f64) -> i32;

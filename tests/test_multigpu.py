@@ -82,6 +82,19 @@ def _rank(rank, world, uid, W_local, out):
     res["reb_cfgs"] = r.get_configs()
     res["reb_weights"] = r.get_weights()
     del r
+    # ---- island imbalance after a block, and the rebalancing mole_dmc_diffuse triggers on it
+    i1 = a.island_imbalance()
+    a.set_weights(np.full(W_local, 1.0 + 2.0 * rank))
+    a.dmc_block(dwf, dmet, dop, m.ffi.BRANCH_SR, 0.025, -0.5, 1)
+    i2 = a.island_imbalance()
+    a.rebalance()
+    a.dmc_block(dwf, dmet, dop, m.ffi.BRANCH_SR, 0.025, -0.5, 2)
+    res["imbalance"] = (i1, i2, a.island_imbalance())
+    # the driver itself: DmcRunner::diffuse over both ranks, starting from islands that differ 3 : 1 in weight per walker
+    run = m.DmcRunner.new(dwf, W_local, -0.5, dop, dmet, m.SRBrancher.new(), identical_start=False, walker_offset=rank * W_local)
+    run.ensemble.set_weights(np.full(W_local, 1.0 + 2.0 * rank))
+    en, er = run.diffuse(0.025, 60, 10, 1)
+    res["diffuse"] = (en, er, run.ensemble.island_imbalance(), run.ensemble.get_weights())
     # ---- large-P path: sample rows on each shard, Gram matrices summed over NCCL
     lwf, lop = _lsj_setup(m, ctx)
     g = m.Ensemble(W_local // 2, 4, SEED, walker_offset=rank * (W_local // 2), ctx=ctx)
@@ -133,6 +146,16 @@ def test_two_gpu_allreduce_and_dmc_block():
     swe = r0["dmc_rows"][:, 0] + r1["dmc_rows"][:, 0]
     sw = r0["dmc_rows"][:, 1] + r1["dmc_rows"][:, 1]
     assert np.array_equal(r0["dmc_block_energies"], swe / sw)
+    # island weights per walker: equal within 2 % after a block from equal weights, 3 : 1 after the hand-set weights,
+    # equal again after mole_rebalance; both ranks see the same numbers
+    assert r0["imbalance"] == r1["imbalance"]
+    i1, i2, i3 = r0["imbalance"]
+    assert 1.0 <= i1 < 1.03 and 2.8 < i2 < 3.2 and 1.0 <= i3 < 1.03, r0["imbalance"]
+    # DmcRunner::diffuse: the same energies on both ranks, near -0.5 for the STO guide; the 3 : 1 islands were merged
+    # after the first block (equal weights per walker on both ranks at the end)
+    assert np.array_equal(r0["diffuse"][0], r1["diffuse"][0]) and np.array_equal(r0["diffuse"][1], r1["diffuse"][1])
+    assert np.all(np.abs(r0["diffuse"][0] + 0.5) < 0.05) and r0["diffuse"][2] < 1.05
+    assert abs(r0["diffuse"][3][0] / r1["diffuse"][3][0] - 1.0) < 0.05
     # large-P path: every rank holds the same summed Gram matrix = the single-rank contraction over the same global walkers
     assert np.array_equal(r0["gram_total"], r1["gram_total"])
     assert np.allclose(r0["gram_total"], r0["gram_local"] + r1["gram_local"], rtol=1e-14, atol=0)
