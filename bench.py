@@ -464,6 +464,7 @@ def run_dmc(args):
     ens = m.Ensemble(W, 1, DMC_SEED, walker_offset=rank * W, ctx=ctx)
     ens.init_normal(1.0)                                                    # independent starts (dmc.rs:49-58 clones one)
     ens.sweep(wf, met, op, n_sweeps=200, observables=0)                     # untimed: sample |psi|^2 first
+    ens.dmc_block_select(args.dmc_block_impl)
     host_cfgs = torch.empty((W, 1, 3), dtype=torch.float64, pin_memory=True)
     host_cfgs.numpy()[...] = ens.get_configs()
     host_w = torch.ones(W, dtype=torch.float64, pin_memory=True)
@@ -559,6 +560,8 @@ def main():
     ap.add_argument("--sr-step", type=float, default=SR_STEP)
     ap.add_argument("--sr-shift", type=float, default=SR_DIAG[1])
     ap.add_argument("--dmc-steps", type=int, default=400, help="dmc: time steps per block (examples/dmc.rs:192)")
+    ap.add_argument("--dmc-block-impl", type=int, default=0, choices=[0, 1, 2],
+                    help="dmc: 0 = one persistent launch per block where eligible (default), 1 = per-step launches (A/B)")
     ap.add_argument("--dmc-guide", default="sto", choices=["gaussian", "sto"],
                     help="sto: 1s STO alpha=0.9, the guide examples/dmc.rs:157 keeps as its commented alternative (stable); gaussian: "
                          "the example's cusp-less guide, whose E_L -> -inf at the nucleus makes large populations collapse (upstream behaviour)")

@@ -358,7 +358,7 @@ int32_t mole_branch_sources(mole_ens_t ens, int32_t* src);
 /* One block of DmcRunner::diffuse's inner loop (dmc.rs:84-141): n_steps x (time step, ensemble energy
  * sum w E / sum w over ALL ranks, branch).  With SRBrancher the block is enqueued without host reads
  * (the reference energy is constant within a block, dmc.rs:143-145).  Thread-per-walker kinds whose population
- * fits a co-resident grid (<= 128 walkers x 16 CTAs per SM) run the whole block as ONE cooperative launch, the
+ * fits a co-resident grid at one walker per thread run the whole block as ONE cooperative launch, the
  * three phases of a step (time step + reduction, weight scan, pick + gather) separated by two grid barriers; other
  * cases enqueue 3 launches per time step.  Either way the branching normalisation is formed on the device and the
  * per-step {sum w E, sum w} rows come back with one copy, and the results are bit-identical.  Multi-rank: every rank is a population island (SRBrancher resamples against the rank's own N, w_max
@@ -367,7 +367,9 @@ int32_t mole_branch_sources(mole_ens_t ens, int32_t* src);
  * n_steps x (mole_dmc_step, mole_branch). */
 int32_t mole_dmc_block(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind,
                        double time_step, double reference_energy, int32_t n_steps, double* step_energies);
-/* impl 0 (default): one persistent launch per block where eligible; 1: always per-step launches (A/B, tests) */
+/* impl 0 (default): one persistent launch per block when the population fits the co-resident grid at one walker per
+ * thread (about 75 000 one-electron walkers on 148 SMs; faster there, slower beyond), per-step launches otherwise;
+ * 1: always per-step launches; 2: the persistent launch for every population it can serve (tests, A/B) */
 int32_t mole_dmc_block_select(mole_ens_t ens, int32_t impl);
 /* DmcRunner::diffuse (dmc.rs:69-153): returns n_out running energies and errors */
 int32_t mole_dmc_diffuse(mole_ens_t ens, mole_wf_t wf, mole_metrop_t m, mole_op_t op, int32_t branch_kind,

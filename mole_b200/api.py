@@ -709,7 +709,8 @@ class Ensemble:
         self._c(lib().mole_gram_allreduce(self.handle))
 
     def dmc_block_select(self, impl):
-        """0: one persistent cooperative launch per DMC block where eligible (default); 1: per-step launches."""
+        """0: one persistent cooperative launch per DMC block when the population fits one walker per resident thread
+        (default); 1: per-step launches; 2: the persistent launch for every population it can serve."""
         self._c(lib().mole_dmc_block_select(self.handle, C.c_int32(impl)))
 
     def gram_select(self, impl):

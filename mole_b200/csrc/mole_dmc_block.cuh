@@ -21,6 +21,11 @@
 //   first fused version (1024-walker scan tiles, 4-ary search: 6-7 dependent L2 round trips per pick)
 //                                             2 500    1 650    3 950    2 030    8 100   18 400
 //   this version                              2 410    1 790    2 130    2 090    5 240   14 000
+// Population dependence (us per time step, this kernel / per-step launches): 4 096 walkers 10.4 / 24.9, 16 384: 11.4 /
+// 24.9, 32 768: 13.7 / 25.0, 65 536: 22.7 / 28.9, 98 304: 43.9 / 31.1, 131 072: 46.6 / 35.6, 262 144: 81.8 / 51.6.  Beyond
+// the co-resident grid (one walker per thread: ~75 000 one-electron walkers on 148 SMs) a CTA walks several virtual
+// blocks per phase, their L2 round trips do not overlap, and the per-step kernels (16 CTAs per SM in flight) win: the
+// default (mole_dmc_block_select 0) uses this kernel only while every CTA owns exactly one virtual block.
 // What is left is ~7 dependent L2 round trips per step (own walker, partial rows, staged sums, prefix line, gather and
 // one per barrier) at ~1.2 us each under this access pattern, plus ~3 us of arithmetic.
 #pragma once

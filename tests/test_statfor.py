@@ -268,7 +268,7 @@ def _dmc_case(mole, name):
                                             ("he", 2000, 6), ("h2p", 1500, 6), ("lcao_h2p", 1500, 6), ("lcao_he", 1200, 6)])
 def test_dmc_block_persistent_launch_is_bit_identical_to_per_step_launches(mole, name, W, n_steps):
     """the whole-block cooperative launch (mole_dmc_block.cuh: three phases, two grid barriers per step, virtual blocks of
-    128 walkers) against the per-step launches selected with mole_dmc_block_select(1): configurations, weights, cached
+    128 walkers) (mole_dmc_block_select(2)) against the per-step launches (select(1)): configurations, weights, cached
     local energies (through the next block), branching sources, step energies and launch counts.  100 003 walkers need
     more virtual blocks than one co-resident grid holds; 300 000 is the largest population class served by the
     persistent launch (2368 partial rows)."""
@@ -276,7 +276,7 @@ def test_dmc_block_persistent_launch_is_bit_identical_to_per_step_launches(mole,
     wf, op, ne, eref = _dmc_case(mole, name)
     met = mole.MetropolisDiffuse.from_rng(0.02, seed)
     ens = []
-    for impl in (0, 1):
+    for impl in (2, 1):                                      # 2: the persistent launch whatever the population
         e = mole.Ensemble(W, ne, seed)
         e.init_normal(0.8)
         e.dmc_block_select(impl)
@@ -298,3 +298,9 @@ def test_dmc_block_persistent_launch_is_bit_identical_to_per_step_launches(mole,
     eb2 = b.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.02, eref, 3)
     assert np.array_equal(ea2, eb2) and np.array_equal(a.get_configs(), b.get_configs())
     assert a.health() == b.health()
+    # the default picks the persistent launch only while one virtual block per CTA fits the co-resident grid
+    c = mole.Ensemble(W, ne, seed)
+    c.init_normal(0.8)
+    n3 = ctx.launch_count()
+    ec = c.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.02, eref, n_steps)
+    assert ctx.launch_count() - n3 == (1 if W <= 40000 else 3 * n_steps) and np.array_equal(ec, eb)
