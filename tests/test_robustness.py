@@ -188,3 +188,10 @@ def test_rebalance_on_one_rank_is_the_identity_after_equalising_weights(mole):
     assert np.all(got == got[0]) and abs(got[0] - w.mean()) < 1e-12
     src = ens.branch_sources()
     assert np.array_equal(ens.get_configs()[:, 0, :], x0[src, 0, :])
+    # one rank = one island: the imbalance the DMC drivers test between blocks is 1, before and after a block
+    assert ens.island_imbalance() == 1.0
+    met = mole.MetropolisDiffuse.from_rng(0.025, SEED0)
+    ens.dmc_block(wf, met, op, mole.ffi.BRANCH_SR, 0.025, -0.5, 4)
+    assert ens.island_imbalance() == 1.0
+    with pytest.raises(mole.MoleError):
+        ens.dmc_block_select(3)
