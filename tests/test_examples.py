@@ -46,3 +46,10 @@ def test_lcao_example():
     e1 = float(out.split("H2+ LCAO   Energy:")[1].split()[0])
     e2 = float(out.split("He LCAO    Energy:")[1].split()[0])
     assert abs(e1 + 0.5648) < 2e-3 and abs(e2 + 2.8477) < 1e-2      # closed forms: LCAO integrals at R = 2.5; alpha^2 - 27 alpha / 8
+
+
+def test_lcao_chain_example_large_p():
+    out = _run("lcao_chain.py", "--walkers", "2048", "--iterations", "6")
+    assert "P = 36 variational parameters" in out and out.count("Energy:") == 6
+    e = [float(l.split()[1]) for l in out.splitlines() if l.startswith("Energy:")]
+    assert e[-1] < e[0] and "non-finite samples skipped: 0" in out
